@@ -1,0 +1,45 @@
+// gemm.h — host-side contract shared by the tcgen05 GEMM (bf16 operands, production) and the SIMT fp32
+// GEMM (check mode). One descriptor covers the three contractions of a linear layer:
+//   forward  Y[M,N]  = X[M,K]  · W[N,K]^T          a_mn=0, b_mn=0   (reference: nn.Linear, upstream BertSelfAttention
+//                                                                    twin Downstream_task/report_generation_and_vqa/sc/
+//                                                                    pytorch_pretrained_bert/model.py:273-298)
+//   dgrad    dX[M,K] = dY[M,N] · W[N,K]            a_mn=0, b_mn=1   (W read in place: its K_in axis is contiguous)
+//   wgrad    dW[N,K] = dY[M,N]^T · X[M,K]          a_mn=1, b_mn=1   (both activations read in place, fp32 reduce-add)
+#pragma once
+#include "common.cuh"
+
+namespace mv {
+
+enum Epilogue : int {
+  EPI_NONE = 0,        // C = acc
+  EPI_BIAS = 1,        // C = acc + bias[n]
+  EPI_BIAS_GELU = 2,   // C2 = acc + bias (pre-activation, optional); C = gelu_erf(C2)
+  EPI_BIAS_RESID = 3,  // C = dropout(acc + bias) + resid[m,n]
+  EPI_BIAS_TANH = 4,   // C = tanh(acc + bias)
+  EPI_RESID = 5,       // C = acc + resid[m,n]
+  EPI_DGELU = 6,       // C = acc * gelu_erf'(aux[m,n])
+};
+
+struct GemmDesc {
+  int M = 0, N = 0, K = 0;
+  const void* A = nullptr; long lda = 0; int a_mn = 0;  // a_mn=0: [M,K] rows; a_mn=1: stored [K,M] rows
+  const void* B = nullptr; long ldb = 0; int b_mn = 0;  // b_mn=0: [N,K] rows; b_mn=1: stored [K,N] rows
+  void* C = nullptr; long ldc = 0; int c_f32 = 0;       // output dtype: activation dtype, or fp32
+  int accumulate = 0;                                   // fp32 outputs only: C += result (split-K reduce-add)
+  void* C2 = nullptr; long ldc2 = 0;                    // optional pre-activation output (activation dtype)
+  int epi = EPI_NONE;
+  const float* bias = nullptr;                          // [N] fp32 (master parameter, never shadowed)
+  const void* resid = nullptr; long ldr = 0;            // [M,N] activation dtype
+  const void* aux = nullptr; long ldaux = 0;            // [M,N] activation dtype
+  int drop_on = 0; uint32_t drop_site = 0; DropoutCfg drop = {0.f, 0u, 1.f, 0ull};
+  int splitk = 0;                                       // 0 = auto (only used when accumulate=1)
+};
+
+// bf16 operands / fp32 accumulate in TMEM / bf16 or fp32 output. sm_100a only.
+int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream);
+// fp32 operands, CUDA-core FMA (check mode, 1e-4 parity gate).
+int gemm_f32_simt(const GemmDesc& d, cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace mv

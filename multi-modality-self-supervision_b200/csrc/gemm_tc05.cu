@@ -1,0 +1,443 @@
+// gemm_tc05.cu — persistent, warp-specialised bf16 GEMM for sm_100a:
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma (cta_group::1, 128 x BN x 16,
+//   fp32 accumulators double-buffered in TMEM) -> tcgen05.ld epilogue (bias / GELU / residual+dropout / tanh /
+//   GELU-backward) -> swizzled smem staging -> TMA store (or TMA fp32 reduce-add for split-K weight gradients).
+//
+// Replaces, for the MedViLL pre-training step, every nn.Linear contraction the reference runs through cuBLAS
+// (SURVEY.md §2b K1,K4-K6,K8-K11,K13): Q/K/V, attention-output, FFN, image projection, pooler, MLM transform and
+// decoder, in forward / dgrad / wgrad form (see gemm.h for the three operand-major combinations).
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue (TMEM lane
+// quarter = warp_id % 4). Grid = min(#SMs, work units); unit = (m_tile, n_tile, k_split), m fastest so that CTAs
+// running concurrently share the weight tile through L2.
+#include "gemm.h"
+#include "tc05.cuh"
+#include "tmap.h"
+
+namespace mv {
+using namespace tc05;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t STG_BYTES = 4096;  // one staging buffer: 32 rows x 128 B (swizzled)
+constexpr uint32_t STG_TOTAL = 4 /*warps*/ * 2 /*outputs*/ * 2 /*double buffer*/ * STG_BYTES;
+
+struct GemmParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_total, kb_per_split, stages;
+  int epi;
+  const float* bias;
+  const bf16* resid; long ldr;
+  const bf16* aux; long ldaux;
+  int has_c2, accumulate;
+  int drop_on; uint32_t drop_site; DropoutCfg drop;
+};
+
+struct Barriers {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void load_row32(const bf16* base, long ld, int row, int col, bool ok, float (&out)[32]) {
+  if (ok) {
+    const uint4* p = reinterpret_cast<const uint4*>(base + static_cast<long>(row) * ld + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 u = __ldg(p + j);
+      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+      out[8 * j + 0] = a.x; out[8 * j + 1] = a.y; out[8 * j + 2] = b.x; out[8 * j + 3] = b.y;
+      out[8 * j + 4] = c.x; out[8 * j + 5] = c.y; out[8 * j + 6] = d.x; out[8 * j + 7] = d.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) out[j] = 0.f;
+  }
+}
+
+// Epilogue math on 32 consecutive columns [col0, col0+32) of output row `row`.
+// f: accumulators in, final values out; pre: pre-activation (only written for EPI_BIAS_GELU).
+__device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[32], float (&pre)[32], int row, int col0,
+                                               bool row_ok) {
+  const int epi = p.epi;
+  if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int c = col0 + j;
+      f[j] += (c < p.N) ? __ldg(p.bias + c) : 0.f;
+    }
+  }
+  if (epi == EPI_BIAS_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { pre[j] = f[j]; f[j] = gelu_erf(f[j]); }
+  } else if (epi == EPI_BIAS_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+  } else if (epi == EPI_BIAS_RESID || epi == EPI_RESID) {
+    if (p.drop_on && epi == EPI_BIAS_RESID) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N) + col0 + 8 * g) >> 3;
+        const uint32_t keep = dropout_keep8(p.drop, p.drop_site, grp);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[8 * g + j] = ((keep >> j) & 1u) ? f[8 * g + j] * p.drop.scale : 0.f;
+      }
+    }
+    float r[32];
+    load_row32(p.resid, p.ldr, row, col0, row_ok && col0 < p.N, r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += r[j];
+  } else if (epi == EPI_DGELU) {
+    float a[32];
+    load_row32(p.aux, p.ldaux, row, col0, row_ok && col0 < p.N, a);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
+  }
+}
+
+// write 32 fp32 values as bf16 into half `half` (0/1) of a [32 rows x 64 cols] swizzled staging tile
+__device__ __forceinline__ void stage_bf16_half(uint8_t* stg, int lane, int half, const float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+    u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+    u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+    u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+    *reinterpret_cast<uint4*>(stg + sw128_off(lane, half * 4 + j)) = u;
+  }
+}
+// write 32 fp32 values into a [32 rows x 32 cols] fp32 swizzled staging tile
+__device__ __forceinline__ void stage_f32(uint8_t* stg, int lane, const float (&f)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    *reinterpret_cast<float4*>(stg + sw128_off(lane, j)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                 const GemmParams p) {
+  constexpr uint32_t A_BYTES = BM * BK * 2;
+  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (BN <= 128) ? 256u : 512u;
+  constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128u : 256u;
+  constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
+  constexpr int NCHUNK = BN / CHUNK_COLS;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* stg_base = smem + static_cast<uint32_t>(p.stages) * STAGE_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(stg_base + STG_TOTAL);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (p.has_c2) tma_prefetch_desc(&tmC2);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&bars->tfull[a], 1);
+      mbar_init(&bars->tempty[a], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int total_units = tiles * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int split = unit % p.splits;
+        const int tile = unit / p.splits;
+        const int m0 = (tile % p.m_tiles) * BM;
+        const int n0 = (tile / p.m_tiles) * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
+          uint8_t* sA = smem + static_cast<uint32_t>(stage) * STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d(&tmA, &bars->full[stage], sA, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g) tma_load_2d(&tmA, &bars->full[stage], sA + g * 8192, m0 + g * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(&tmB, &bars->full[stage], sB, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) tma_load_2d(&tmB, &bars->full[stage], sB + g * 8192, n0 + g * 64, kb * BK);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int split = unit % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + static_cast<uint32_t>(stage) * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: 16 bf16 along K = +32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
+            // MN-major: 16 K rows = +2048 B; 64-element MN groups 8192 B apart, 8-row K groups 1024 B apart.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint8_t* my_stg = stg_base + static_cast<uint32_t>(q) * (4 * STG_BYTES);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int tile = unit / p.splits;
+      const int m0 = (tile % p.m_tiles) * BM;
+      const int n0 = (tile / p.m_tiles) * BN;
+      mbar_wait(&bars->tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c) {
+        if (lane == 0) tma_wait_group_read<1>();  // staging buffer `buf` (used two chunks ago) is free again
+        __syncwarp();
+        uint8_t* s1 = my_stg + static_cast<uint32_t>(buf) * STG_BYTES;
+        uint8_t* s2 = my_stg + static_cast<uint32_t>(2 + buf) * STG_BYTES;
+        if constexpr (!OUT_F32) {
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(t_row + static_cast<uint32_t>(c * 64 + half * 32), v);
+            tmem_ld_wait();
+            float f[32], pre[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            epilogue_apply(p, f, pre, row, n0 + c * 64 + half * 32, row_ok);
+            stage_bf16_half(s1, lane, half, f);
+            if (p.has_c2) stage_bf16_half(s2, lane, half, pre);
+          }
+        } else {
+          uint32_t v[32];
+          tmem_ld32(t_row + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          float f[32], pre[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          epilogue_apply(p, f, pre, row, n0 + c * 32, row_ok);
+          stage_f32(s1, lane, f);
+        }
+        if (c == NCHUNK - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int r0 = m0 + q * 32;
+          const int c0 = n0 + c * CHUNK_COLS;
+          if (r0 < p.M && c0 < p.N) {
+            if (p.accumulate) tma_reduce_add_2d(&tmC, s1, c0, r0);
+            else tma_store_2d(&tmC, s1, c0, r0);
+            if (p.has_c2) tma_store_2d(&tmC2, s2, c0, r0);
+          }
+          tma_commit_group();
+        }
+        buf ^= 1;
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) tma_wait_group<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN>
+constexpr uint32_t stage_bytes() { return BM * BK * 2 + BN * BK * 2; }
+
+inline int pick_stages(uint32_t stage_b) {
+  const uint32_t budget = 232448u - 1024u - STG_TOTAL - static_cast<uint32_t>(sizeof(Barriers)) - 64u;
+  int s = static_cast<int>(budget / stage_b);
+  if (s > kMaxStages) s = kMaxStages;
+  return s;
+}
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
+  CUtensorMap tmA, tmB, tmC, tmC2;
+  int rc;
+  if (!d.a_mn) rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.K, d.M, d.lda * 2, BK, BM);
+  else rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.M, d.K, d.lda * 2, 64, BK);
+  if (rc) return rc;
+  if (!d.b_mn) rc = tmap_encode_2d(&tmB, TMAP_BF16, d.B, d.K, d.N, d.ldb * 2, BK, BN);
+  else rc = tmap_encode_2d(&tmB, TMAP_BF16, d.B, d.N, d.K, d.ldb * 2, 64, BK);
+  if (rc) return rc;
+  if (OUT_F32) rc = tmap_encode_2d(&tmC, TMAP_F32, d.C, d.N, d.M, d.ldc * 4, 32, 32);
+  else rc = tmap_encode_2d(&tmC, TMAP_BF16, d.C, d.N, d.M, d.ldc * 2, 64, 32);
+  if (rc) return rc;
+  if (d.C2) {
+    rc = tmap_encode_2d(&tmC2, TMAP_BF16, d.C2, d.N, d.M, d.ldc2 * 2, 64, 32);
+    if (rc) return rc;
+  } else {
+    tmC2 = tmC;
+  }
+  p.n_tiles = (d.N + BN - 1) / BN;
+  p.stages = pick_stages(stage_bytes<BN>());
+  // split-K only for fp32 reduce-add outputs (weight gradients): fill ~2 waves of SMs
+  const int sms = device_sm_count();
+  const int tiles = p.m_tiles * p.n_tiles;
+  int splits = 1;
+  if (d.accumulate) {
+    splits = d.splitk > 0 ? d.splitk : (2 * sms) / tiles;
+    if (splits < 1) splits = 1;
+    const int max_splits = (p.kb_total + 7) / 8;  // keep >= 8 k-blocks per unit
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  const int units = tiles * p.splits;
+  const int grid = units < sms ? units : sms;
+  const uint32_t smem = 1024u + static_cast<uint32_t>(p.stages) * stage_bytes<BN>() + STG_TOTAL + sizeof(Barriers) + 64u;
+  auto kern = gemm_tc05_kernel<BN, A_MN, B_MN, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmC2, p);
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+int dispatch_major(const GemmDesc& d, const GemmParams& p, cudaStream_t s) {
+  if (!d.a_mn && !d.b_mn) return d.c_f32 ? launch<BN, false, false, true>(d, p, s) : launch<BN, false, false, false>(d, p, s);
+  if (!d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, false, true, true>(d, p, s) : launch<BN, false, true, false>(d, p, s);
+  if (d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, true, true, true>(d, p, s) : launch<BN, true, true, false>(d, p, s);
+  set_error("gemm_bf16_tc05: operand-major combination a_mn=1,b_mn=0 is not instantiated");
+  return -1;
+}
+
+// pick the N tile that minimises (waves x per-tile cost) on this GPU
+int pick_bn(int m_tiles, int N, int sms, bool accumulate) {
+  const int cands[3] = {192, 256, 128};
+  int best = 192;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
+    const long waves = accumulate ? 1 : (tiles + sms - 1) / sms;
+    const double per_tile = bn + 24.0;  // MMA time ~ BN, plus fixed prologue/epilogue overhead
+    const double wasted = static_cast<double>(((N + bn - 1) / bn) * bn) / N;
+    const double cost = accumulate ? wasted * per_tile / bn : waves * per_tile;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
+  MV_REQUIRE(d.M > 0 && d.N > 0 && d.K > 0, "gemm: empty problem M=%d N=%d K=%d", d.M, d.N, d.K);
+  MV_REQUIRE(d.A && d.B && d.C, "gemm: null operand");
+  MV_REQUIRE(!d.accumulate || d.c_f32, "gemm: accumulate requires fp32 output");
+  MV_REQUIRE(!(d.C2 && d.c_f32), "gemm: pre-activation output only with activation-dtype C");
+  if (d.epi == EPI_BIAS || d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_RESID || d.epi == EPI_BIAS_TANH)
+    MV_REQUIRE(d.bias != nullptr, "gemm: epilogue %d needs bias", d.epi);
+  if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID)
+    MV_REQUIRE(d.resid != nullptr && d.N % 32 == 0 && d.ldr % 8 == 0, "gemm: residual epilogue needs resid, N%%32==0");
+  if (d.epi == EPI_DGELU)
+    MV_REQUIRE(d.aux != nullptr && d.N % 32 == 0 && d.ldaux % 8 == 0, "gemm: DGELU epilogue needs aux, N%%32==0");
+  GemmParams p;
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.m_tiles = (d.M + BM - 1) / BM;
+  p.n_tiles = 0;
+  p.kb_total = (d.K + BK - 1) / BK;
+  p.splits = 1; p.kb_per_split = p.kb_total; p.stages = 0;
+  p.epi = d.epi;
+  p.bias = d.bias;
+  p.resid = static_cast<const bf16*>(d.resid); p.ldr = d.ldr;
+  p.aux = static_cast<const bf16*>(d.aux); p.ldaux = d.ldaux;
+  p.has_c2 = d.C2 != nullptr; p.accumulate = d.accumulate;
+  p.drop_on = d.drop_on; p.drop_site = d.drop_site; p.drop = d.drop;
+  const int bn = pick_bn(p.m_tiles, d.N, device_sm_count(), d.accumulate != 0);
+  switch (bn) {
+    case 128: return dispatch_major<128>(d, p, stream);
+    case 256: return dispatch_major<256>(d, p, stream);
+    default: return dispatch_major<192>(d, p, stream);
+  }
+}
+
+}  // namespace mv
