@@ -451,8 +451,11 @@ def joint_embeddings(params, batch, cfg, feats=None, keep=None):
     ids, seg = torch.as_tensor(batch["input_ids"]), torch.as_tensor(batch["segment"])
     ridx = torch.as_tensor(batch["region_idx"])
     B, T = ids.shape
-    cls_out = ln(W[cls_tok] + P[:1][None] + Ty[0][None, None])               # :118 (position restarts at 0)
-    sep_out = ln(W[sep_tok] + P[:1][None] + Ty[0][None, None])               # :119
+    # upstream BertEmbeddings.word_embeddings = nn.Embedding(V, H, padding_idx=pad_token_id=0): the LOOKUP gradient of
+    # id 0 ([PAD]) is dropped (the tied MLM-decoder gradient of row 0 is kept) — pinned by make_golden.py.
+    emb = lambda i: F.embedding(i, W, padding_idx=PAD)
+    cls_out = ln(emb(cls_tok) + P[:1][None] + Ty[0][None, None])             # :118 (position restarts at 0)
+    sep_out = ln(emb(sep_tok) + P[:1][None] + Ty[0][None, None])             # :119
     if feats is None:
         fmap = resnet50_trunk(params, batch["image"])                        # image.py:56
         feats = torch.flatten(fmap, start_dim=2).transpose(1, 2).contiguous()  # image.py:57-58  [B, grid, 2048]
@@ -461,7 +464,7 @@ def joint_embeddings(params, batch, cfg, feats=None, keep=None):
     sampled = feats[:, ridx]                                                 # image.py:67
     img = sampled @ params["enc.img_embeddings.img_embeddings.weight"].t() + params["enc.img_embeddings.img_embeddings.bias"]
     img_out = ln(img + P[ridx][None] + Ty[0][None, None])                    # cxrbert_origin.py:24-33
-    txt_out = ln(W[ids] + P[:T][None] + Ty[seg])                             # :124
+    txt_out = ln(emb(ids) + P[:T][None] + Ty[seg])                           # :124
     return torch.cat([cls_out, img_out, sep_out, txt_out], 1)                # :125
 
 
@@ -511,7 +514,7 @@ def loss_and_grads(params, batch, cfg, feats=None, keep=None):
     mlm_l, itm_l, loss = losses(logits, itm, batch)
     loss.backward()
     grads = {n: (leaf[n].grad if leaf[n].grad is not None else torch.zeros_like(leaf[n])) for n in names}
-    return dict(loss=float(loss), mlm_loss=float(mlm_l), itm_loss=float(itm_l), logits=logits.detach(),
+    return dict(loss=loss.item(), mlm_loss=mlm_l.item(), itm_loss=itm_l.item(), logits=logits.detach(),
                 itm_logits=itm.detach(), grads=grads)
 
 
