@@ -1,0 +1,158 @@
+/* medvill_sm100.h — C ABI of libmedvill_sm100.so: the B200-native (sm_100a) implementation of the MedViLL joint
+ * vision-language PRE-TRAINING STEP.  Plain pointers and sizes only; no torch types.  Every entry returns 0 on success
+ * or a negative status (message: mv_last_error()); nothing throws or exits.  All device pointers are caller-owned
+ * (PyTorch-allocated) and only borrowed while the enqueued work runs; the handle owns workspaces, TMA descriptors,
+ * events and the NCCL communicator.  Work is enqueued on the cudaStream_t passed as `stream` (void* here so the
+ * header needs no CUDA include).  There is no CPU fallback: without an sm_100 GPU every compute entry fails loudly.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   mv_forward / mv_backward        CXRBERT.forward + loss.backward()   models/cxrbert_origin.py:144-149,
+ *                                   CXRBertEncoder.forward :87-130, ImageBertEmbeddings.forward :22-35,
+ *                                   BertPreTrainingHeads :205-248, ImageTextMatching :164-173,
+ *                                   losses models/train_origin.py:62-63,118-126, metrics :133-146
+ *   mv_adamw_step                   transformers AdamW.step (upstream)  models/train_origin.py:60,129-131
+ *   mv_comm_* / bucketed all-reduce nn.DataParallel gradient reduction  models/train_origin.py:53-55
+ *   mv_attn_mask_dump / classify    CXRDataset mask construction        data/dataset_origin.py:138-176
+ *                                   get_extended_attn_mask              models/cxrbert_origin.py:75-85
+ *   mv_full_logits                  prediction_scores [B,L,V] of CXRBERT.forward (drop-in output)
+ *   mv_gemm / mv_attention_* / mv_layernorm_* / mv_mlm_ce             per-op entry points used by the parity tests
+ */
+#ifndef MEDVILL_SM100_H_
+#define MEDVILL_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MV_ABI_VERSION 1
+
+enum { MV_PREC_BF16 = 0, MV_PREC_FP32 = 1 };          /* activation / GEMM-operand precision policy */
+enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3 };   /* attention-mask modes */
+enum {                                                 /* GEMM epilogues (mv_gemm) */
+  MV_EPI_NONE = 0, MV_EPI_BIAS = 1, MV_EPI_BIAS_GELU = 2, MV_EPI_BIAS_RESID = 3, MV_EPI_BIAS_TANH = 4,
+  MV_EPI_RESID = 5, MV_EPI_DGELU = 6
+};
+
+typedef struct mv_handle mv_handle;
+
+typedef struct mv_config {
+  int32_t hidden, heads, layers, inter, vocab, max_pos, type_vocab;  /* BertConfig (head dim must be 64)            */
+  int32_t num_image_embeds;   /* N: sampled regions            main_origin.py:137                                  */
+  int32_t seq_len;            /* S: text tokens                main_origin.py:130  (T = S+1, L = N + S + 3)        */
+  int32_t img_hidden;         /* 2048                          main_origin.py:133                                  */
+  int32_t grid;               /* ResNet regions per image: (img_size/32)^2                                         */
+  int32_t max_batch;          /* per-micro-batch sample capacity (workspaces are sized for it)                     */
+  int32_t precision;          /* MV_PREC_*                                                                         */
+  float ln_eps;               /* encoder / embedding LayerNorm eps (1e-12)                                         */
+  float head_ln_eps;          /* MLM-head TF-style LayerNorm eps (1e-5)  models/cxrbert_origin.py:212              */
+  float dropout_p;            /* hidden / attention-prob / embedding dropout (reference default 0.1)               */
+} mv_config;
+
+/* Offsets (in elements) of every trainable tensor inside the flat parameter arena.  The fp32 master parameters,
+ * their gradients, both Adam moments and the bf16 shadow all use this one layout, so the torch nn.Parameters of the
+ * drop-in modules are views into the arena and gradient buckets are contiguous ranges.  Per-layer offsets are
+ * relative to layer0 + l * layer_stride. */
+typedef struct mv_layout {
+  int64_t total;
+  int64_t word, pos, type, emb_ln_g, emb_ln_b, img_w, img_b;
+  int64_t layer0, layer_stride;
+  int64_t l_wqkv, l_bqkv, l_wo, l_bo, l_ln1_g, l_ln1_b, l_w1, l_b1, l_w2, l_b2, l_ln2_g, l_ln2_b;
+  int64_t pool_w, pool_b, mlm_bias, mlm_tw, mlm_tb, mlm_ln_g, mlm_ln_b, itm_w, itm_b;
+  int64_t vocab_padded;       /* row stride of logits buffers (vocab rounded up to 64)                              */
+} mv_layout;
+
+typedef struct mv_batch {
+  int32_t B;                   /* samples in this micro-batch (<= max_batch)                                        */
+  const int64_t* cls_tok;      /* [B]      device                                                                   */
+  const int64_t* sep_tok;      /* [B]                                                                               */
+  const int64_t* input_ids;    /* [B, T]                                                                            */
+  const int64_t* segment;      /* [B, T]                                                                            */
+  const int64_t* is_aligned;   /* [B]      ITM labels                                                               */
+  const int64_t* region_idx;   /* [N]      sorted sampled grid positions (models/image.py:64-69)                    */
+  const uint8_t* mode;         /* [B]      MV_MODE_* per sample (the Mixed mode draws per sample)                   */
+  const int32_t* t_len;        /* [B]      real text length incl. [SEP]                                             */
+  const void* feats;           /* [B, grid, img_hidden] activation dtype: ResNet-50 grid features, channels-last    */
+  int32_t n_lab;               /* number of labelled (MLM) positions in this micro-batch                            */
+  const int64_t* lab_rows;     /* [n_lab]  flattened b * L + s of every position with txt_labels != -100            */
+  const int64_t* lab_labels;   /* [n_lab]  the labels at those positions                                            */
+  float inv_n_lab_global;      /* 1 / #labelled tokens of the GLOBAL batch (all ranks, all micro-batches)           */
+  float inv_batch_global;      /* 1 / GLOBAL batch size                                                             */
+  uint64_t dropout_seed;       /* per-step seed of the counter-based dropout RNG                                    */
+  int32_t train;               /* 1: dropout active (if dropout_p > 0) and backward state is kept                   */
+} mv_batch;
+
+typedef struct mv_step_stats {
+  float mlm_loss_sum;          /* sum over labelled tokens of the token CE  (mean = sum * inv_n_lab)                */
+  float itm_loss_sum;          /* sum over samples of the ITM CE                                                    */
+  int32_t mlm_correct, itm_correct;   /* models/train_origin.py:133-146                                             */
+} mv_step_stats;
+
+typedef struct mv_gemm_desc {
+  int32_t M, N, K;
+  const void* A; int64_t lda; int32_t a_mn;   /* a_mn = 0: A is [M,K] row-major; 1: stored [K,M]                    */
+  const void* B; int64_t ldb; int32_t b_mn;   /* b_mn = 0: B is [N,K] row-major (nn.Linear weight); 1: stored [K,N] */
+  void* C; int64_t ldc; int32_t c_f32; int32_t accumulate;
+  void* C2; int64_t ldc2;
+  int32_t epi;
+  const float* bias;
+  const void* resid; int64_t ldr;
+  const void* aux; int64_t ldaux;
+  float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+} mv_gemm_desc;
+
+const char* mv_last_error(void);
+int mv_abi_version(void);
+
+/* ---- lifecycle ---- */
+int mv_layout_query(const mv_config* cfg, mv_layout* out);               /* host only, no GPU needed                */
+int mv_bucket_plan(const mv_config* cfg, int64_t* offsets, int64_t* counts, int32_t max_buckets, int32_t* n_buckets);
+int mv_create(mv_handle** out, const mv_config* cfg);
+int mv_destroy(mv_handle* h);
+int mv_bind_arenas(mv_handle* h, float* params, float* grads, float* adam_m, float* adam_v, void* shadow_bf16);
+int mv_refresh_shadow(mv_handle* h, void* stream);                       /* bf16 shadow <- fp32 master              */
+
+/* ---- the pre-training step ---- */
+int mv_stats_reset(mv_handle* h, void* stream);
+int mv_forward(mv_handle* h, const mv_batch* b, void* stream);           /* fwd + both losses + metrics             */
+int mv_backward(mv_handle* h, const mv_batch* b, int32_t allreduce, void* stream);  /* grads += ; optional bucketed */
+                                                                         /* NCCL all-reduce overlapped with bwd     */
+int mv_zero_grads(mv_handle* h, void* stream);
+int mv_adamw_step(mv_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                  float grad_scale, void* stream);                       /* waits for pending all-reduces; zeroes g */
+int mv_read_stats(mv_handle* h, mv_step_stats* host_out, void* stream);  /* D2H + stream sync                       */
+int mv_itm_logits(mv_handle* h, float* host_out, int32_t B, void* stream);
+int mv_full_logits(mv_handle* h, const mv_batch* b, float* logits, int64_t ld, void* stream);  /* [B*L, ld] fp32    */
+int mv_peek(mv_handle* h, const char* name, int32_t layer, void* dst, int64_t max_bytes, int64_t* bytes, void* stream);
+
+/* ---- data-parallel gradient exchange (one process per GPU) ---- */
+int mv_comm_unique_id(uint8_t out[128]);
+int mv_comm_init(mv_handle* h, const uint8_t id[128], int32_t rank, int32_t world);
+int mv_comm_allreduce_f32(mv_handle* h, float* buf, int64_t count, void* stream);   /* scalars (label counts)       */
+int mv_comm_sync(mv_handle* h, void* stream);
+
+/* ---- per-op entry points (parity tests, integration of single kernels) ---- */
+int mv_gemm(const mv_gemm_desc* d, int32_t precision, void* stream);
+int mv_attn_mask_dump(const uint8_t* mode, const int32_t* t_len, int32_t B, int32_t A, int32_t L, uint8_t* out, void* stream);
+int mv_mask_classify(const int64_t* mask, int32_t dims, int32_t B, int32_t A, int32_t L, uint8_t* mode, int32_t* t_len,
+                     int32_t* mismatches, void* stream);
+int mv_attention_fwd(int32_t B, int32_t L, int32_t heads, int32_t A, const uint8_t* mode, const int32_t* t_len,
+                     const void* qkv, void* ctx, float* lse, float dropout_p, uint64_t seed, uint32_t site,
+                     int32_t precision, void* stream);
+int mv_attention_bwd(int32_t B, int32_t L, int32_t heads, int32_t A, const uint8_t* mode, const int32_t* t_len,
+                     const void* qkv, const void* ctx, const float* lse, const void* dctx, void* dqkv, float* dq_acc,
+                     float* delta, float dropout_p, uint64_t seed, uint32_t site, int32_t precision, void* stream);
+int mv_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t H, float eps,
+                     int32_t precision, void* stream);
+int mv_layernorm_bwd(const void* dy, const void* x, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                     int32_t rows, int32_t H, float eps, int32_t precision, void* stream);
+int mv_mlm_ce(const float* logits, int64_t ld, const int64_t* labels, int32_t n, int32_t V, void* dlogits, float gscale,
+              float* loss_sum, int32_t* correct, float* row_lse, int32_t* row_argmax, int32_t precision, void* stream);
+int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
+             float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDVILL_SM100_H_ */

@@ -1,0 +1,497 @@
+// attention_tc05.cu — fused masked attention for sm_100a, forward and backward, head dim 64, bf16 operands.
+//   * Q/K/V tiles arrive by TMA straight out of the packed [B*L, 3H] QKV activation (no head-major transpose);
+//   * S = QK^T, PV, and the five backward products run on tcgen05.mma with fp32 accumulators in TMEM;
+//   * the MedViLL image/text block mask is evaluated from (mode, A, t_len) per element (mask.cuh) — no mask tensor —
+//     and KV / Q tiles that are fully masked for the sample's mode are skipped (exact: the reference's additive
+//     -10000 underflows to 0 after softmax, models/cxrbert_origin.py:82-83);
+//   * probabilities never touch HBM: forward keeps one row per thread (online softmax), backward recomputes P from
+//     the saved row log-sum-exp; attention-probability dropout is regenerated from a counter-based RNG.
+// Reference arithmetic: upstream BertSelfAttention (twin: .../pytorch_pretrained_bert/model.py:301-320).
+#include "attn_common.cuh"
+#include "kernels.h"
+#include "tc05.cuh"
+#include "tmap.h"
+
+namespace mv {
+using namespace tc05;
+
+namespace {
+
+constexpr int D = 64;
+constexpr int TQ = 128, TK = 128;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr uint32_t TILE_BYTES = TQ * D * 2;       // 16 KB: one [128 x 64] bf16 tile
+constexpr uint32_t P_BYTES = TQ * TK * 2;         // 32 KB: [128 x 128] bf16 as two 64-column halves
+
+struct FwdSmem {
+  uint64_t bar_q, bar_k, bar_v, bar_s, bar_o;
+  uint32_t tmem_base;
+};
+
+// P (or dS) row `r`: 32 consecutive columns starting at c32*32 -> bf16 into the swizzled [128 x 128] tile
+__device__ __forceinline__ void store_p32(uint8_t* sP, int r, int c32, const float (&p)[32]) {
+  uint8_t* half = sP + (c32 >> 1) * TILE_BYTES;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16x2(p[8 * j + 0], p[8 * j + 1]);
+    u.y = pack_bf16x2(p[8 * j + 2], p[8 * j + 3]);
+    u.z = pack_bf16x2(p[8 * j + 4], p[8 * j + 5]);
+    u.w = pack_bf16x2(p[8 * j + 6], p[8 * j + 7]);
+    *reinterpret_cast<uint4*>(half + sw128_off(r, (c32 & 1) * 4 + j)) = u;
+  }
+}
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = smem + 2 * TILE_BYTES;
+  uint8_t* sP = smem + 3 * TILE_BYTES;
+  FwdSmem* sh = reinterpret_cast<FwdSmem*>(smem + 3 * TILE_BYTES + P_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int L = a.L, H = a.nh * D, A = a.A;
+  const int mode = a.mode[b], tl = a.t_len[b];
+  const int q_lo = qt * TQ, q_hi = min(q_lo + TQ - 1, L - 1);
+  const int n_kv = (L + TK - 1) / TK;
+  const int row0 = b * L;  // first row of this sample in the [B*L, 3H] matrix
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(&sh->bar_q, 1); mbar_init(&sh->bar_k, 1); mbar_init(&sh->bar_v, 1);
+    mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&sh->tmem_base, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  auto active = [&](int j) { return tile_any_allowed(mode, q_lo, q_hi, j * TK, min(j * TK + TK - 1, L - 1), A, tl); };
+  auto next_active = [&](int j) { ++j; while (j < n_kv && !active(j)) ++j; return j; };
+  int j = next_active(-1);
+
+  if (tid == 0) {
+    mbar_expect_tx(&sh->bar_q, TILE_BYTES);
+    tma_load_2d(&tmQKV, &sh->bar_q, sQ, h * D, row0 + q_lo);
+    if (j < n_kv) {
+      mbar_expect_tx(&sh->bar_k, TILE_BYTES);
+      tma_load_2d(&tmQKV, &sh->bar_k, sK, H + h * D, row0 + j * TK);
+      mbar_expect_tx(&sh->bar_v, TILE_BYTES);
+      tma_load_2d(&tmQKV, &sh->bar_v, sV, 2 * H + h * D, row0 + j * TK);
+    }
+  }
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);
+  constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D, 0, 1);
+  const float scale2 = 0.125f * kLog2e;
+  const int q = q_lo + tid;
+  float o_acc[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  uint32_t it = 0;
+
+  for (; j < n_kv; ++it) {
+    const int jn = next_active(j);
+    const uint32_t ph = it & 1u;
+    const int k_lo = j * TK;
+    if (tid == 0) {
+      if (it == 0) mbar_wait(&sh->bar_q, 0);
+      mbar_wait(&sh->bar_k, ph);
+      tc_fence_after();
+      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit(&sh->bar_s);
+    }
+    mbar_wait(&sh->bar_s, ph);
+    tc_fence_after();
+    if (tid == 0 && jn < n_kv) {  // K buffer is free: prefetch the next active key tile under the softmax
+      mbar_expect_tx(&sh->bar_k, TILE_BYTES);
+      tma_load_2d(&tmQKV, &sh->bar_k, sK, H + h * D, row0 + jn * TK);
+    }
+    const bool full = tile_all_allowed(mode, q_lo, q_hi, k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L);
+    // pass 1: row maximum of the scaled, masked scores
+    float m_tile = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = k_lo + c * 32 + i;
+        const bool ok = full || (k < L && mask_allowed(mode, q, k, A, tl));
+        m_tile = fmaxf(m_tile, ok ? __uint_as_float(v[i]) * scale2 : -INFINITY);
+      }
+    }
+    const float m_new = fmaxf(m_run, m_tile);
+    const float m_use = m_new == -INFINITY ? 0.f : m_new;
+    const float alpha = m_run == -INFINITY ? 1.f : exp2f(m_run - m_use);
+    // pass 2: probabilities -> smem (bf16), row sum
+    float l_tile = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + c * 32, v);
+      tmem_ld_wait();
+      float p[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = k_lo + c * 32 + i;
+        const bool ok = full || (k < L && mask_allowed(mode, q, k, A, tl));
+        p[i] = ok ? exp2f(__uint_as_float(v[i]) * scale2 - m_use) : 0.f;
+        l_tile += p[i];
+      }
+      if (a.drop_on) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t keep = dropout_keep8(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (k_lo + c * 32 + 8 * g) >> 3));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p[8 * g + i] = ((keep >> i) & 1u) ? p[8 * g + i] * a.drop.scale : 0.f;
+        }
+      }
+      store_p32(sP, tid, c, p);
+    }
+    l_run = l_run * alpha + l_tile;
+    m_run = m_new;
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(&sh->bar_v, ph);
+      const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+#pragma unroll
+      for (int kk = 0; kk < TK / 16; ++kk)
+        umma_bf16(tmem + 128, make_smem_desc_sw128(pa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                  make_smem_desc_sw128(va + kk * 2048, 8192, 1024), idesc_o, kk > 0);
+      umma_commit(&sh->bar_o);
+    }
+    mbar_wait(&sh->bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && jn < n_kv) {  // V buffer is free
+      mbar_expect_tx(&sh->bar_v, TILE_BYTES);
+      tma_load_2d(&tmQKV, &sh->bar_v, sV, 2 * H + h * D, row0 + jn * TK);
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + 128 + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(v[i]);
+    }
+    j = jn;
+  }
+
+  if (q < L) {
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    bf16* dst = static_cast<bf16*>(a.ctx) + (static_cast<long>(row0) + q) * H + h * D;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint4 u;
+      u.x = pack_bf16x2(o_acc[8 * c + 0] * inv, o_acc[8 * c + 1] * inv);
+      u.y = pack_bf16x2(o_acc[8 * c + 2] * inv, o_acc[8 * c + 3] * inv);
+      u.z = pack_bf16x2(o_acc[8 * c + 4] * inv, o_acc[8 * c + 5] * inv);
+      u.w = pack_bf16x2(o_acc[8 * c + 6] * inv, o_acc[8 * c + 7] * inv);
+      reinterpret_cast<uint4*>(dst)[c] = u;
+    }
+    a.lse[(static_cast<long>(b) * a.nh + h) * L + q] = m_run * kLn2 + logf(l_run);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// delta[b,h,q] = sum_d dO[q,d] * O[q,d]   (one warp per row of the [B*L, H] activations)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O,
+                                                         float* __restrict__ delta, int rows, int L, int nh) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int H = nh * D, b = warp / L, q = warp % L;
+  for (int ch = lane; ch < (H >> 3); ch += 32) {
+    const uint4 x = *reinterpret_cast<const uint4*>(dO + static_cast<long>(warp) * H + ch * 8);
+    const uint4 y = *reinterpret_cast<const uint4*>(O + static_cast<long>(warp) * H + ch * 8);
+    const float2 a0 = unpack_bf16x2(x.x), a1 = unpack_bf16x2(x.y), a2 = unpack_bf16x2(x.z), a3 = unpack_bf16x2(x.w);
+    const float2 b0 = unpack_bf16x2(y.x), b1 = unpack_bf16x2(y.y), b2 = unpack_bf16x2(y.z), b3 = unpack_bf16x2(y.w);
+    float s = a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0) delta[(static_cast<long>(b) * nh + (ch >> 3)) * L + q] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv,
+                                                              long rows, int H) {
+  const long n8 = rows * (H >> 3);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / (H >> 3);
+    const int c = static_cast<int>(i % (H >> 3)) * 8;
+    const float4 x = *reinterpret_cast<const float4*>(dq_acc + r * H + c), y = *reinterpret_cast<const float4*>(dq_acc + r * H + c + 4);
+    uint4 u;
+    u.x = pack_bf16x2(x.x, x.y); u.y = pack_bf16x2(x.z, x.w); u.z = pack_bf16x2(y.x, y.y); u.w = pack_bf16x2(y.z, y.w);
+    *reinterpret_cast<uint4*>(dqkv + r * 3 * H + c) = u;
+  }
+}
+
+struct BwdSmem {
+  uint64_t bar_kv, bar_q, bar_s, bar_o;
+  uint32_t tmem_base;
+};
+
+// One CTA per (key tile, head, sample); loops over the query tiles that can see this key tile.
+// TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448)
+__global__ void __launch_bounds__(128, 1)
+attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  uint8_t* smem = smem_raw + pad;
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;
+  uint8_t* sdO = smem + 3 * TILE_BYTES;
+  uint8_t* sP = smem + 4 * TILE_BYTES;
+  uint8_t* sdS = sP + P_BYTES;
+  BwdSmem* sh = reinterpret_cast<BwdSmem*>(sdS + P_BYTES);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int L = a.L, H = a.nh * D, A = a.A;
+  const int mode = a.mode[b], tl = a.t_len[b];
+  const int k_lo = kt * TK, k_hi = min(k_lo + TK - 1, L - 1);
+  const int n_q = (L + TQ - 1) / TQ;
+  const int row0 = b * L;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(&sh->bar_kv, 1); mbar_init(&sh->bar_q, 1); mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&sh->tmem_base, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+  auto active = [&](int i) { return tile_any_allowed(mode, i * TQ, min(i * TQ + TQ - 1, L - 1), k_lo, k_hi, A, tl); };
+  auto next_active = [&](int i) { ++i; while (i < n_q && !active(i)) ++i; return i; };
+  int i = next_active(-1);
+
+  if (tid == 0 && i < n_q) {
+    mbar_expect_tx(&sh->bar_kv, 2 * TILE_BYTES);
+    tma_load_2d(&tmQKV, &sh->bar_kv, sK, H + h * D, row0 + k_lo);
+    tma_load_2d(&tmQKV, &sh->bar_kv, sV, 2 * H + h * D, row0 + k_lo);
+    mbar_expect_tx(&sh->bar_q, 2 * TILE_BYTES);
+    tma_load_2d(&tmQKV, &sh->bar_q, sQ, h * D, row0 + i * TQ);
+    tma_load_2d(&tmDO, &sh->bar_q, sdO, h * D, row0 + i * TQ);
+  }
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);     // S, dP : K-major x K-major
+  constexpr uint32_t idesc_t = make_idesc_bf16(TK, D, 1, 1);      // dV, dK: P^T / dS^T (MN-major) x dO / Q (MN-major)
+  constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D, 0, 1);      // dQ    : dS (K-major) x K (MN-major)
+  const float scale2 = 0.125f * kLog2e;
+  const bool any = i < n_q;
+  uint32_t it = 0;
+
+  for (; i < n_q; ++it) {
+    const int in = next_active(i);
+    const uint32_t ph = it & 1u;
+    const int q_lo = i * TQ;
+    if (tid == 0) {
+      if (it == 0) mbar_wait(&sh->bar_kv, 0);
+      mbar_wait(&sh->bar_q, ph);
+      tc_fence_after();
+      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit(&sh->bar_s);
+    }
+    mbar_wait(&sh->bar_s, ph);
+    tc_fence_after();
+    const int q = q_lo + tid;
+    const bool q_ok = q < L;
+    const long st = (static_cast<long>(b) * a.nh + h) * L + (q_ok ? q : 0);
+    const float lse2 = q_ok ? a.lse[st] * kLog2e : 0.f;
+    const float delta = q_ok ? a.delta[st] : 0.f;
+    const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t sv[32], dv[32];
+      tmem_ld32(t_lane + c * 32, sv);
+      tmem_ld32(t_lane + 128 + c * 32, dv);
+      tmem_ld_wait();
+      float p[32], ds[32];
+      uint32_t keep_bits = 0xffffffffu;
+      if (a.drop_on) {
+        keep_bits = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          keep_bits |= dropout_keep8(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + c * 32 + 8 * g) >> 3)) << (8 * g);
+      }
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int k = k_lo + c * 32 + e;
+        const bool ok = q_ok && (full || (k < L && mask_allowed(mode, q, k, A, tl)));
+        const float pe = ok ? exp2f(__uint_as_float(sv[e]) * scale2 - lse2) : 0.f;
+        float dp = __uint_as_float(dv[e]);
+        float pd = pe;
+        if (a.drop_on) {
+          const bool kp = (keep_bits >> e) & 1u;
+          dp = kp ? dp * a.drop.scale : 0.f;
+          pd = kp ? pe * a.drop.scale : 0.f;
+        }
+        p[e] = pd;
+        ds[e] = pe * (dp - delta) * 0.125f;
+      }
+      store_p32(sP, tid, c, p);
+      store_p32(sdS, tid, c, ds);
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sdO);
+#pragma unroll
+      for (int kk = 0; kk < TQ / 16; ++kk)  // dV[k,d] += sum_q P[q,k] dO[q,d]
+        umma_bf16(tmem + 256, make_smem_desc_sw128(pa + kk * 2048, TILE_BYTES, 1024),
+                  make_smem_desc_sw128(da + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
+#pragma unroll
+      for (int kk = 0; kk < TQ / 16; ++kk)  // dK[k,d] += sum_q dS[q,k] Q[q,d]
+        umma_bf16(tmem + 320, make_smem_desc_sw128(sa + kk * 2048, TILE_BYTES, 1024),
+                  make_smem_desc_sw128(qa + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
+#pragma unroll
+      for (int kk = 0; kk < TK / 16; ++kk)  // dQ[q,d] = sum_k dS[q,k] K[k,d]
+        umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                  make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+      umma_commit(&sh->bar_o);
+    }
+    mbar_wait(&sh->bar_o, ph);
+    tc_fence_after();
+    if (tid == 0 && in < n_q) {  // Q / dO buffers are free
+      mbar_expect_tx(&sh->bar_q, 2 * TILE_BYTES);
+      tma_load_2d(&tmQKV, &sh->bar_q, sQ, h * D, row0 + in * TQ);
+      tma_load_2d(&tmDO, &sh->bar_q, sdO, h * D, row0 + in * TQ);
+    }
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_lane + 384 + c * 32, v);
+      tmem_ld_wait();
+      if (q_ok) {
+        float* dst = a.dq_acc + (static_cast<long>(row0) + q) * H + h * D + c * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + e), make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
+                                                                    __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+      }
+    }
+    i = in;
+  }
+
+  // epilogue: dV, dK rows of this key tile
+  // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only the stores are predicated on k < L.
+  // `any` is uniform across the CTA (a key tile no query tile can see gets exact zeros).
+  const int k = k_lo + tid;
+  bf16* dk_dst = static_cast<bf16*>(a.dqkv) + (static_cast<long>(row0) + (k < L ? k : 0)) * 3 * H + H + h * D;
+  bf16* dv_dst = dk_dst + H;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    bf16* dst = which == 0 ? dv_dst : dk_dst;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      if (any) {
+        tmem_ld32(t_lane + 256 + which * 64 + c * 32, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0u;
+      }
+      if (k < L) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+          u.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          u.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+          u.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + e) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+constexpr uint32_t kFwdSmem = 1024 + 3 * TILE_BYTES + P_BYTES + 128;
+constexpr uint32_t kBwdSmem = 1024 + 4 * TILE_BYTES + 2 * P_BYTES + 128;
+
+}  // namespace
+
+int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s) {
+  MV_REQUIRE(a.qkv && a.ctx && a.lse && a.mode && a.t_len, "attention_fwd: null argument");
+  const int H = a.nh * D;
+  CUtensorMap tm;
+  int rc = tmap_encode_2d(&tm, TMAP_BF16, a.qkv, 3 * H, static_cast<uint64_t>(a.B) * a.L, static_cast<uint64_t>(3 * H) * 2, D, TQ);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    MV_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    attr = true;
+  }
+  dim3 grid((a.L + TQ - 1) / TQ, a.nh, a.B);
+  attn_fwd_tc05_kernel<<<grid, 128, kFwdSmem, s>>>(tm, a);
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
+  MV_REQUIRE(a.qkv && a.ctx && a.lse && a.dctx && a.dqkv && a.dq_acc && a.delta, "attention_bwd: null argument");
+  const int H = a.nh * D;
+  const long rows = static_cast<long>(a.B) * a.L;
+  CUtensorMap tmQKV, tmDO;
+  int rc = tmap_encode_2d(&tmQKV, TMAP_BF16, a.qkv, 3 * H, rows, static_cast<uint64_t>(3 * H) * 2, D, TQ);
+  if (rc) return rc;
+  rc = tmap_encode_2d(&tmDO, TMAP_BF16, a.dctx, H, rows, static_cast<uint64_t>(H) * 2, D, TQ);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    MV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    attr = true;
+  }
+  MV_CUDA_CHECK(cudaMemsetAsync(a.dq_acc, 0, rows * H * sizeof(float), s));
+  attn_delta_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, s>>>(static_cast<const bf16*>(a.dctx),
+                                                                             static_cast<const bf16*>(a.ctx), a.delta,
+                                                                             static_cast<int>(rows), a.L, a.nh);
+  MV_CUDA_CHECK(cudaGetLastError());
+  dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
+  attn_bwd_tc05_kernel<<<grid, 128, kBwdSmem, s>>>(tmQKV, tmDO, a);
+  MV_CUDA_CHECK(cudaGetLastError());
+  attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mv

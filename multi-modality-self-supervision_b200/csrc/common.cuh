@@ -14,6 +14,7 @@ namespace mv {
 // ---- error plumbing: every C-ABI entry returns 0 or a negative status; message via mv_last_error ----
 void set_error(const char* fmt, ...);
 const char* last_error();
+int device_sm_count();
 
 #define MV_CUDA_CHECK(expr)                                                                         \
   do {                                                                                              \

@@ -40,6 +40,4 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream);
 // fp32 operands, CUDA-core FMA (check mode, 1e-4 parity gate).
 int gemm_f32_simt(const GemmDesc& d, cudaStream_t stream);
 
-int device_sm_count();
-
 }  // namespace mv

@@ -1,0 +1,120 @@
+// kernels.h — launchers for the HBM-bound fused kernels and the attention kernels of the MedViLL pre-training step.
+// `f32` selects the activation dtype: 0 = bf16 (production), 1 = fp32 (check mode). All launch on `stream`, return 0
+// or a negative status (message via mv::last_error()).
+#pragma once
+#include "common.cuh"
+#include "mask.cuh"
+
+namespace mv {
+
+// ---- joint embedding: [CLS] + regions + [SEP] + text  (models/cxrbert_origin.py:112-125, 22-35; upstream BertEmbeddings)
+struct EmbedArgs {
+  int B, L, H, N, T, A;              // A = N + 2, L = A + T
+  const long long* cls_tok;          // [B]      int64 (reference dtype)
+  const long long* sep_tok;          // [B]
+  const long long* input_ids;        // [B, T]
+  const long long* segment;          // [B, T]
+  const long long* region_idx;       // [N]      sampled grid positions (models/image.py:64-69)
+  const float* word; const float* pos; const float* type;   // fp32 master tables
+  const float* gamma; const float* beta; float eps;
+  const void* proj;                  // [B*N, H] activation dtype: img projection + bias (GEMM output)
+  void* emb_sum;                     // [B*L, H] pre-LayerNorm sum (saved for backward)
+  void* out;                         // [B*L, H] LN + dropout output = encoder input
+  int drop_on; uint32_t drop_site; DropoutCfg drop;
+};
+int embed_ln_fwd(const EmbedArgs& a, int f32, cudaStream_t s);
+
+struct EmbedBwdArgs {
+  int B, L, H, N, T, A, V;
+  const long long* cls_tok; const long long* sep_tok; const long long* input_ids; const long long* segment;
+  const long long* region_idx;
+  const void* dsum;                  // [B*L, H] gradient w.r.t. the pre-LN sum (output of ln_bwd)
+  float* d_word; float* d_pos; float* d_type;   // fp32 gradient tables (atomically accumulated)
+  void* d_proj;                      // [B*N, H] gradient of the projected image rows (activation dtype)
+  int pad_id;                        // upstream nn.Embedding(padding_idx=0): lookup gradient of [PAD] is dropped
+};
+int embed_bwd_scatter(const EmbedBwdArgs& a, int f32, cudaStream_t s);
+
+// ---- LayerNorm (eps is an argument: 1e-12 encoder, 1e-5 TF-style MLM head, models/cxrbert_origin.py:189-202)
+int ln_fwd(const void* x, void* y, const float* gamma, const float* beta, int rows, int H, float eps, int drop_on,
+           uint32_t drop_site, const DropoutCfg& drop, int f32, cudaStream_t s);
+// dy: grad w.r.t. LN output (with in_drop: grad w.r.t. dropout(LN(x)), mask re-generated from drop_site)
+// dx: grad w.r.t. x; dx_drop (optional, out_drop): dx * dropout mask of `drop_site` (grad of the dense output that
+// was dropped before the residual add). dgamma/dbeta/dbias are fp32 and accumulated atomically (dbias <- dx_drop or dx).
+int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta,
+           float* dbias, int rows, int H, float eps, int in_drop, int out_drop, uint32_t drop_site,
+           const DropoutCfg& drop, int f32, cudaStream_t s);
+
+// ---- small utilities
+int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, cudaStream_t s);   // out[c] += sum_r x[r,c]
+// dst[i,:] = src[(i / period) * stride + idx[i % period], :]
+int gather_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int f32,
+                cudaStream_t s);
+// dst[(i / period) * stride + idx[i % period], :] (+)= src[i,:]
+int scatter_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int add,
+                 int f32, cudaStream_t s);
+int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaStream_t s);          // dx = dy * gelu'(pre)
+int cast_f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t s);
+int cast_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t s);
+int mask_dump(const unsigned char* mode, const int* t_len, int B, int A, int L, unsigned char* out, cudaStream_t s);
+// derive (mode, t_len) from an explicit [B,L,L] (or [B,L]) int64 mask and count cells that differ from the predicate
+int mask_classify(const long long* mask, int dims, int B, int A, int L, unsigned char* mode, int* t_len,
+                  int* mismatches, cudaStream_t s);
+
+// ---- losses (models/train_origin.py:62-63,118-126) and step metrics (:133-146)
+struct CeArgs {
+  int n, V; long ldv;
+  const float* logits;               // [n, ldv] fp32
+  const long long* labels;           // [n]
+  void* dlogits;                     // [n, ldv] activation dtype: (softmax - onehot) * gscale, pad columns zeroed
+  float gscale;                      // 1 / (#labelled tokens in the GLOBAL batch)
+  float* loss_sum;                   // += sum_i (lse_i - logit_i[label_i])
+  int* correct;                      // += #(argmax == label)
+  float* row_lse; int* row_argmax;   // optional per-row outputs (parity aids)
+};
+int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s);
+
+struct ItmArgs {
+  int B, H;
+  const void* pooled;                // [B, H] activation dtype, tanh output
+  const float* w; const float* b;    // [2, H], [2]
+  const long long* labels;           // [B]
+  float gscale;                      // 1 / (GLOBAL batch)
+  float* logits;                     // [B, 2] fp32 out
+  float* loss_sum; int* correct;
+  void* d_pre;                       // [B, H] activation dtype: grad w.r.t. pooler pre-activation; null = forward only
+  float* dw; float* db;              // fp32 grads (atomic)
+};
+int itm_head_fwd_bwd(const ItmArgs& a, int f32, cudaStream_t s);
+
+// ---- optimizer: HF-3.x AdamW, correct_bias=True (models/train_origin.py:60,129-131)
+struct AdamArgs {
+  long n;
+  float* p; float* g; float* m; float* v; bf16* shadow;
+  float lr, beta1, beta2, eps, weight_decay; int step;
+  float grad_scale;                  // multiply g before use (1 unless gradients were pre-accumulated unscaled)
+  int zero_grad;                     // write zeros back to g (fuses optimizer.zero_grad())
+};
+int adamw_step(const AdamArgs& a, cudaStream_t s);
+
+// ---- fused masked attention (upstream BertSelfAttention; twin .../pytorch_pretrained_bert/model.py:301-320)
+struct AttnArgs {
+  int B, L, nh, A;                   // head dim fixed at 64; H = nh * 64
+  const unsigned char* mode;         // [B] MaskMode
+  const int* t_len;                  // [B]
+  const void* qkv;                   // [B*L, 3H] activation dtype (Q | K | V along columns)
+  void* ctx;                         // [B*L, H]
+  float* lse;                        // [B, nh, L] natural-log row log-sum-exp of the scaled, masked scores
+  // backward only
+  const void* dctx;                  // [B*L, H]
+  void* dqkv;                        // [B*L, 3H]
+  float* dq_acc;                     // [B*L, H] fp32 scratch (tcgen05 path; zeroed by the launcher)
+  float* delta;                      // [B, nh, L] scratch: rowsum(dO * O)
+  int drop_on; uint32_t drop_site; DropoutCfg drop;
+};
+int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s);
+int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s);
+int attention_fwd_simt(const AttnArgs& a, cudaStream_t s);
+int attention_bwd_simt(const AttnArgs& a, cudaStream_t s);
+
+}  // namespace mv

@@ -1,0 +1,540 @@
+// rowwise.cu — HBM-bound fused kernels: joint embedding-sum + LayerNorm (+dropout), LayerNorm forward/backward with
+// dropout-backward and bias/affine gradient reductions, row gather/scatter, column sums, GELU backward, casts, and the
+// on-the-fly mask dump / classifier.  One warp owns one row; every global access is a 16-byte vector; rows are
+// 8-element aligned (H % 8 == 0, H <= 1024).  Templated on the activation type (bf16 production, fp32 check mode).
+#include "kernels.h"
+
+namespace mv {
+namespace {
+
+constexpr int kMaxChunks = 4;  // 8-element chunks per lane: H <= 32 * 4 * 8 = 1024
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<bf16>(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ void atomic_add8(float* p, const float (&v)[8]) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  atomicAdd(reinterpret_cast<float4*>(p + 4), make_float4(v[4], v[5], v[6], v[7]));
+}
+
+// mean / rstd of a row held as nchunk x 8 values per lane (two-pass, fp32)
+__device__ __forceinline__ void row_stats(const float (&x)[kMaxChunks][8], int nch, int lane, int H, float eps,
+                                          float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+    if (lane + 32 * c < nch)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += x[c][j];
+  mean = warp_sum(s) / H;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c)
+    if (lane + 32 * c < nch)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = x[c][j] - mean; q += d * d; }
+  rstd = rsqrtf(warp_sum(q) / H + eps);
+}
+
+__device__ __forceinline__ void apply_dropout8(float (&v)[8], const DropoutCfg& d, uint32_t site, long row, int H, int col) {
+  const uint32_t keep = dropout_keep8(d, site, (static_cast<uint64_t>(row) * H + col) >> 3);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * d.scale : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const EmbedArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int rows = a.B * a.L;
+  if (warp >= rows) return;
+  const int b = warp / a.L, s = warp % a.L;
+  const int H = a.H, nch = H >> 3;
+  const float* wrow = nullptr;
+  const T* prow = nullptr;
+  int pos_id = 0, type_id = 0;
+  if (s == 0) {
+    wrow = a.word + a.cls_tok[b] * H;                                         // [CLS]: position 0, type 0
+  } else if (s <= a.N) {
+    prow = static_cast<const T*>(a.proj) + (static_cast<long>(b) * a.N + (s - 1)) * H;
+    pos_id = static_cast<int>(a.region_idx[s - 1]);                           // grid index as position id
+  } else if (s == a.N + 1) {
+    wrow = a.word + a.sep_tok[b] * H;                                         // [SEP]: position restarts at 0
+  } else {
+    const int i = s - a.A;
+    wrow = a.word + a.input_ids[static_cast<long>(b) * a.T + i] * H;
+    pos_id = i;
+    type_id = static_cast<int>(a.segment[static_cast<long>(b) * a.T + i]);
+  }
+  const float* posrow = a.pos + static_cast<long>(pos_id) * H;
+  const float* typerow = a.type + static_cast<long>(type_id) * H;
+  float x[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      float w[8], p[8], t[8];
+      if (wrow) load8<float>(wrow + ch * 8, w); else load8<T>(prow + ch * 8, w);
+      load8<float>(posrow + ch * 8, p);
+      load8<float>(typerow + ch * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[c][j] = w[j] + p[j] + t[j];
+      store8<T>(static_cast<T*>(a.emb_sum) + static_cast<long>(warp) * H + ch * 8, x[c]);
+    }
+  }
+  float mean, rstd;
+  row_stats(x, nch, lane, H, a.eps, mean, rstd);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      float g[8], bt[8], y[8];
+      load8<float>(a.gamma + ch * 8, g);
+      load8<float>(a.beta + ch * 8, bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (x[c][j] - mean) * rstd * g[j] + bt[j];
+      if (a.drop_on) apply_dropout8(y, a.drop, a.drop_site, warp, H, ch * 8);
+      store8<T>(static_cast<T*>(a.out) + static_cast<long>(warp) * H + ch * 8, y);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* gamma,
+                                                     const float* beta, int rows, int H, float eps, int drop_on,
+                                                     uint32_t site, DropoutCfg drop) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nch = H >> 3;
+  float v[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) load8<T>(x + static_cast<long>(warp) * H + ch * 8, v[c]);
+  }
+  float mean, rstd;
+  row_stats(v, nch, lane, H, eps, mean, rstd);
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      float g[8], bt[8], o[8];
+      load8<float>(gamma + ch * 8, g);
+      load8<float>(beta + ch * 8, bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + bt[j];
+      if (drop_on) apply_dropout8(o, drop, site, warp, H, ch * 8);
+      store8<T>(y + static_cast<long>(warp) * H + ch * 8, o);
+    }
+  }
+}
+
+// LayerNorm backward. 8 warps / CTA, each warp strides over rows; per-lane partial sums of dgamma / dbeta / dbias are
+// reduced across the CTA's warps through shared memory, then one fp32 atomicAdd per column per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                     const float* __restrict__ gamma, T* __restrict__ dx,
+                                                     T* __restrict__ dx_drop, float* dgamma, float* dbeta, float* dbias,
+                                                     int rows, int H, float eps, int in_drop, int out_drop, uint32_t site,
+                                                     DropoutCfg drop) {
+  extern __shared__ float red[];  // [8][H]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nch = H >> 3;
+  float g[kMaxChunks][8];
+  float ag[kMaxChunks][8], ab[kMaxChunks][8], abias[kMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) load8<float>(gamma + ch * 8, g[c]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ag[c][j] = 0.f; ab[c][j] = 0.f; abias[c][j] = 0.f; }
+  }
+  for (long row = static_cast<long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long>(gridDim.x) * 8) {
+    float xv[kMaxChunks][8], dv[kMaxChunks][8];
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        load8<T>(x + row * H + ch * 8, xv[c]);
+        load8<T>(dy + row * H + ch * 8, dv[c]);
+        if (in_drop) apply_dropout8(dv[c], drop, site, row, H, ch * 8);
+      }
+    }
+    float mean, rstd;
+    row_stats(xv, nch, lane, H, eps, mean, rstd);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      if (lane + 32 * c < nch) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[c][j] - mean) * rstd;
+          const float gy = dv[c][j] * g[c][j];
+          s1 += gy; s2 += gy * xh;
+          ag[c][j] += dv[c][j] * xh;
+          ab[c][j] += dv[c][j];
+          xv[c][j] = xh;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / H;
+    s2 = warp_sum(s2) / H;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[c][j] * g[c][j] - s1 - xv[c][j] * s2);
+        store8<T>(dx + row * H + ch * 8, o);
+        if (out_drop) {
+          apply_dropout8(o, drop, site, row, H, ch * 8);
+          store8<T>(dx_drop + row * H + ch * 8, o);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) abias[c][j] += o[j];
+      }
+    }
+  }
+  // cross-warp reduction, one quantity at a time
+  for (int which = 0; which < 3; ++which) {
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
+    if (dst == nullptr) continue;  // uniform across the CTA
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          red[warp * H + ch * 8 + j] = which == 0 ? ag[c][j] : (which == 1 ? ab[c][j] : abias[c][j]);
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < H; col += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w * H + col];
+      atomicAdd(dst + col, s);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const EmbedBwdArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int rows = a.B * a.L;
+  if (warp >= rows) return;
+  const int b = warp / a.L, s = warp % a.L;
+  const int H = a.H, nch = H >> 3;
+  long word_id = -1;
+  int pos_id = 0, type_id = 0;
+  T* proj_row = nullptr;
+  if (s == 0) word_id = a.cls_tok[b];
+  else if (s <= a.N) { proj_row = static_cast<T*>(a.d_proj) + (static_cast<long>(b) * a.N + (s - 1)) * H; pos_id = static_cast<int>(a.region_idx[s - 1]); }
+  else if (s == a.N + 1) word_id = a.sep_tok[b];
+  else {
+    const int i = s - a.A;
+    word_id = a.input_ids[static_cast<long>(b) * a.T + i];
+    pos_id = i;
+    type_id = static_cast<int>(a.segment[static_cast<long>(b) * a.T + i]);
+  }
+  const T* src = static_cast<const T*>(a.dsum) + static_cast<long>(warp) * H;
+  for (int ch = lane; ch < nch; ch += 32) {
+    float v[8];
+    load8<T>(src + ch * 8, v);
+    if (proj_row) store8<T>(proj_row + ch * 8, v);
+    else if (word_id != a.pad_id) atomic_add8(a.d_word + word_id * H + ch * 8, v);
+    atomic_add8(a.d_pos + static_cast<long>(pos_id) * H + ch * 8, v);
+    atomic_add8(a.d_type + static_cast<long>(type_id) * H + ch * 8, v);
+  }
+}
+
+// out[c] += sum_r x[r, c]; grid = (col groups of 256, row splits); 8 warps per CTA stride over rows
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ld, int rows, int cols, float* out) {
+  __shared__ float red[8][256 + 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < cols) {
+    for (long r = static_cast<long>(blockIdx.y) * 8 + warp; r < rows; r += static_cast<long>(gridDim.y) * 8) {
+      float v[8];
+      load8<T>(x + r * ld + col, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    atomicAdd(out + blockIdx.x * 256 + c, s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                          const long long* __restrict__ idx, int n, int period,
+                                                          long stride, int H) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const long srow = static_cast<long>(warp / period) * stride + idx[warp % period];
+  const uint4* s = reinterpret_cast<const uint4*>(src + srow * H);
+  uint4* d = reinterpret_cast<uint4*>(dst + static_cast<long>(warp) * H);
+  const int nvec = H * static_cast<int>(sizeof(T)) / 16;
+  for (int i = lane; i < nvec; i += 32) d[i] = s[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                           const long long* __restrict__ idx, int n, int period,
+                                                           long stride, int H, int add) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const long drow = static_cast<long>(warp / period) * stride + idx[warp % period];
+  const T* s = src + static_cast<long>(warp) * H;
+  T* d = dst + drow * H;
+  for (int ch = lane; ch < (H >> 3); ch += 32) {
+    float v[8];
+    load8<T>(s + ch * 8, v);
+    if (add) {
+      float o[8];
+      load8<T>(d + ch * 8, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += o[j];
+    }
+    store8<T>(d + ch * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dgelu_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dx, long n8) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float a[8], p[8];
+    load8<T>(dy + i * 8, a);
+    load8<T>(pre + i * 8, p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= gelu_erf_grad(p[j]);
+    store8<T>(dx + i * 8, a);
+  }
+}
+
+__global__ void cast_f2b_kernel(const float* __restrict__ s, bf16* __restrict__ d, long n) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void cast_b2f_kernel(const bf16* __restrict__ s, float* __restrict__ d, long n) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    d[i] = __bfloat162float(s[i]);
+}
+
+__global__ void mask_dump_kernel(const unsigned char* mode, const int* t_len, int B, int A, int L, unsigned char* out) {
+  const long total = static_cast<long>(B) * L * L;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % L), q = static_cast<int>((i / L) % L), b = static_cast<int>(i / (static_cast<long>(L) * L));
+    out[i] = mask_allowed(mode[b], q, k, A, t_len[b]) ? 1 : 0;
+  }
+}
+
+// One CTA per sample: probe three cells to pick the mode, count row 0 for t_len, then verify every cell.
+__global__ void __launch_bounds__(256) mask_classify_kernel(const long long* mask, int dims, int B, int A, int L,
+                                                            unsigned char* mode_out, int* tlen_out, int* mismatches) {
+  const int b = blockIdx.x;
+  __shared__ int s_mode, s_tlen, s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  if (dims == 2) {  // [B, L] key-padding mask: bidirectional
+    const long long* m = mask + static_cast<long>(b) * L;
+    int c = 0;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) c += m[k] != 0;
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) { s_mode = MODE_BIDIR; s_tlen = s_cnt - A; s_cnt = 0; }
+    __syncthreads();
+    int bad = 0;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) bad += (m[k] != 0) != mask_allowed(MODE_BIDIR, 0, k, A, s_tlen);
+    if (bad) atomicAdd(mismatches, bad);
+  } else {
+    const long long* m = mask + static_cast<long>(b) * L * L;
+    int c = 0;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) c += m[static_cast<long>(L - 1) * L + k] != 0;  // last text row
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const bool txt_sees_img = m[static_cast<long>(A) * L + 0] != 0;
+      const bool img_sees_txt = m[0 * L + A] != 0;
+      const bool txt_sees_next = m[static_cast<long>(A) * L + A + 1] != 0;
+      int md;
+      if (!txt_sees_img) md = MODE_NONCROSS;
+      else if (!img_sees_txt) md = MODE_S2S;
+      else if (!txt_sees_next) md = MODE_BAR;
+      else md = MODE_BIDIR;
+      s_mode = md;
+      s_tlen = md == MODE_BIDIR ? s_cnt - A : L - A;
+    }
+    __syncthreads();
+    const int md = s_mode, tl = s_tlen;
+    int bad = 0;
+    for (long i = threadIdx.x; i < static_cast<long>(L) * L; i += blockDim.x)
+      bad += (m[i] != 0) != mask_allowed(md, static_cast<int>(i / L), static_cast<int>(i % L), A, tl);
+    if (bad) atomicAdd(mismatches, bad);
+  }
+  if (threadIdx.x == 0) { mode_out[b] = static_cast<unsigned char>(s_mode); tlen_out[b] = s_tlen; }
+}
+
+inline int rows_grid(int rows) { return (rows * 32 + 255) / 256; }
+
+}  // namespace
+
+#define MV_DISPATCH_T(f32, ...)                                  \
+  do {                                                           \
+    if (f32) { using T = float; __VA_ARGS__; } else { using T = bf16; __VA_ARGS__; } \
+  } while (0)
+
+static int check_h(int H) {
+  MV_REQUIRE(H % 8 == 0 && H <= 32 * kMaxChunks * 8 && H > 0, "row kernels need H %% 8 == 0 and H <= 1024 (got %d)", H);
+  return 0;
+}
+
+int embed_ln_fwd(const EmbedArgs& a, int f32, cudaStream_t s) {
+  if (check_h(a.H)) return -1;
+  const int rows = a.B * a.L;
+  MV_DISPATCH_T(f32, (embed_ln_fwd_kernel<T><<<rows_grid(rows), 256, 0, s>>>(a)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int embed_bwd_scatter(const EmbedBwdArgs& a, int f32, cudaStream_t s) {
+  if (check_h(a.H)) return -1;
+  const int rows = a.B * a.L;
+  MV_DISPATCH_T(f32, (embed_bwd_scatter_kernel<T><<<rows_grid(rows), 256, 0, s>>>(a)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ln_fwd(const void* x, void* y, const float* gamma, const float* beta, int rows, int H, float eps, int drop_on,
+           uint32_t drop_site, const DropoutCfg& drop, int f32, cudaStream_t s) {
+  if (check_h(H)) return -1;
+  if (rows <= 0) return 0;
+  MV_DISPATCH_T(f32, (ln_fwd_kernel<T><<<rows_grid(rows), 256, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(y), gamma,
+                                                                       beta, rows, H, eps, drop_on, drop_site, drop)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta,
+           float* dbias, int rows, int H, float eps, int in_drop, int out_drop, uint32_t drop_site,
+           const DropoutCfg& drop, int f32, cudaStream_t s) {
+  if (check_h(H)) return -1;
+  if (rows <= 0) return 0;
+  MV_REQUIRE(!out_drop || dx_drop != nullptr, "ln_bwd: out_drop needs dx_drop");
+  int grid = (rows + 7) / 8;
+  const int cap = device_sm_count() * 4;
+  if (grid > cap) grid = cap;
+  const size_t smem = static_cast<size_t>(8) * H * sizeof(float);
+  MV_DISPATCH_T(f32, (ln_bwd_kernel<T><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
+                                                               static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
+                                                               dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, cudaStream_t s) {
+  MV_REQUIRE(cols % 8 == 0 && ld % 8 == 0, "colsum: cols and ld must be multiples of 8");
+  if (rows <= 0) return 0;
+  int ysplit = (rows + 63) / 64;
+  if (ysplit > 64) ysplit = 64;
+  dim3 grid((cols + 255) / 256, ysplit);
+  MV_DISPATCH_T(f32, (colsum_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, rows, cols, out)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int gather_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int f32,
+                cudaStream_t s) {
+  if (n <= 0) return 0;
+  MV_REQUIRE(H % 8 == 0, "gather_rows: H %% 8");
+  MV_DISPATCH_T(f32, (gather_rows_kernel<T><<<rows_grid(n), 256, 0, s>>>(static_cast<const T*>(src), static_cast<T*>(dst), idx, n,
+                                                                         period, stride, H)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int scatter_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int add,
+                 int f32, cudaStream_t s) {
+  if (n <= 0) return 0;
+  MV_REQUIRE(H % 8 == 0, "scatter_rows: H %% 8");
+  MV_DISPATCH_T(f32, (scatter_rows_kernel<T><<<rows_grid(n), 256, 0, s>>>(static_cast<const T*>(src), static_cast<T*>(dst), idx, n,
+                                                                          period, stride, H, add)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaStream_t s) {
+  MV_REQUIRE(n % 8 == 0, "dgelu: n %% 8");
+  if (n <= 0) return 0;
+  const long n8 = n / 8;
+  int grid = static_cast<int>((n8 + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  MV_DISPATCH_T(f32, (dgelu_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(pre), static_cast<T*>(dx), n8)));
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int cast_f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  cast_f2b_kernel<<<148 * 8, 256, 0, s>>>(src, dst, n);
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int cast_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  cast_b2f_kernel<<<148 * 8, 256, 0, s>>>(src, dst, n);
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mask_dump(const unsigned char* mode, const int* t_len, int B, int A, int L, unsigned char* out, cudaStream_t s) {
+  mask_dump_kernel<<<148 * 4, 256, 0, s>>>(mode, t_len, B, A, L, out);
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int mask_classify(const long long* mask, int dims, int B, int A, int L, unsigned char* mode, int* t_len,
+                  int* mismatches, cudaStream_t s) {
+  MV_REQUIRE(dims == 2 || dims == 3, "mask_classify: mask must be [B,L] or [B,L,L]");
+  MV_CUDA_CHECK(cudaMemsetAsync(mismatches, 0, sizeof(int), s));
+  mask_classify_kernel<<<B, 256, 0, s>>>(mask, dims, B, A, L, mode, t_len, mismatches);
+  MV_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mv

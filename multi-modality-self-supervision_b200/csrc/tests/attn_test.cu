@@ -1,0 +1,199 @@
+// attn_test.cu — standalone GPU check of the fused masked attention (tcgen05 bf16 and SIMT fp32, forward + backward)
+// against a double-precision CPU evaluation of softmax(QK^T/8 + mask) V and its gradients, for every mask mode.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../kernels.h"
+
+using namespace mv;
+
+static uint32_t g_seed = 777;
+static float frand() {
+  g_seed = g_seed * 1664525u + 1013904223u;
+  return ((g_seed >> 8) & 0xFFFF) / 65536.0f - 0.5f;
+}
+static float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+template <typename T>
+static T* dupload(const std::vector<T>& h) {
+  T* d;
+  cudaMalloc(&d, h.size() * sizeof(T));
+  cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  return d;
+}
+static bf16* dupload_bf16(const std::vector<float>& h) {
+  std::vector<bf16> hb(h.size());
+  for (size_t i = 0; i < h.size(); ++i) hb[i] = __float2bfloat16_rn(h[i]);
+  return dupload(hb);
+}
+static std::vector<float> ddownload_bf16(const bf16* d, size_t n) {
+  std::vector<bf16> hb(n);
+  cudaMemcpy(hb.data(), d, n * 2, cudaMemcpyDeviceToHost);
+  std::vector<float> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = __bfloat162float(hb[i]);
+  return h;
+}
+static std::vector<float> ddownload(const float* d, size_t n) {
+  std::vector<float> h(n);
+  cudaMemcpy(h.data(), d, n * 4, cudaMemcpyDeviceToHost);
+  return h;
+}
+
+static double max_rel(const std::vector<float>& got, const std::vector<double>& ref) {
+  double mx = 0, den = 1e-12;
+  for (size_t i = 0; i < ref.size(); ++i) den = fmax(den, fabs(ref[i]));
+  for (size_t i = 0; i < ref.size(); ++i) {
+    double e = fabs((double)got[i] - ref[i]);
+    if (!(e == e)) return 1e30;
+    mx = fmax(mx, e);
+  }
+  return mx / den;
+}
+
+static int run(int B, int nh, int L, int A, const std::vector<int>& modes, const std::vector<int>& tlens, const char* name) {
+  const int H = nh * 64;
+  const size_t rows = (size_t)B * L;
+  std::vector<float> qkv(rows * 3 * H), dctx(rows * H);
+  for (auto& v : qkv) v = bf16_round(frand() * 4.f);
+  for (auto& v : dctx) v = bf16_round(frand());
+  std::vector<unsigned char> mode(B);
+  std::vector<int> tlen(B);
+  for (int b = 0; b < B; ++b) { mode[b] = (unsigned char)modes[b % modes.size()]; tlen[b] = tlens[b % tlens.size()]; }
+  // ---- CPU reference (double) ----
+  std::vector<double> ctx_ref(rows * H, 0.0), lse_ref((size_t)B * nh * L), dqkv_ref(rows * 3 * H, 0.0);
+  std::vector<double> P((size_t)L * L), dS((size_t)L * L);
+  for (int b = 0; b < B; ++b)
+    for (int h = 0; h < nh; ++h) {
+      const float* base = qkv.data() + (size_t)b * L * 3 * H;
+      for (int q = 0; q < L; ++q) {
+        double mx = -1e300;
+        for (int k = 0; k < L; ++k) {
+          double s = -1e300;
+          if (mask_allowed(mode[b], q, k, A, tlen[b])) {
+            s = 0;
+            for (int d = 0; d < 64; ++d) s += (double)base[(size_t)q * 3 * H + h * 64 + d] * base[(size_t)k * 3 * H + H + h * 64 + d];
+            s *= 0.125;
+          }
+          P[(size_t)q * L + k] = s;
+          mx = fmax(mx, s);
+        }
+        double sum = 0;
+        for (int k = 0; k < L; ++k) { double& p = P[(size_t)q * L + k]; p = p <= -1e299 ? 0.0 : exp(p - mx); sum += p; }
+        for (int k = 0; k < L; ++k) P[(size_t)q * L + k] /= sum;
+        lse_ref[((size_t)b * nh + h) * L + q] = mx + log(sum);
+        for (int d = 0; d < 64; ++d) {
+          double o = 0;
+          for (int k = 0; k < L; ++k) o += P[(size_t)q * L + k] * base[(size_t)k * 3 * H + 2 * H + h * 64 + d];
+          ctx_ref[((size_t)b * L + q) * H + h * 64 + d] = o;
+        }
+      }
+      for (int q = 0; q < L; ++q) {
+        const float* dO = dctx.data() + ((size_t)b * L + q) * H + h * 64;
+        double delta = 0;
+        for (int d = 0; d < 64; ++d) delta += (double)dO[d] * ctx_ref[((size_t)b * L + q) * H + h * 64 + d];
+        for (int k = 0; k < L; ++k) {
+          double dp = 0;
+          for (int d = 0; d < 64; ++d) dp += (double)dO[d] * base[(size_t)k * 3 * H + 2 * H + h * 64 + d];
+          dS[(size_t)q * L + k] = P[(size_t)q * L + k] * (dp - delta) * 0.125;
+        }
+      }
+      for (int q = 0; q < L; ++q)
+        for (int k = 0; k < L; ++k) {
+          const double p = P[(size_t)q * L + k], ds = dS[(size_t)q * L + k];
+          if (p == 0.0 && ds == 0.0) continue;
+          for (int d = 0; d < 64; ++d) {
+            dqkv_ref[((size_t)b * L + q) * 3 * H + h * 64 + d] += ds * base[(size_t)k * 3 * H + H + h * 64 + d];
+            dqkv_ref[((size_t)b * L + k) * 3 * H + H + h * 64 + d] += ds * base[(size_t)q * 3 * H + h * 64 + d];
+            dqkv_ref[((size_t)b * L + k) * 3 * H + 2 * H + h * 64 + d] += p * dctx[((size_t)b * L + q) * H + h * 64 + d];
+          }
+        }
+    }
+  // ---- GPU ----
+  unsigned char* d_mode = dupload(mode);
+  int* d_tlen = dupload(tlen);
+  float *lse, *delta, *dq_acc;
+  cudaMalloc(&lse, (size_t)B * nh * L * 4); cudaMalloc(&delta, (size_t)B * nh * L * 4); cudaMalloc(&dq_acc, rows * H * 4);
+  int fails = 0;
+  for (int f32 = 0; f32 < 2; ++f32) {
+    void* d_qkv = f32 ? (void*)dupload(qkv) : (void*)dupload_bf16(qkv);
+    void* d_dctx = f32 ? (void*)dupload(dctx) : (void*)dupload_bf16(dctx);
+    const size_t es = f32 ? 4 : 2;
+    void *d_ctx, *d_dqkv;
+    cudaMalloc(&d_ctx, rows * H * es); cudaMalloc(&d_dqkv, rows * 3 * H * es);
+    cudaMemset(d_ctx, 0xFF, rows * H * es); cudaMemset(d_dqkv, 0xFF, rows * 3 * H * es);
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.L = L; a.nh = nh; a.A = A; a.mode = d_mode; a.t_len = d_tlen; a.qkv = d_qkv; a.ctx = d_ctx; a.lse = lse;
+    a.dctx = d_dctx; a.dqkv = d_dqkv; a.dq_acc = dq_acc; a.delta = delta; a.drop_on = 0; a.drop = make_dropout(0.f, 1);
+    int rc = f32 ? attention_fwd_simt(a, 0) : attention_fwd_tc05(a, 0);
+    if (rc) { printf("launch error: %s\n", last_error()); return 1; }
+    rc = f32 ? attention_bwd_simt(a, 0) : attention_bwd_tc05(a, 0);
+    if (rc) { printf("launch error: %s\n", last_error()); return 1; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(3); }
+    std::vector<float> ctx = f32 ? ddownload((float*)d_ctx, rows * H) : ddownload_bf16((bf16*)d_ctx, rows * H);
+    std::vector<float> dq = f32 ? ddownload((float*)d_dqkv, rows * 3 * H) : ddownload_bf16((bf16*)d_dqkv, rows * 3 * H);
+    std::vector<float> lse_h = ddownload(lse, (size_t)B * nh * L);
+    const double e_ctx = max_rel(ctx, ctx_ref), e_lse = max_rel(lse_h, lse_ref), e_dq = max_rel(dq, dqkv_ref);
+    const double tol = f32 ? 2e-4 : 2e-2;
+    const bool ok = e_ctx < tol && e_lse < (f32 ? 1e-5 : 2e-3) && e_dq < tol;
+    printf("  %-26s [%s] ctx %.2e  lse %.2e  dqkv %.2e  %s\n", name, f32 ? "simt f32" : "tc05 bf16", e_ctx, e_lse, e_dq, ok ? "PASS" : "FAIL");
+    fails += !ok;
+    cudaFree(d_qkv); cudaFree(d_dctx); cudaFree(d_ctx); cudaFree(d_dqkv);
+  }
+  cudaFree(d_mode); cudaFree(d_tlen); cudaFree(lse); cudaFree(delta); cudaFree(dq_acc);
+  return fails;
+}
+
+// dropout consistency: tc05 and SIMT share the RNG, so with identical (bf16-representable) inputs they must agree
+static int run_dropout(int B, int nh, int L, int A) {
+  const int H = nh * 64;
+  const size_t rows = (size_t)B * L;
+  std::vector<float> qkv(rows * 3 * H), dctx(rows * H);
+  for (auto& v : qkv) v = bf16_round(frand() * 4.f);
+  for (auto& v : dctx) v = bf16_round(frand());
+  std::vector<unsigned char> mode(B, MODE_BAR);
+  std::vector<int> tlen(B, 100);
+  unsigned char* d_mode = dupload(mode);
+  int* d_tlen = dupload(tlen);
+  float *lse, *delta, *dq_acc;
+  cudaMalloc(&lse, (size_t)B * nh * L * 4); cudaMalloc(&delta, (size_t)B * nh * L * 4); cudaMalloc(&dq_acc, rows * H * 4);
+  std::vector<float> res[2], resd[2];
+  for (int f32 = 0; f32 < 2; ++f32) {
+    void* d_qkv = f32 ? (void*)dupload(qkv) : (void*)dupload_bf16(qkv);
+    void* d_dctx = f32 ? (void*)dupload(dctx) : (void*)dupload_bf16(dctx);
+    const size_t es = f32 ? 4 : 2;
+    void *d_ctx, *d_dqkv;
+    cudaMalloc(&d_ctx, rows * H * es); cudaMalloc(&d_dqkv, rows * 3 * H * es);
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.L = L; a.nh = nh; a.A = A; a.mode = d_mode; a.t_len = d_tlen; a.qkv = d_qkv; a.ctx = d_ctx; a.lse = lse;
+    a.dctx = d_dctx; a.dqkv = d_dqkv; a.dq_acc = dq_acc; a.delta = delta; a.drop_on = 1; a.drop_site = 5; a.drop = make_dropout(0.1f, 4242);
+    if (f32) { attention_fwd_simt(a, 0); attention_bwd_simt(a, 0); } else { attention_fwd_tc05(a, 0); attention_bwd_tc05(a, 0); }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(3); }
+    res[f32] = f32 ? ddownload((float*)d_ctx, rows * H) : ddownload_bf16((bf16*)d_ctx, rows * H);
+    resd[f32] = f32 ? ddownload((float*)d_dqkv, rows * 3 * H) : ddownload_bf16((bf16*)d_dqkv, rows * 3 * H);
+    cudaFree(d_qkv); cudaFree(d_dctx); cudaFree(d_ctx); cudaFree(d_dqkv);
+  }
+  std::vector<double> r0(res[1].begin(), res[1].end()), r1(resd[1].begin(), resd[1].end());
+  const double e0 = max_rel(res[0], r0), e1 = max_rel(resd[0], r1);
+  const bool ok = e0 < 2e-2 && e1 < 2e-2;
+  printf("  %-26s [tc05 vs simt] ctx %.2e dqkv %.2e %s\n", "dropout p=0.1 BAR", e0, e1, ok ? "PASS" : "FAIL");
+  return !ok;
+}
+
+int main() {
+  int fails = 0;
+  printf("== fused masked attention ==\n");
+  fails += run(4, 2, 436, 182, {MODE_BAR, MODE_S2S, MODE_NONCROSS, MODE_BIDIR}, {254, 254, 254, 57}, "L=436 all modes");
+  fails += run(4, 1, 512, 258, {MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS}, {17, 254, 254, 254}, "L=512 all modes");
+  fails += run(2, 2, 32, 11, {MODE_BAR, MODE_S2S}, {21, 21}, "L=32 tiny");
+  fails += run_dropout(2, 2, 436, 182);
+  printf("%s (%d failures)\n", fails ? "ATTN TEST FAILED" : "ATTN TEST PASSED", fails);
+  return fails ? 1 : 0;
+}
