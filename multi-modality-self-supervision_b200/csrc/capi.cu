@@ -1,0 +1,263 @@
+// capi.cu — extern "C" surface of libmedvill_sm100.so (see include/medvill_sm100.h for the reference citations).
+#include <string.h>
+
+#include "engine.h"
+
+namespace mv {
+int nccl_unique_id(uint8_t out[128]);
+int engine_comm_init(Engine* e, const uint8_t id[128], int rank, int world);
+int engine_allreduce(Engine* e, float* buf, int64_t count, cudaStream_t s);
+int engine_comm_sync(Engine* e, cudaStream_t s);
+}  // namespace mv
+
+using namespace mv;
+
+struct mv_handle {
+  Engine eng;
+};
+
+#define MV_CHECK_HANDLE(h) do { if (!(h)) { mv::set_error("null mv_handle"); return -1; } } while (0)
+static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+extern "C" {
+
+const char* mv_last_error(void) { return mv::last_error(); }
+int mv_abi_version(void) { return MV_ABI_VERSION; }
+
+int mv_layout_query(const mv_config* cfg, mv_layout* out) {
+  MV_REQUIRE(cfg && out, "mv_layout_query: null argument");
+  return layout_compute(*cfg, out);
+}
+
+int mv_bucket_plan(const mv_config* cfg, int64_t* offsets, int64_t* counts, int32_t max_buckets, int32_t* n_buckets) {
+  MV_REQUIRE(cfg && offsets && counts && n_buckets, "mv_bucket_plan: null argument");
+  mv_layout lay;
+  if (layout_compute(*cfg, &lay)) return -1;
+  const std::vector<Bucket> b = bucket_plan(*cfg, lay);
+  MV_REQUIRE(static_cast<int>(b.size()) <= max_buckets, "mv_bucket_plan: need room for %d buckets", (int)b.size());
+  for (size_t i = 0; i < b.size(); ++i) { offsets[i] = b[i].offset; counts[i] = b[i].count; }
+  *n_buckets = static_cast<int32_t>(b.size());
+  return 0;
+}
+
+int mv_create(mv_handle** out, const mv_config* cfg) {
+  MV_REQUIRE(out && cfg, "mv_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    mv::set_error("no CUDA device visible: libmedvill_sm100 has no CPU fallback");
+    return -4;
+  }
+  mv_handle* h = new mv_handle();
+  const int rc = h->eng.init(*cfg);
+  if (rc) { h->eng.destroy(); delete h; return rc; }
+  *out = h;
+  return 0;
+}
+
+int mv_destroy(mv_handle* h) {
+  if (!h) return 0;
+  h->eng.destroy();
+  delete h;
+  return 0;
+}
+
+int mv_bind_arenas(mv_handle* h, float* params, float* grads, float* adam_m, float* adam_v, void* shadow_bf16) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(params && grads, "mv_bind_arenas: params and grads are required");
+  MV_REQUIRE(h->eng.f32 || shadow_bf16, "mv_bind_arenas: bf16 precision needs the shadow arena");
+  h->eng.params = params; h->eng.grads = grads; h->eng.adam_m = adam_m; h->eng.adam_v = adam_v;
+  h->eng.shadow = static_cast<bf16*>(shadow_bf16);
+  return 0;
+}
+
+int mv_refresh_shadow(mv_handle* h, void* stream) {
+  MV_CHECK_HANDLE(h);
+  if (!h->eng.shadow) return 0;
+  return cast_f32_to_bf16(h->eng.params, h->eng.shadow, h->eng.lay.total, S(stream));
+}
+
+int mv_stats_reset(mv_handle* h, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_CUDA_CHECK(cudaMemsetAsync(h->eng.stats, 0, sizeof(mv_step_stats), S(stream)));
+  return 0;
+}
+
+int mv_forward(mv_handle* h, const mv_batch* b, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(b, "mv_forward: null batch");
+  return h->eng.forward(*b, S(stream));
+}
+
+int mv_backward(mv_handle* h, const mv_batch* b, int32_t allreduce, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(b, "mv_backward: null batch");
+  return h->eng.backward(*b, allreduce, S(stream));
+}
+
+int mv_zero_grads(mv_handle* h, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(h->eng.grads, "arenas not bound");
+  MV_CUDA_CHECK(cudaMemsetAsync(h->eng.grads, 0, h->eng.lay.total * sizeof(float), S(stream)));
+  return 0;
+}
+
+int mv_adamw_step(mv_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                  float grad_scale, void* stream) {
+  MV_CHECK_HANDLE(h);
+  Engine& e = h->eng;
+  MV_REQUIRE(e.params && e.grads && e.adam_m && e.adam_v, "mv_adamw_step: arenas (incl. Adam moments) not bound");
+  if (engine_comm_sync(&e, S(stream))) return -2;
+  AdamArgs a;
+  a.n = e.lay.total; a.p = e.params; a.g = e.grads; a.m = e.adam_m; a.v = e.adam_v; a.shadow = e.shadow;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
+  a.grad_scale = grad_scale; a.zero_grad = 1;
+  return adamw_step(a, S(stream));
+}
+
+int mv_read_stats(mv_handle* h, mv_step_stats* host_out, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(host_out, "mv_read_stats: null output");
+  MV_CUDA_CHECK(cudaMemcpyAsync(h->eng.stats_host, h->eng.stats, sizeof(mv_step_stats), cudaMemcpyDeviceToHost, S(stream)));
+  MV_CUDA_CHECK(cudaStreamSynchronize(S(stream)));
+  *host_out = *h->eng.stats_host;
+  return 0;
+}
+
+int mv_itm_logits(mv_handle* h, float* host_out, int32_t B, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(host_out && B > 0 && B <= h->eng.cfg.max_batch, "mv_itm_logits: bad arguments");
+  MV_CUDA_CHECK(cudaMemcpyAsync(host_out, h->eng.itm_logits, sizeof(float) * 2 * B, cudaMemcpyDeviceToHost, S(stream)));
+  MV_CUDA_CHECK(cudaStreamSynchronize(S(stream)));
+  return 0;
+}
+
+int mv_full_logits(mv_handle* h, const mv_batch* b, float* logits, int64_t ld, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(b && logits, "mv_full_logits: null argument");
+  return h->eng.full_logits(*b, logits, ld, S(stream));
+}
+
+// Copy a named intermediate to `dst` (device or host pointer; cudaMemcpyDefault). Parity-test aid.
+int mv_peek(mv_handle* h, const char* name, int32_t layer, void* dst, int64_t max_bytes, int64_t* bytes, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(name && dst && bytes, "mv_peek: null argument");
+  Engine& e = h->eng;
+  const size_t es = e.es, M = static_cast<size_t>(e.cfg.max_batch) * e.L, H = e.cfg.hidden, I = e.cfg.inter;
+  const void* src = nullptr;
+  size_t n = 0;
+  const bool lay_ok = layer >= 0 && layer < e.cfg.layers;
+  if (!strcmp(name, "x") && layer >= 0 && layer <= e.cfg.layers) { src = e.x[layer]; n = M * H * es; }
+  else if (!strcmp(name, "emb_sum")) { src = e.emb_sum; n = M * H * es; }
+  else if (!strcmp(name, "proj")) { src = e.proj; n = static_cast<size_t>(e.cfg.max_batch) * e.cfg.num_image_embeds * H * es; }
+  else if (!strcmp(name, "qkv") && lay_ok) { src = e.lw[layer].qkv; n = M * 3 * H * es; }
+  else if (!strcmp(name, "ctx") && lay_ok) { src = e.lw[layer].ctx; n = M * H * es; }
+  else if (!strcmp(name, "x1") && lay_ok) { src = e.lw[layer].x1; n = M * H * es; }
+  else if (!strcmp(name, "h1") && lay_ok) { src = e.lw[layer].h1; n = M * I * es; }
+  else if (!strcmp(name, "lse") && lay_ok) { src = e.lw[layer].lse; n = static_cast<size_t>(e.cfg.max_batch) * e.nh * e.L * 4; }
+  else if (!strcmp(name, "pooled")) { src = e.pooled; n = static_cast<size_t>(e.cfg.max_batch) * H * es; }
+  else if (!strcmp(name, "itm_logits")) { src = e.itm_logits; n = static_cast<size_t>(e.cfg.max_batch) * 2 * 4; }
+  else if (!strcmp(name, "logits")) { src = e.logits; n = static_cast<size_t>(e.mlm_cap) * e.Vpad * 4; }
+  else if (!strcmp(name, "row_lse")) { src = e.row_lse; n = static_cast<size_t>(e.mlm_cap) * 4; }
+  else if (!strcmp(name, "row_argmax")) { src = e.row_argmax; n = static_cast<size_t>(e.mlm_cap) * 4; }
+  else if (!strcmp(name, "dx")) { src = e.dxa; n = M * H * es; }
+  MV_REQUIRE(src != nullptr, "mv_peek: unknown buffer '%s' (layer %d)", name, layer);
+  if (static_cast<int64_t>(n) > max_bytes) n = static_cast<size_t>(max_bytes);
+  MV_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, S(stream)));
+  MV_CUDA_CHECK(cudaStreamSynchronize(S(stream)));
+  *bytes = static_cast<int64_t>(n);
+  return 0;
+}
+
+int mv_comm_unique_id(uint8_t out[128]) { return nccl_unique_id(out); }
+int mv_comm_init(mv_handle* h, const uint8_t id[128], int32_t rank, int32_t world) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(world >= 1 && rank >= 0 && rank < world, "mv_comm_init: bad rank/world");
+  return engine_comm_init(&h->eng, id, rank, world);
+}
+int mv_comm_allreduce_f32(mv_handle* h, float* buf, int64_t count, void* stream) {
+  MV_CHECK_HANDLE(h);
+  return engine_allreduce(&h->eng, buf, count, S(stream));
+}
+int mv_comm_sync(mv_handle* h, void* stream) {
+  MV_CHECK_HANDLE(h);
+  return engine_comm_sync(&h->eng, S(stream));
+}
+
+int mv_gemm(const mv_gemm_desc* g, int32_t precision, void* stream) {
+  MV_REQUIRE(g, "mv_gemm: null descriptor");
+  GemmDesc d;
+  d.M = g->M; d.N = g->N; d.K = g->K;
+  d.A = g->A; d.lda = g->lda; d.a_mn = g->a_mn;
+  d.B = g->B; d.ldb = g->ldb; d.b_mn = g->b_mn;
+  d.C = g->C; d.ldc = g->ldc; d.c_f32 = g->c_f32; d.accumulate = g->accumulate;
+  d.C2 = g->C2; d.ldc2 = g->ldc2;
+  d.epi = g->epi; d.bias = g->bias; d.resid = g->resid; d.ldr = g->ldr; d.aux = g->aux; d.ldaux = g->ldaux;
+  d.drop_on = g->dropout_p > 0.f; d.drop_site = g->dropout_site; d.drop = make_dropout(g->dropout_p, g->dropout_seed);
+  return precision == MV_PREC_FP32 ? gemm_f32_simt(d, S(stream)) : gemm_bf16_tc05(d, S(stream));
+}
+
+int mv_attn_mask_dump(const uint8_t* mode, const int32_t* t_len, int32_t B, int32_t A, int32_t L, uint8_t* out, void* stream) {
+  MV_REQUIRE(mode && t_len && out, "mv_attn_mask_dump: null argument");
+  return mask_dump(mode, t_len, B, A, L, out, S(stream));
+}
+
+int mv_mask_classify(const int64_t* mask, int32_t dims, int32_t B, int32_t A, int32_t L, uint8_t* mode, int32_t* t_len,
+                     int32_t* mismatches, void* stream) {
+  MV_REQUIRE(mask && mode && t_len && mismatches, "mv_mask_classify: null argument");
+  return mask_classify(reinterpret_cast<const int64_t*>(mask), dims, B, A, L, mode, t_len, mismatches, S(stream));
+}
+
+static AttnArgs make_attn(int32_t B, int32_t L, int32_t heads, int32_t A, const uint8_t* mode, const int32_t* t_len,
+                          const void* qkv, void* ctx, float* lse, float p, uint64_t seed, uint32_t site) {
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.L = L; a.nh = heads; a.A = A; a.mode = mode; a.t_len = t_len; a.qkv = qkv; a.ctx = ctx; a.lse = lse;
+  a.drop_on = p > 0.f; a.drop_site = site; a.drop = make_dropout(p, seed);
+  return a;
+}
+
+int mv_attention_fwd(int32_t B, int32_t L, int32_t heads, int32_t A, const uint8_t* mode, const int32_t* t_len,
+                     const void* qkv, void* ctx, float* lse, float dropout_p, uint64_t seed, uint32_t site,
+                     int32_t precision, void* stream) {
+  AttnArgs a = make_attn(B, L, heads, A, mode, t_len, qkv, ctx, lse, dropout_p, seed, site);
+  return precision == MV_PREC_FP32 ? attention_fwd_simt(a, S(stream)) : attention_fwd_tc05(a, S(stream));
+}
+
+int mv_attention_bwd(int32_t B, int32_t L, int32_t heads, int32_t A, const uint8_t* mode, const int32_t* t_len,
+                     const void* qkv, const void* ctx, const float* lse, const void* dctx, void* dqkv, float* dq_acc,
+                     float* delta, float dropout_p, uint64_t seed, uint32_t site, int32_t precision, void* stream) {
+  AttnArgs a = make_attn(B, L, heads, A, mode, t_len, qkv, const_cast<void*>(ctx), const_cast<float*>(lse), dropout_p, seed, site);
+  a.dctx = dctx; a.dqkv = dqkv; a.dq_acc = dq_acc; a.delta = delta;
+  return precision == MV_PREC_FP32 ? attention_bwd_simt(a, S(stream)) : attention_bwd_tc05(a, S(stream));
+}
+
+int mv_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t H, float eps,
+                     int32_t precision, void* stream) {
+  return ln_fwd(x, y, gamma, beta, rows, H, eps, 0, 0, make_dropout(0.f, 0), precision == MV_PREC_FP32, S(stream));
+}
+
+int mv_layernorm_bwd(const void* dy, const void* x, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                     int32_t rows, int32_t H, float eps, int32_t precision, void* stream) {
+  return ln_bwd(dy, x, gamma, dx, nullptr, dgamma, dbeta, nullptr, rows, H, eps, 0, 0, 0, make_dropout(0.f, 0),
+                precision == MV_PREC_FP32, S(stream));
+}
+
+int mv_mlm_ce(const float* logits, int64_t ld, const int64_t* labels, int32_t n, int32_t V, void* dlogits, float gscale,
+              float* loss_sum, int32_t* correct, float* row_lse, int32_t* row_argmax, int32_t precision, void* stream) {
+  CeArgs a;
+  a.n = n; a.V = V; a.ldv = ld; a.logits = logits; a.labels = reinterpret_cast<const int64_t*>(labels); a.dlogits = dlogits;
+  a.gscale = gscale; a.loss_sum = loss_sum; a.correct = correct; a.row_lse = row_lse; a.row_argmax = row_argmax;
+  return mlm_ce_fwd_bwd(a, precision == MV_PREC_FP32, S(stream));
+}
+
+int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
+             float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream) {
+  AdamArgs a;
+  a.n = n; a.p = p; a.g = g; a.m = m; a.v = v; a.shadow = static_cast<bf16*>(shadow_bf16);
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
+  a.grad_scale = grad_scale; a.zero_grad = zero_grad;
+  return adamw_step(a, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,443 @@
+// engine.cu — drivers of the MedViLL pre-training step on one B200.
+//
+// Data layout in HBM (B = micro-batch, L = N + S + 3 joint length, M = B*L rows, H hidden, I intermediate):
+//   * one flat fp32 parameter arena (+ identical-layout grad / Adam m / Adam v arenas and a bf16 shadow used as GEMM
+//     operands); nn.Linear weights stay [out, in] so forward is a K-major x K-major ("TN") GEMM, dgrad reads the same
+//     weight MN-major and wgrad reads both activations MN-major — nothing is ever transposed in memory;
+//   * activations are row-major [M, features] in the activation dtype; Q|K|V share one [M, 3H] buffer that the
+//     attention kernels read with strided TMA boxes; everything backward needs is kept per layer
+//     (qkv, ctx, pre-LN sums y1/y2, x1, pre-GELU h1, GELU g1, row LSE) — 686 MB per layer at B=64 in bf16;
+//   * dropout masks are never stored: regenerated from (step seed, site id, element index).
+//
+// Reference call stack replaced: CXRBERT.forward (models/cxrbert_origin.py:144-149) -> CXRBertEncoder.forward (:87-130)
+// -> upstream BertEncoder x12 -> heads (:205-248, :164-173) -> CE losses (models/train_origin.py:118-126) -> backward
+// -> AdamW (:129-131), with nn.DataParallel's gradient reduction (:53-55) replaced by bucketed NCCL all-reduce.
+#include "engine.h"
+
+#include <dlfcn.h>
+#include <string.h>
+
+namespace mv {
+
+namespace {
+inline int64_t up64(int64_t x) { return (x + 63) / 64 * 64; }
+
+enum : uint32_t { SITE_EMB = 1, SITE_LAYER0 = 16 };
+inline uint32_t site_att(int l) { return SITE_LAYER0 + 4 * l; }
+inline uint32_t site_h1(int l) { return SITE_LAYER0 + 4 * l + 1; }
+inline uint32_t site_h2(int l) { return SITE_LAYER0 + 4 * l + 2; }
+}  // namespace
+
+int layout_compute(const mv_config& c, mv_layout* o) {
+  MV_REQUIRE(c.hidden > 0 && c.hidden % 64 == 0 && c.hidden <= 1024, "hidden must be a multiple of 64, <= 1024 (got %d)", c.hidden);
+  MV_REQUIRE(c.heads * 64 == c.hidden, "head dim must be 64: hidden=%d heads=%d", c.hidden, c.heads);
+  MV_REQUIRE(c.inter > 0 && c.inter % 64 == 0, "intermediate size must be a multiple of 64 (got %d)", c.inter);
+  MV_REQUIRE(c.img_hidden > 0 && c.img_hidden % 64 == 0, "img_hidden must be a multiple of 64 (got %d)", c.img_hidden);
+  MV_REQUIRE(c.layers > 0 && c.vocab > 0 && c.max_pos > 0 && c.type_vocab > 0, "bad BERT dims");
+  MV_REQUIRE(c.num_image_embeds > 0 && c.seq_len > 0 && c.grid >= c.num_image_embeds, "bad sequence dims (N=%d S=%d grid=%d)",
+             c.num_image_embeds, c.seq_len, c.grid);
+  MV_REQUIRE(c.seq_len + 1 <= c.max_pos && c.grid <= c.max_pos, "position table too small");
+  const int64_t H = c.hidden, I = c.inter, V = c.vocab;
+  int64_t off = 0;
+  auto take = [&](int64_t n) { const int64_t at = off; off += up64(n); return at; };
+  o->word = take(V * H); o->pos = take(static_cast<int64_t>(c.max_pos) * H); o->type = take(static_cast<int64_t>(c.type_vocab) * H);
+  o->emb_ln_g = take(H); o->emb_ln_b = take(H);
+  o->img_w = take(H * c.img_hidden); o->img_b = take(H);
+  o->layer0 = off;
+  int64_t r = 0;
+  auto rel = [&](int64_t n) { const int64_t at = r; r += n; return at; };
+  o->l_wqkv = rel(3 * H * H); o->l_bqkv = rel(3 * H); o->l_wo = rel(H * H); o->l_bo = rel(H);
+  o->l_ln1_g = rel(H); o->l_ln1_b = rel(H); o->l_w1 = rel(I * H); o->l_b1 = rel(I); o->l_w2 = rel(H * I); o->l_b2 = rel(H);
+  o->l_ln2_g = rel(H); o->l_ln2_b = rel(H);
+  o->layer_stride = up64(r);
+  off += o->layer_stride * c.layers;
+  o->pool_w = take(H * H); o->pool_b = take(H);
+  o->mlm_bias = take(V); o->mlm_tw = take(H * H); o->mlm_tb = take(H); o->mlm_ln_g = take(H); o->mlm_ln_b = take(H);
+  o->itm_w = take(2 * H); o->itm_b = take(2);
+  o->total = off;
+  o->vocab_padded = up64(V);
+  return 0;
+}
+
+std::vector<Bucket> bucket_plan(const mv_config& c, const mv_layout& lay) {
+  std::vector<Bucket> b;
+  b.push_back({lay.pool_w, lay.total - lay.pool_w});                       // heads (ready first)
+  for (int l = c.layers - 1; l >= 0; --l) b.push_back({lay.layer0 + l * lay.layer_stride, lay.layer_stride});
+  b.push_back({0, lay.layer0});                                            // embeddings + image projection (last)
+  return b;
+}
+
+// ---- NCCL through dlopen: whichever libnccl.so.2 the process already mapped (torch's) is reused ----
+struct NcclUid { char b[128]; };  // ncclUniqueId is passed by value
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi* load_nccl() {
+  static NcclApi api;
+  if (api.lib) return &api;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return nullptr; }
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) {
+    set_error("libnccl.so.2 lacks required symbols");
+    return nullptr;
+  }
+  api.lib = lib;
+  return &api;
+}
+
+int nccl_unique_id(uint8_t out[128]) {
+  NcclApi* n = load_nccl();
+  if (!n) return -3;
+  const int rc = n->GetUniqueId(out);
+  MV_REQUIRE(rc == 0, "ncclGetUniqueId failed: %s", n->GetErrorString ? n->GetErrorString(rc) : "?");
+  return 0;
+}
+
+int engine_comm_init(Engine* e, const uint8_t id[128], int rank, int world) {
+  NcclApi* n = load_nccl();
+  if (!n) return -3;
+  NcclUid uid;
+  memcpy(uid.b, id, 128);
+  void* comm = nullptr;
+  const int rc = n->CommInitRank(&comm, world, uid, rank);
+  MV_REQUIRE(rc == 0, "ncclCommInitRank failed: %s", n->GetErrorString ? n->GetErrorString(rc) : "?");
+  e->nccl = n; e->comm = comm; e->rank = rank; e->world = world;
+  MV_CUDA_CHECK(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
+  MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
+  MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+  return 0;
+}
+
+int engine_allreduce(Engine* e, float* buf, int64_t count, cudaStream_t s) {
+  MV_REQUIRE(e->comm != nullptr, "communicator not initialised (mv_comm_init)");
+  const int rc = e->nccl->AllReduce(buf, buf, static_cast<size_t>(count), /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, s);
+  MV_REQUIRE(rc == 0, "ncclAllReduce failed: %s", e->nccl->GetErrorString ? e->nccl->GetErrorString(rc) : "?");
+  return 0;
+}
+
+int engine_comm_sync(Engine* e, cudaStream_t s) {
+  if (e->comm_pending) {
+    MV_CUDA_CHECK(cudaEventRecord(e->ev_done, e->comm_stream));
+    MV_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_done, 0));
+    e->comm_pending = false;
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+int Engine::alloc(void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  MV_CUDA_CHECK(cudaMalloc(p, (bytes + 255) / 256 * 256));
+  allocs.push_back(*p);
+  return 0;
+}
+
+int Engine::init(const mv_config& c) {
+  cfg = c;
+  if (layout_compute(c, &lay)) return -1;
+  MV_REQUIRE(c.max_batch > 0, "max_batch must be positive");
+  MV_REQUIRE(c.precision == MV_PREC_BF16 || c.precision == MV_PREC_FP32, "unknown precision %d", c.precision);
+  MV_REQUIRE(c.dropout_p >= 0.f && c.dropout_p < 1.f, "dropout_p out of range");
+  int dev = 0, major = 0;
+  MV_CUDA_CHECK(cudaGetDevice(&dev));
+  MV_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MV_REQUIRE(major == 10, "libmedvill_sm100 needs an sm_100 (Blackwell B200) GPU; device %d is sm_%d0 — no fallback path", dev, major);
+  f32 = c.precision == MV_PREC_FP32;
+  es = f32 ? 4 : 2;
+  nh = c.heads;
+  A = c.num_image_embeds + 2; T = c.seq_len + 1; L = A + T;
+  Vpad = static_cast<int>(lay.vocab_padded);
+  const size_t M = static_cast<size_t>(c.max_batch) * L, H = c.hidden, I = c.inter, B = c.max_batch, N = c.num_image_embeds;
+  x.resize(c.layers + 1);
+  for (auto& p : x) if (alloc(&p, M * H * es)) return -2;
+  lw.resize(c.layers);
+  for (auto& w : lw) {
+    if (alloc(&w.qkv, M * 3 * H * es) || alloc(&w.ctx, M * H * es) || alloc(&w.y1, M * H * es) || alloc(&w.x1, M * H * es) ||
+        alloc(&w.h1, M * I * es) || alloc(&w.g1, M * I * es) || alloc(&w.y2, M * H * es) ||
+        alloc(reinterpret_cast<void**>(&w.lse), B * nh * L * sizeof(float)))
+      return -2;
+  }
+  if (alloc(&emb_sum, M * H * es) || alloc(&proj, B * N * H * es) || alloc(&feats_g, B * N * c.img_hidden * es) ||
+      alloc(&cls_rows, B * H * es) || alloc(&pooled, B * H * es) || alloc(&d_pre, B * H * es) || alloc(&d_cls, B * H * es) ||
+      alloc(reinterpret_cast<void**>(&itm_logits), B * 2 * sizeof(float)) || alloc(&dxa, M * H * es) || alloc(&dxb, M * H * es) ||
+      alloc(&dxc, M * H * es) || alloc(&dh1, M * I * es) || alloc(&dqkv, M * 3 * H * es) || alloc(&dctx, M * H * es) ||
+      alloc(&dproj, B * N * H * es) || alloc(reinterpret_cast<void**>(&dq_acc), M * H * sizeof(float)) ||
+      alloc(reinterpret_cast<void**>(&delta), B * nh * L * sizeof(float)) || alloc(reinterpret_cast<void**>(&zero_idx), 16) ||
+      alloc(reinterpret_cast<void**>(&stats), sizeof(mv_step_stats)))
+    return -2;
+  MV_CUDA_CHECK(cudaMemset(zero_idx, 0, 16));
+  MV_CUDA_CHECK(cudaMemset(stats, 0, sizeof(mv_step_stats)));
+  MV_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&stats_host), sizeof(mv_step_stats)));
+  buckets = bucket_plan(cfg, lay);
+  return ensure_mlm(static_cast<int>(B * T / 4 + 64));
+}
+
+void Engine::destroy() {
+  cudaDeviceSynchronize();
+  for (void* p : allocs) cudaFree(p);
+  allocs.clear();
+  void* mlm[] = {rows_h, t_pre, t_act, t_ln, dlogits, d_tln, d_tact, d_tpre, d_rows, logits, row_lse, row_argmax};
+  for (void* p : mlm) if (p) cudaFree(p);
+  if (stats_host) cudaFreeHost(stats_host);
+  if (comm && nccl) nccl->CommDestroy(comm);
+  if (comm_stream) cudaStreamDestroy(comm_stream);
+  if (ev_ready) cudaEventDestroy(ev_ready);
+  if (ev_done) cudaEventDestroy(ev_done);
+}
+
+int Engine::ensure_mlm(int n) {
+  if (n <= mlm_cap) return 0;
+  MV_CUDA_CHECK(cudaDeviceSynchronize());
+  void** ptrs[] = {&rows_h, &t_pre, &t_act, &t_ln, &dlogits, &d_tln, &d_tact, &d_tpre, &d_rows,
+                   reinterpret_cast<void**>(&logits), reinterpret_cast<void**>(&row_lse), reinterpret_cast<void**>(&row_argmax)};
+  for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  int cap = mlm_cap * 2 > n ? mlm_cap * 2 : n;
+  cap = (cap + 127) / 128 * 128;
+  const size_t H = cfg.hidden, c = cap;
+  MV_CUDA_CHECK(cudaMalloc(&rows_h, c * H * es)); MV_CUDA_CHECK(cudaMalloc(&t_pre, c * H * es));
+  MV_CUDA_CHECK(cudaMalloc(&t_act, c * H * es)); MV_CUDA_CHECK(cudaMalloc(&t_ln, c * H * es));
+  MV_CUDA_CHECK(cudaMalloc(&dlogits, c * Vpad * es)); MV_CUDA_CHECK(cudaMalloc(&d_tln, c * H * es));
+  MV_CUDA_CHECK(cudaMalloc(&d_tact, c * H * es)); MV_CUDA_CHECK(cudaMalloc(&d_tpre, c * H * es));
+  MV_CUDA_CHECK(cudaMalloc(&d_rows, c * H * es));
+  MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&logits), c * Vpad * sizeof(float)));
+  MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&row_lse), c * sizeof(float)));
+  MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&row_argmax), c * sizeof(int)));
+  mlm_cap = cap;
+  return 0;
+}
+
+// Y[M,N] = epi(X[M,K] . W[N,K]^T + b)
+int Engine::linear_fwd(const void* X, int M, int K, int64_t w_off, int N, int64_t b_off, void* Y, int epi, void* pre,
+                       const void* resid, int drop_on, uint32_t site, const DropoutCfg& dc, cudaStream_t s, int y_f32, long ldy) {
+  GemmDesc d;
+  d.M = M; d.N = N; d.K = K;
+  d.A = X; d.lda = K; d.a_mn = 0;
+  d.B = W(w_off); d.ldb = K; d.b_mn = 0;
+  d.C = Y; d.ldc = ldy ? ldy : N; d.c_f32 = y_f32;
+  d.C2 = pre; d.ldc2 = N;
+  d.epi = epi; d.bias = b_off >= 0 ? params + b_off : nullptr;
+  d.resid = resid; d.ldr = N;
+  d.drop_on = drop_on; d.drop_site = site; d.drop = dc;
+  return gemm(d, s);
+}
+
+// dX[M,K] = epi(dY[M,N] . W[N,K])   (W read MN-major in place)
+int Engine::linear_dgrad(const void* dY, long lddy, int M, int N, int64_t w_off, int K, void* dX, int epi, const void* extra,
+                         cudaStream_t s) {
+  GemmDesc d;
+  d.M = M; d.N = K; d.K = N;
+  d.A = dY; d.lda = lddy; d.a_mn = 0;
+  d.B = W(w_off); d.ldb = K; d.b_mn = 1;
+  d.C = dX; d.ldc = K;
+  d.epi = epi; d.resid = extra; d.ldr = K; d.aux = extra; d.ldaux = K;
+  return gemm(d, s);
+}
+
+// dW[N,K] += dY[M,N]^T . X[M,K]     (fp32, split-K reduce-add into the gradient arena)
+int Engine::linear_wgrad(const void* dY, long lddy, const void* X, int M, int N, int K, int64_t w_off, cudaStream_t s) {
+  GemmDesc d;
+  d.M = N; d.N = K; d.K = M;
+  d.A = dY; d.lda = lddy; d.a_mn = 1;
+  d.B = X; d.ldb = K; d.b_mn = 1;
+  d.C = grads + w_off; d.ldc = K; d.c_f32 = 1; d.accumulate = 1;
+  d.epi = EPI_NONE;
+  return gemm(d, s);
+}
+
+#define MV_TRY(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+int Engine::forward(const mv_batch& b, cudaStream_t s) {
+  MV_REQUIRE(params && grads && (f32 || shadow), "arenas not bound (mv_bind_arenas)");
+  MV_REQUIRE(b.B > 0 && b.B <= cfg.max_batch, "batch %d exceeds capacity %d", b.B, cfg.max_batch);
+  MV_REQUIRE(b.cls_tok && b.sep_tok && b.input_ids && b.segment && b.region_idx && b.mode && b.t_len && b.feats, "mv_batch: null input");
+  MV_REQUIRE(b.n_lab >= 0 && b.n_lab <= b.B * T, "n_lab out of range");
+  const int B = b.B, H = cfg.hidden, I = cfg.inter, N = cfg.num_image_embeds, M = B * L;
+  const bool drop = b.train && cfg.dropout_p > 0.f;
+  const DropoutCfg dc = make_dropout(cfg.dropout_p, b.dropout_seed);
+  MV_TRY(ensure_mlm(b.n_lab));
+
+  // --- visual tokens: sample regions, project 2048 -> H (models/image.py:57-69, cxrbert_origin.py:24) ---
+  MV_TRY(gather_rows(b.feats, feats_g, b.region_idx, B * N, N, cfg.grid, cfg.img_hidden, f32, s));
+  MV_TRY(linear_fwd(feats_g, B * N, cfg.img_hidden, lay.img_w, H, lay.img_b, proj, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s));
+  // --- joint embedding + LayerNorm + dropout, written straight into the concatenated [B, L, H] buffer ---
+  EmbedArgs ea;
+  ea.B = B; ea.L = L; ea.H = H; ea.N = N; ea.T = T; ea.A = A;
+  ea.cls_tok = reinterpret_cast<const int64_t*>(b.cls_tok); ea.sep_tok = reinterpret_cast<const int64_t*>(b.sep_tok);
+  ea.input_ids = reinterpret_cast<const int64_t*>(b.input_ids); ea.segment = reinterpret_cast<const int64_t*>(b.segment);
+  ea.region_idx = reinterpret_cast<const int64_t*>(b.region_idx);
+  ea.word = params + lay.word; ea.pos = params + lay.pos; ea.type = params + lay.type;
+  ea.gamma = params + lay.emb_ln_g; ea.beta = params + lay.emb_ln_b; ea.eps = cfg.ln_eps;
+  ea.proj = proj; ea.emb_sum = emb_sum; ea.out = x[0];
+  ea.drop_on = drop; ea.drop_site = SITE_EMB; ea.drop = dc;
+  MV_TRY(embed_ln_fwd(ea, f32, s));
+
+  // --- encoder ---
+  for (int l = 0; l < cfg.layers; ++l) {
+    const int64_t base = lay.layer0 + l * lay.layer_stride;
+    LayerWs& w = lw[l];
+    MV_TRY(linear_fwd(x[l], M, H, base + lay.l_wqkv, 3 * H, base + lay.l_bqkv, w.qkv, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s));
+    AttnArgs aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
+    aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
+    MV_TRY(f32 ? attention_fwd_simt(aa, s) : attention_fwd_tc05(aa, s));
+    MV_TRY(linear_fwd(w.ctx, M, H, base + lay.l_wo, H, base + lay.l_bo, w.y1, EPI_BIAS_RESID, nullptr, x[l], drop, site_h1(l), dc, s));
+    MV_TRY(ln_fwd(w.y1, w.x1, params + base + lay.l_ln1_g, params + base + lay.l_ln1_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s));
+    MV_TRY(linear_fwd(w.x1, M, H, base + lay.l_w1, I, base + lay.l_b1, w.g1, EPI_BIAS_GELU, w.h1, nullptr, 0, 0, dc, s));
+    MV_TRY(linear_fwd(w.g1, M, I, base + lay.l_w2, H, base + lay.l_b2, w.y2, EPI_BIAS_RESID, nullptr, w.x1, drop, site_h2(l), dc, s));
+    MV_TRY(ln_fwd(w.y2, x[l + 1], params + base + lay.l_ln2_g, params + base + lay.l_ln2_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s));
+  }
+  const void* seq = x[cfg.layers];
+
+  // --- pooler + ITM head + CE (cxrbert_origin.py:130,164-173; train_origin.py:63,123,133-136) ---
+  MV_TRY(gather_rows(seq, cls_rows, zero_idx, B, 1, L, H, f32, s));
+  MV_TRY(linear_fwd(cls_rows, B, H, lay.pool_w, H, lay.pool_b, pooled, EPI_BIAS_TANH, nullptr, nullptr, 0, 0, dc, s));
+  ItmArgs ia;
+  ia.B = B; ia.H = H; ia.pooled = pooled; ia.w = params + lay.itm_w; ia.b = params + lay.itm_b;
+  ia.labels = reinterpret_cast<const int64_t*>(b.is_aligned); ia.gscale = b.inv_batch_global; ia.logits = itm_logits;
+  ia.loss_sum = &stats->itm_loss_sum; ia.correct = &stats->itm_correct;
+  ia.d_pre = (b.train && b.is_aligned) ? d_pre : nullptr; ia.dw = grads + lay.itm_w; ia.db = grads + lay.itm_b;
+  MV_TRY(itm_head_fwd_bwd(ia, f32, s));
+
+  // --- MLM head on the labelled rows only (cxrbert_origin.py:205-248; train_origin.py:62,120,138-146) ---
+  if (b.n_lab > 0) {
+    MV_REQUIRE(b.lab_rows && b.lab_labels, "mv_batch: n_lab > 0 needs lab_rows / lab_labels");
+    const int n = b.n_lab;
+    MV_TRY(gather_rows(seq, rows_h, reinterpret_cast<const int64_t*>(b.lab_rows), n, n, 0, H, f32, s));
+    MV_TRY(linear_fwd(rows_h, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
+    MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, n, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
+    MV_TRY(linear_fwd(t_ln, n, H, lay.word, cfg.vocab, lay.mlm_bias, logits, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, Vpad));
+    CeArgs ca;
+    ca.n = n; ca.V = cfg.vocab; ca.ldv = Vpad; ca.logits = logits; ca.labels = reinterpret_cast<const int64_t*>(b.lab_labels);
+    ca.dlogits = b.train ? dlogits : nullptr; ca.gscale = b.inv_n_lab_global;
+    ca.loss_sum = &stats->mlm_loss_sum; ca.correct = &stats->mlm_correct; ca.row_lse = row_lse; ca.row_argmax = row_argmax;
+    MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
+  }
+  return 0;
+}
+
+int Engine::bucket_done(size_t idx, int allreduce, cudaStream_t s) {
+  if (!allreduce || world <= 1) return 0;
+  MV_REQUIRE(comm != nullptr, "allreduce requested but mv_comm_init was not called");
+  const Bucket& bk = buckets[idx];
+  MV_CUDA_CHECK(cudaEventRecord(ev_ready, s));
+  MV_CUDA_CHECK(cudaStreamWaitEvent(comm_stream, ev_ready, 0));
+  MV_TRY(engine_allreduce(this, grads + bk.offset, bk.count, comm_stream));
+  comm_pending = true;
+  return 0;
+}
+
+int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
+  MV_REQUIRE(b.train, "mv_backward needs a batch forwarded with train=1");
+  const int B = b.B, H = cfg.hidden, I = cfg.inter, N = cfg.num_image_embeds, M = B * L;
+  const bool drop = cfg.dropout_p > 0.f;
+  const DropoutCfg dc = make_dropout(cfg.dropout_p, b.dropout_seed);
+  void* P = dxa; void* Q = dxb; void* R = dxc;
+  MV_CUDA_CHECK(cudaMemsetAsync(P, 0, static_cast<size_t>(M) * H * es, s));   // d(seq): only labelled + [CLS] rows are non-zero
+
+  // --- MLM head backward ---
+  if (b.n_lab > 0) {
+    const int n = b.n_lab;
+    MV_TRY(colsum_add(dlogits, Vpad, n, Vpad, grads + lay.mlm_bias, f32, s));
+    {  // tied decoder weight: dE[V,H] += dlogits^T . t_ln   (the embedding-lookup part is added at the end)
+      GemmDesc d;
+      d.M = cfg.vocab; d.N = H; d.K = n;
+      d.A = dlogits; d.lda = Vpad; d.a_mn = 1;
+      d.B = t_ln; d.ldb = H; d.b_mn = 1;
+      d.C = grads + lay.word; d.ldc = H; d.c_f32 = 1; d.accumulate = 1;
+      MV_TRY(gemm(d, s));
+    }
+    MV_TRY(linear_dgrad(dlogits, Vpad, n, cfg.vocab, lay.word, H, d_tln, EPI_NONE, nullptr, s));
+    MV_TRY(ln_bwd(d_tln, t_act, params + lay.mlm_ln_g, d_tact, nullptr, grads + lay.mlm_ln_g, grads + lay.mlm_ln_b, nullptr, n, H,
+                  cfg.head_ln_eps, 0, 0, 0, dc, f32, s));
+    MV_TRY(dgelu_mul(d_tact, t_pre, d_tpre, static_cast<long>(n) * H, f32, s));
+    MV_TRY(colsum_add(d_tpre, H, n, H, grads + lay.mlm_tb, f32, s));
+    MV_TRY(linear_wgrad(d_tpre, H, rows_h, n, H, H, lay.mlm_tw, s));
+    MV_TRY(linear_dgrad(d_tpre, H, n, H, lay.mlm_tw, H, d_rows, EPI_NONE, nullptr, s));
+    MV_TRY(scatter_rows(d_rows, P, reinterpret_cast<const int64_t*>(b.lab_rows), n, n, 0, H, 0, f32, s));
+  }
+  // --- pooler backward (d_pre was produced by the ITM kernel in forward) ---
+  if (b.is_aligned) {
+    MV_TRY(colsum_add(d_pre, H, B, H, grads + lay.pool_b, f32, s));
+    MV_TRY(linear_wgrad(d_pre, H, cls_rows, B, H, H, lay.pool_w, s));
+    MV_TRY(linear_dgrad(d_pre, H, B, H, lay.pool_w, H, d_cls, EPI_NONE, nullptr, s));
+    MV_TRY(scatter_rows(d_cls, P, zero_idx, B, 1, L, H, 1, f32, s));
+  }
+  MV_TRY(bucket_done(0, allreduce, s));
+
+  // --- encoder layers, last to first ---
+  for (int l = cfg.layers - 1; l >= 0; --l) {
+    const int64_t base = lay.layer0 + l * lay.layer_stride;
+    LayerWs& w = lw[l];
+    float* g = grads + base;
+    // P = d(layer output).  LN2: y2 -> x[l+1]
+    void* dY2d = drop ? R : Q;
+    MV_TRY(ln_bwd(P, w.y2, params + base + lay.l_ln2_g, Q, drop ? R : nullptr, g + lay.l_ln2_g, g + lay.l_ln2_b, g + lay.l_b2, M, H,
+                  cfg.ln_eps, 0, drop, site_h2(l), dc, f32, s));
+    MV_TRY(linear_wgrad(dY2d, H, w.g1, M, H, I, base + lay.l_w2, s));
+    MV_TRY(linear_dgrad(dY2d, H, M, H, base + lay.l_w2, I, dh1, EPI_DGELU, w.h1, s));
+    MV_TRY(colsum_add(dh1, I, M, I, g + lay.l_b1, f32, s));
+    MV_TRY(linear_wgrad(dh1, I, w.x1, M, I, H, base + lay.l_w1, s));
+    MV_TRY(linear_dgrad(dh1, I, M, I, base + lay.l_w1, H, P, EPI_RESID, Q, s));          // P = d(x1)
+    // LN1: y1 -> x1
+    void* dY1d = drop ? R : Q;
+    MV_TRY(ln_bwd(P, w.y1, params + base + lay.l_ln1_g, Q, drop ? R : nullptr, g + lay.l_ln1_g, g + lay.l_ln1_b, g + lay.l_bo, M, H,
+                  cfg.ln_eps, 0, drop, site_h1(l), dc, f32, s));
+    MV_TRY(linear_wgrad(dY1d, H, w.ctx, M, H, H, base + lay.l_wo, s));
+    MV_TRY(linear_dgrad(dY1d, H, M, H, base + lay.l_wo, H, dctx, EPI_NONE, nullptr, s));
+    AttnArgs aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
+    aa.dctx = dctx; aa.dqkv = dqkv; aa.dq_acc = dq_acc; aa.delta = delta;
+    aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
+    MV_TRY(f32 ? attention_bwd_simt(aa, s) : attention_bwd_tc05(aa, s));
+    MV_TRY(colsum_add(dqkv, 3 * H, M, 3 * H, g + lay.l_bqkv, f32, s));
+    MV_TRY(linear_wgrad(dqkv, 3 * H, x[l], M, 3 * H, H, base + lay.l_wqkv, s));
+    MV_TRY(linear_dgrad(dqkv, 3 * H, M, 3 * H, base + lay.l_wqkv, H, P, EPI_RESID, Q, s));   // P = d(x[l])
+    MV_TRY(bucket_done(static_cast<size_t>(cfg.layers - l), allreduce, s));
+  }
+
+  // --- embeddings: dropout-bwd + LN-bwd, scatter into the tables, image-projection wgrad ---
+  MV_TRY(ln_bwd(P, emb_sum, params + lay.emb_ln_g, Q, nullptr, grads + lay.emb_ln_g, grads + lay.emb_ln_b, nullptr, M, H, cfg.ln_eps,
+                drop, 0, SITE_EMB, dc, f32, s));
+  EmbedBwdArgs eb;
+  eb.B = B; eb.L = L; eb.H = H; eb.N = N; eb.T = T; eb.A = A; eb.V = cfg.vocab;
+  eb.cls_tok = reinterpret_cast<const int64_t*>(b.cls_tok); eb.sep_tok = reinterpret_cast<const int64_t*>(b.sep_tok);
+  eb.input_ids = reinterpret_cast<const int64_t*>(b.input_ids); eb.segment = reinterpret_cast<const int64_t*>(b.segment);
+  eb.region_idx = reinterpret_cast<const int64_t*>(b.region_idx);
+  eb.dsum = Q; eb.d_word = grads + lay.word; eb.d_pos = grads + lay.pos; eb.d_type = grads + lay.type; eb.d_proj = dproj; eb.pad_id = 0;
+  MV_TRY(embed_bwd_scatter(eb, f32, s));
+  MV_TRY(colsum_add(dproj, H, B * N, H, grads + lay.img_b, f32, s));
+  MV_TRY(linear_wgrad(dproj, H, feats_g, B * N, H, cfg.img_hidden, lay.img_w, s));
+  MV_TRY(bucket_done(buckets.size() - 1, allreduce, s));
+  return 0;
+}
+
+// prediction_scores for EVERY position (reference semantics, models/cxrbert_origin.py:147): [B*L, ld] fp32
+int Engine::full_logits(const mv_batch& b, float* out, int64_t ld, cudaStream_t s) {
+  const int H = cfg.hidden, M = b.B * L;
+  MV_REQUIRE(ld >= cfg.vocab && ld % 4 == 0, "full_logits: ld must be >= vocab and a multiple of 4");
+  MV_TRY(ensure_mlm(M));
+  const DropoutCfg dc = make_dropout(0.f, 0);
+  const void* seq = x[cfg.layers];
+  MV_TRY(linear_fwd(seq, M, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
+  MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, M, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
+  MV_TRY(linear_fwd(t_ln, M, H, lay.word, cfg.vocab, lay.mlm_bias, out, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, ld));
+  return 0;
+}
+
+}  // namespace mv

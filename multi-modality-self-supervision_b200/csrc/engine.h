@@ -1,0 +1,76 @@
+// engine.h — the per-GPU engine behind mv_handle: flat parameter arena layout, activation workspaces, the
+// forward / backward / optimizer drivers of the MedViLL pre-training step, and the NCCL gradient exchange.
+#pragma once
+#include <vector>
+
+#include "../../include/medvill_sm100.h"
+#include "gemm.h"
+#include "kernels.h"
+
+namespace mv {
+
+int layout_compute(const mv_config& c, mv_layout* out);
+
+struct Bucket { int64_t offset, count; };
+// gradient buckets in the order backward finishes them: heads tail block, layers L-1..0, embeddings head block
+std::vector<Bucket> bucket_plan(const mv_config& c, const mv_layout& lay);
+
+struct LayerWs {
+  void *qkv, *ctx, *y1, *x1, *h1, *g1, *y2;
+  float* lse;
+};
+
+struct NcclApi;
+
+struct Engine {
+  mv_config cfg;
+  mv_layout lay;
+  int f32 = 0;          // activation dtype is fp32 (check mode)
+  size_t es = 2;        // bytes per activation element
+  int L = 0, A = 0, T = 0, nh = 0, Vpad = 0;
+
+  // borrowed arenas
+  float* params = nullptr; float* grads = nullptr; float* adam_m = nullptr; float* adam_v = nullptr; bf16* shadow = nullptr;
+
+  // owned workspaces
+  std::vector<void*> allocs;
+  std::vector<void*> x;          // [layers + 1] : x[0] = embedding output, x[l+1] = output of layer l
+  std::vector<LayerWs> lw;
+  void *emb_sum = nullptr, *proj = nullptr, *feats_g = nullptr;
+  void *cls_rows = nullptr, *pooled = nullptr, *d_pre = nullptr, *d_cls = nullptr;
+  float* itm_logits = nullptr;
+  void *dxa = nullptr, *dxb = nullptr, *dxc = nullptr, *dh1 = nullptr, *dqkv = nullptr, *dctx = nullptr, *dproj = nullptr;
+  float *dq_acc = nullptr, *delta = nullptr;
+  int64_t* zero_idx = nullptr;     // [1] = {0}: gather/scatter of the [CLS] rows
+  mv_step_stats* stats = nullptr;    // device
+  mv_step_stats* stats_host = nullptr;  // pinned
+  // MLM head workspace (grown on demand)
+  int mlm_cap = 0;
+  void *rows_h = nullptr, *t_pre = nullptr, *t_act = nullptr, *t_ln = nullptr, *dlogits = nullptr, *d_tln = nullptr,
+       *d_tact = nullptr, *d_tpre = nullptr, *d_rows = nullptr;
+  float* logits = nullptr; float* row_lse = nullptr; int* row_argmax = nullptr;
+
+  // data-parallel state
+  NcclApi* nccl = nullptr; void* comm = nullptr; int rank = 0, world = 1;
+  cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool comm_pending = false;
+  std::vector<Bucket> buckets;
+
+  int init(const mv_config& c);
+  void destroy();
+  int ensure_mlm(int n);
+  int alloc(void** p, size_t bytes);
+
+  const void* W(int64_t off) const { return f32 ? static_cast<const void*>(params + off) : static_cast<const void*>(shadow + off); }
+  int gemm(const GemmDesc& d, cudaStream_t s) { return f32 ? gemm_f32_simt(d, s) : gemm_bf16_tc05(d, s); }
+  int linear_fwd(const void* X, int M, int K, int64_t w_off, int N, int64_t b_off, void* Y, int epi, void* pre,
+                 const void* resid, int drop_on, uint32_t site, const DropoutCfg& dc, cudaStream_t s, int y_f32 = 0, long ldy = 0);
+  int linear_dgrad(const void* dY, long lddy, int M, int N, int64_t w_off, int K, void* dX, int epi, const void* extra, cudaStream_t s);
+  int linear_wgrad(const void* dY, long lddy, const void* X, int M, int N, int K, int64_t w_off, cudaStream_t s);
+
+  int forward(const mv_batch& b, cudaStream_t s);
+  int backward(const mv_batch& b, int allreduce, cudaStream_t s);
+  int full_logits(const mv_batch& b, float* out, int64_t ld, cudaStream_t s);
+  int bucket_done(size_t idx, int allreduce, cudaStream_t s);
+};
+
+}  // namespace mv

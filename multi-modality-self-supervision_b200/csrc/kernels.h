@@ -10,11 +10,11 @@ namespace mv {
 // ---- joint embedding: [CLS] + regions + [SEP] + text  (models/cxrbert_origin.py:112-125, 22-35; upstream BertEmbeddings)
 struct EmbedArgs {
   int B, L, H, N, T, A;              // A = N + 2, L = A + T
-  const long long* cls_tok;          // [B]      int64 (reference dtype)
-  const long long* sep_tok;          // [B]
-  const long long* input_ids;        // [B, T]
-  const long long* segment;          // [B, T]
-  const long long* region_idx;       // [N]      sampled grid positions (models/image.py:64-69)
+  const int64_t* cls_tok;          // [B]      int64 (reference dtype)
+  const int64_t* sep_tok;          // [B]
+  const int64_t* input_ids;        // [B, T]
+  const int64_t* segment;          // [B, T]
+  const int64_t* region_idx;       // [N]      sampled grid positions (models/image.py:64-69)
   const float* word; const float* pos; const float* type;   // fp32 master tables
   const float* gamma; const float* beta; float eps;
   const void* proj;                  // [B*N, H] activation dtype: img projection + bias (GEMM output)
@@ -26,8 +26,8 @@ int embed_ln_fwd(const EmbedArgs& a, int f32, cudaStream_t s);
 
 struct EmbedBwdArgs {
   int B, L, H, N, T, A, V;
-  const long long* cls_tok; const long long* sep_tok; const long long* input_ids; const long long* segment;
-  const long long* region_idx;
+  const int64_t* cls_tok; const int64_t* sep_tok; const int64_t* input_ids; const int64_t* segment;
+  const int64_t* region_idx;
   const void* dsum;                  // [B*L, H] gradient w.r.t. the pre-LN sum (output of ln_bwd)
   float* d_word; float* d_pos; float* d_type;   // fp32 gradient tables (atomically accumulated)
   void* d_proj;                      // [B*N, H] gradient of the projected image rows (activation dtype)
@@ -48,24 +48,24 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx
 // ---- small utilities
 int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, cudaStream_t s);   // out[c] += sum_r x[r,c]
 // dst[i,:] = src[(i / period) * stride + idx[i % period], :]
-int gather_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int f32,
+int gather_rows(const void* src, void* dst, const int64_t* idx, int n, int period, long stride, int H, int f32,
                 cudaStream_t s);
 // dst[(i / period) * stride + idx[i % period], :] (+)= src[i,:]
-int scatter_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int add,
+int scatter_rows(const void* src, void* dst, const int64_t* idx, int n, int period, long stride, int H, int add,
                  int f32, cudaStream_t s);
 int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaStream_t s);          // dx = dy * gelu'(pre)
 int cast_f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t s);
 int cast_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t s);
 int mask_dump(const unsigned char* mode, const int* t_len, int B, int A, int L, unsigned char* out, cudaStream_t s);
 // derive (mode, t_len) from an explicit [B,L,L] (or [B,L]) int64 mask and count cells that differ from the predicate
-int mask_classify(const long long* mask, int dims, int B, int A, int L, unsigned char* mode, int* t_len,
+int mask_classify(const int64_t* mask, int dims, int B, int A, int L, unsigned char* mode, int* t_len,
                   int* mismatches, cudaStream_t s);
 
 // ---- losses (models/train_origin.py:62-63,118-126) and step metrics (:133-146)
 struct CeArgs {
   int n, V; long ldv;
   const float* logits;               // [n, ldv] fp32
-  const long long* labels;           // [n]
+  const int64_t* labels;           // [n]
   void* dlogits;                     // [n, ldv] activation dtype: (softmax - onehot) * gscale, pad columns zeroed
   float gscale;                      // 1 / (#labelled tokens in the GLOBAL batch)
   float* loss_sum;                   // += sum_i (lse_i - logit_i[label_i])
@@ -78,7 +78,7 @@ struct ItmArgs {
   int B, H;
   const void* pooled;                // [B, H] activation dtype, tanh output
   const float* w; const float* b;    // [2, H], [2]
-  const long long* labels;           // [B]
+  const int64_t* labels;           // [B]
   float gscale;                      // 1 / (GLOBAL batch)
   float* logits;                     // [B, 2] fp32 out
   float* loss_sum; int* correct;

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(256) itm_kernel(const ItmArgs a) {
     for (int w = 0; w < 8; ++w) { z0 += s_red[0][w]; z1 += s_red[1][w]; }
     a.logits[2 * b] = z0;
     a.logits[2 * b + 1] = z1;
+    if (a.labels == nullptr) { s_dl[0] = 0.f; s_dl[1] = 0.f; }   // forward-only: logits are all that is asked
+    else {
     const int y = static_cast<int>(a.labels[b]);
     const float mx = fmaxf(z0, z1);
     const float e0 = __expf(z0 - mx), e1 = __expf(z1 - mx);
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(256) itm_kernel(const ItmArgs a) {
     s_dl[0] = d0;
     s_dl[1] = d1;
     if (a.d_pre) { atomicAdd(a.db, d0); atomicAdd(a.db + 1, d1); }
+    }
   }
   __syncthreads();
   if (a.d_pre) {
@@ -164,7 +167,8 @@ int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s) {
 
 int itm_head_fwd_bwd(const ItmArgs& a, int f32, cudaStream_t s) {
   if (a.B <= 0) return 0;
-  MV_REQUIRE(a.pooled && a.w && a.b && a.labels && a.logits && a.loss_sum && a.correct, "itm: null argument");
+  MV_REQUIRE(a.pooled && a.w && a.b && a.logits && a.loss_sum && a.correct, "itm: null argument");
+  MV_REQUIRE(a.labels || !a.d_pre, "itm: backward needs labels");
   if (f32) itm_kernel<float><<<a.B, 256, 0, s>>>(a); else itm_kernel<bf16><<<a.B, 256, 0, s>>>(a);
   MV_CUDA_CHECK(cudaGetLastError());
   return 0;

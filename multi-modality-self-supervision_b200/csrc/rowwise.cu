@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
 
 template <typename T>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ src, T* __restrict__ dst,
-                                                          const long long* __restrict__ idx, int n, int period,
+                                                          const int64_t* __restrict__ idx, int n, int period,
                                                           long stride, int H) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const T* __restrict__ 
 
 template <typename T>
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const T* __restrict__ src, T* __restrict__ dst,
-                                                           const long long* __restrict__ idx, int n, int period,
+                                                           const int64_t* __restrict__ idx, int n, int period,
                                                            long stride, int H, int add) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
@@ -365,14 +365,14 @@ __global__ void mask_dump_kernel(const unsigned char* mode, const int* t_len, in
 }
 
 // One CTA per sample: probe three cells to pick the mode, count row 0 for t_len, then verify every cell.
-__global__ void __launch_bounds__(256) mask_classify_kernel(const long long* mask, int dims, int B, int A, int L,
+__global__ void __launch_bounds__(256) mask_classify_kernel(const int64_t* mask, int dims, int B, int A, int L,
                                                             unsigned char* mode_out, int* tlen_out, int* mismatches) {
   const int b = blockIdx.x;
   __shared__ int s_mode, s_tlen, s_cnt;
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
   if (dims == 2) {  // [B, L] key-padding mask: bidirectional
-    const long long* m = mask + static_cast<long>(b) * L;
+    const int64_t* m = mask + static_cast<long>(b) * L;
     int c = 0;
     for (int k = threadIdx.x; k < L; k += blockDim.x) c += m[k] != 0;
     atomicAdd(&s_cnt, c);
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(256) mask_classify_kernel(const long long* mas
     for (int k = threadIdx.x; k < L; k += blockDim.x) bad += (m[k] != 0) != mask_allowed(MODE_BIDIR, 0, k, A, s_tlen);
     if (bad) atomicAdd(mismatches, bad);
   } else {
-    const long long* m = mask + static_cast<long>(b) * L * L;
+    const int64_t* m = mask + static_cast<long>(b) * L * L;
     int c = 0;
     for (int k = threadIdx.x; k < L; k += blockDim.x) c += m[static_cast<long>(L - 1) * L + k] != 0;  // last text row
     atomicAdd(&s_cnt, c);
@@ -478,7 +478,7 @@ int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, 
   return 0;
 }
 
-int gather_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int f32,
+int gather_rows(const void* src, void* dst, const int64_t* idx, int n, int period, long stride, int H, int f32,
                 cudaStream_t s) {
   if (n <= 0) return 0;
   MV_REQUIRE(H % 8 == 0, "gather_rows: H %% 8");
@@ -488,7 +488,7 @@ int gather_rows(const void* src, void* dst, const long long* idx, int n, int per
   return 0;
 }
 
-int scatter_rows(const void* src, void* dst, const long long* idx, int n, int period, long stride, int H, int add,
+int scatter_rows(const void* src, void* dst, const int64_t* idx, int n, int period, long stride, int H, int add,
                  int f32, cudaStream_t s) {
   if (n <= 0) return 0;
   MV_REQUIRE(H % 8 == 0, "scatter_rows: H %% 8");
@@ -528,7 +528,7 @@ int mask_dump(const unsigned char* mode, const int* t_len, int B, int A, int L, 
   return 0;
 }
 
-int mask_classify(const long long* mask, int dims, int B, int A, int L, unsigned char* mode, int* t_len,
+int mask_classify(const int64_t* mask, int dims, int B, int A, int L, unsigned char* mode, int* t_len,
                   int* mismatches, cudaStream_t s) {
   MV_REQUIRE(dims == 2 || dims == 3, "mask_classify: mask must be [B,L] or [B,L,L]");
   MV_CUDA_CHECK(cudaMemsetAsync(mismatches, 0, sizeof(int), s));

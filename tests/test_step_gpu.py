@@ -1,0 +1,114 @@
+"""GPU parity of the whole pre-training step (forward, losses, metrics, backward, AdamW) through the C ABI against
+the golden fixtures produced by the real reference (tests/golden, oracle/make_golden.py) and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): fp32 check mode 1e-4 relative on losses/logits; bf16 1e-2 relative.
+MLM token selection (labelled rows, argmax) and masks are bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import medvill_oracle as orc
+from tests.util import dims_from_cfg, golden_batch, load_golden, oracle_feats, summarize
+
+pytestmark = pytest.mark.gpu
+
+TINY = ["tiny_bar", "tiny_s2s", "tiny_noncross", "tiny_bidir", "tiny_mixed"]
+
+
+def run_step(name, precision):
+    import medvill_b200 as m
+
+    g, cfg = load_golden(name)
+    batch = golden_batch(g, cfg)
+    params = orc.synth_params(cfg, seed=0)
+    feats = oracle_feats(params, batch)
+    eng = m.PretrainEngine(dims_from_cfg(cfg), "cuda:0", precision=precision, max_batch=int(g["B"]))
+    eng.load_params(params)
+    b = eng.make_batch(cls_tok=batch["cls_tok"], input_ids=batch["input_ids"], segment=batch["segment"], sep_tok=batch["sep_tok"],
+                       mode=batch["mode"], t_len=batch["t_len"], region_idx=batch["region_idx"], feats=feats,
+                       txt_labels=batch["txt_labels"], is_aligned=batch["is_aligned"], seed=1, train=True)
+    assert np.array_equal(b.lab_rows.cpu().numpy(), g["lab_rows"][:, 0] * cfg.L + g["lab_rows"][:, 1])   # bit-exact token selection
+    eng.zero_grads()
+    eng.stats_reset()
+    eng.forward(b)
+    st = eng.read_stats()
+    out = dict(g=g, cfg=cfg, eng=eng, b=b, st=st, params=params)
+    out["mlm_loss"] = st["mlm_loss_sum"] / b.n_lab
+    out["itm_loss"] = st["itm_loss_sum"] / b.B
+    out["itm_logits"] = eng.itm_logits(b.B).numpy()
+    out["row_lse"] = eng.peek("row_lse", shape=(b.n_lab,), dtype=torch.float32).numpy()
+    out["row_argmax"] = eng.peek("row_argmax", shape=(b.n_lab,), dtype=torch.int32).numpy()
+    ld = eng.layout["vocab_padded"]
+    logits = eng.peek("logits", shape=(b.n_lab, ld), dtype=torch.float32).numpy()
+    out["lab_logits"] = logits[:, g["lab_cols"]]
+    eng.backward(b)
+    torch.cuda.synchronize()
+    return out
+
+
+def check_forward(o, tol):
+    g = o["g"]
+    assert abs(o["mlm_loss"] - float(g["mlm_loss"])) <= tol * abs(float(g["mlm_loss"])), (o["mlm_loss"], float(g["mlm_loss"]))
+    assert abs(o["itm_loss"] - float(g["itm_loss"])) <= tol * max(1.0, abs(float(g["itm_loss"]))), (o["itm_loss"], float(g["itm_loss"]))
+    scale = np.abs(g["lab_logits"]).max()
+    assert np.abs(o["lab_logits"] - g["lab_logits"]).max() <= tol * scale
+    assert np.abs(o["itm_logits"] - g["itm_logits"]).max() <= tol * max(1.0, np.abs(g["itm_logits"]).max())
+    assert np.abs(o["row_lse"] - g["lab_lse"]).max() <= tol * np.abs(g["lab_lse"]).max()
+    assert o["st"]["itm_correct"] == int(g["itm_correct"])
+
+
+def check_grads(o, tol_norm, tol_probe):
+    g, eng = o["g"], o["eng"]
+    names = [str(n) for n in g["grad_names"]]
+    worst = 0.0
+    for i, n in enumerate(names):
+        got = summarize(eng.view(n, eng.grads))
+        ref = g["grad_summary"][i]
+        nrm = max(ref[2], 1e-7)
+        e_norm = abs(got[2] - ref[2]) / nrm
+        e_probe = np.abs(got[3:] - ref[3:]).max() / max(np.abs(ref[3:]).max(), 1e-3 * nrm, 1e-8)
+        worst = max(worst, e_norm)
+        assert e_norm <= tol_norm, "grad norm %s: got %.6e ref %.6e" % (n, got[2], ref[2])
+        assert e_probe <= tol_probe, "grad probes %s: got %s ref %s" % (n, got[3:], ref[3:])
+    return worst
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_step_fp32_check_mode_tiny(name):
+    o = run_step(name, "fp32")
+    check_forward(o, 1e-4)
+    assert np.array_equal(o["row_argmax"], o["g"]["lab_argmax"])
+    assert o["st"]["mlm_correct"] == int(o["g"]["mlm_correct"])
+    check_grads(o, 2e-3, 5e-3)
+    # one AdamW step (HF-3.x formula, lr 1e-5): parameter deltas
+    eng, g = o["eng"], o["g"]
+    before = {n: eng.view(n).clone() for n in eng.pmap}
+    eng.adamw_step(lr=1e-5)
+    torch.cuda.synchronize()
+    for i, n in enumerate(str(x) for x in g["grad_names"]):
+        got = summarize(eng.view(n) - before[n])
+        ref = g["adamw_summary"][i]
+        # key-bias gradients are analytically zero, so Adam only normalises rounding noise there: absolute floor
+        assert abs(got[2] - ref[2]) <= 2e-2 * ref[2] + 1e-8 * np.sqrt(eng.view(n).numel()), (n, got[2], ref[2])
+    assert float(eng.grads.abs().max()) == 0.0     # optimizer.zero_grad() fused into the step
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_step_bf16_tiny(name):
+    o = run_step(name, "bf16")
+    check_forward(o, 1e-2)
+    check_grads(o, 6e-2, 0.25)
+
+
+def test_step_fp32_config1():
+    o = run_step("config1_bar", "fp32")
+    check_forward(o, 1e-4)
+    assert np.array_equal(o["row_argmax"], o["g"]["lab_argmax"])
+    check_grads(o, 3e-3, 1e-2)
+
+
+def test_step_bf16_config1():
+    o = run_step("config1_bar", "bf16")
+    check_forward(o, 1e-2)
+    check_grads(o, 6e-2, 0.3)
