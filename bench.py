@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py — MedViLL MLM+ITM pre-training throughput on N B200s (one process per GPU), plus the roofline of the
+dominant kernel family, the end-to-end number through the public API with host buffers, and the CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 64] [--impl ours|reference]
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" = one full pre-training step of BASELINE.json configs[1]: ResNet-50 trunk (cuDNN, frozen, train-mode BN) ->
+region gather + projection -> joint embedding -> 12 BERT layers (tcgen05 GEMMs + fused masked attention, BAR mask,
+dropout 0.1 on) -> pooler/ITM + MLM heads + both CE losses -> full backward -> (bucketed NCCL all-reduce) -> AdamW.
+Synthetic data (seeded), random-init weights, bf16 compute with fp32 master weights.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MLM+ITM pretrain samples/sec"
+UNIT = "samples/s"
+# dense algorithmic FLOPs per sample of one training step: encoder linears + attention, fwd + dgrad + wgrad
+ENC_FLOPS_PER_SAMPLE = 2.4321e11
+
+
+def workload(args, n):
+    return {"workload": "MedViLL pretrain step (MLM+ITM), BERT-base, Bidirectional Auto-Regressive mask, batch %d/GPU, synthetic "
+                        "512x512 CXR + random report tokens, N=180 regions, S=253 (L=436), dropout 0.1, AdamW" % args.batch,
+            "global_batch": args.batch * n, "joint_len": 436, "parallelism": "dp%d" % n,
+            "l2": "no flush needed: one step streams ~10 GB of saved activations (>> 126 MB L2)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz, self.stop_flag = [], set(), None, False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        names = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                 0x80: "hw_power_brake_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        import statistics
+
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_step_rate(steps, warmup, batch=2):
+    """The reference's CPU path restated (oracle/medvill_oracle.py, pinned against the real reference): fp32, all host
+    threads, BAR mask, forward + CE losses + backward + HF-AdamW, B=2 (BASELINE.json configs[0])."""
+    import torch
+
+    from oracle import medvill_oracle as orc
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = orc.Cfg()
+    params = orc.synth_params(cfg, seed=0)
+    state = {}
+    times = []
+    for i in range(warmup + steps):
+        batch_i = orc.synthetic_batch(cfg, batch, seed=1000 + i, mode=orc.MODE_BAR)
+        t0 = time.perf_counter()
+        out = orc.loss_and_grads(params, batch_i, cfg)
+        upd = orc.adamw_step({n: params[n] for n in out["grads"]}, out["grads"], state, lr=1e-5, step=i + 1)
+        params.update(upd)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, med, os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 1))
+    rate, med, cores = cpu_reference_step_rate(steps, warm)
+    n = args.gpus
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": n, "steps": steps, "warmup": warm,
+            "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload(args, n),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d timed steps of the B=2 (configs[0]) step after %d warm-up, median" % (steps, warm)},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import types
+
+    import torch
+
+    import medvill_b200  # noqa: F401
+    from medvill_b200 import _lib
+    from medvill_b200.config import BertConfig
+    from medvill_b200.data.prefetch import DevicePrefetcher
+    from medvill_b200.data.synthetic import as_tuple, synthetic_batch
+    from medvill_b200.models import CXRBERT
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libmedvill_sm100 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    margs = types.SimpleNamespace(img_hidden_sz=2048, embedding_size=768, hidden_size=768, dropout_prob=args.dropout,
+                                  img_encoder="random-pixel", num_image_embeds=180, img_size=512, seq_len=253, lr=1e-5,
+                                  precision="bf16", max_micro_batch=B, seed=123)
+    torch.manual_seed(0)
+    model = CXRBERT(BertConfig.from_pretrained("bert-base-uncased"), margs).to(dev)
+    model.train()
+    eng = model.engine(B)
+    if world > 1:
+        def bcast(raw):
+            box = [raw]
+            torch.distributed.broadcast_object_list(box, src=0)
+            return box[0]
+        eng.comm_init(rank, world, bcast)
+        torch.distributed.broadcast(eng.params, src=0)
+        model.sync_params()
+
+    # a small pool of distinct synthetic batches (pinned host memory), cycled
+    pool = [synthetic_batch(B, seed=123 + 17 * rank + i, pin=True) for i in range(2)]
+    dev_pool = [{k: (v if k == "txt_labels" else v.to(dev)) for k, v in b.items()} for b in pool]
+
+    def step_device(i):
+        b = dev_pool[i % len(dev_pool)]
+        return model.pretrain_step(b["cls_tok"], b["input_ids"], b["txt_labels"], None, b["image"], b["segment"], b["is_aligned"],
+                                   b["sep_tok"], mode=b["mode"], t_len=b["t_len"])
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        out = step_device(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.lib().mv_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step_device(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.lib().mv_launch_count() - launches0
+    sampler.stop_flag = True
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host tensors -> prefetcher -> pretrain_step -> loss on the host ----
+    class Cycle:
+        def __init__(self, n):
+            self.n = n
+
+        def __len__(self):
+            return self.n
+
+        def __iter__(self):
+            for i in range(self.n):
+                yield as_tuple(pool[i % len(pool)])
+
+    def run_e2e(n):
+        pf = DevicePrefetcher(Cycle(n), dev, host_indices=(2,))
+        last = None
+        for data in pf:
+            cls_tok, input_ids, txt_labels, attn, img, segment, is_aligned, sep_tok, _ = data
+            last = model.pretrain_step(cls_tok, input_ids, txt_labels, attn, img, segment, is_aligned, sep_tok,
+                                       mode=attn[:, 0].to(torch.uint8), t_len=attn[:, 1].to(torch.int32))
+        return pf.bytes_last, last
+
+    run_e2e(max(1, min(2, args.warmup)))
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    h2d, last = run_e2e(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    e2e_value = B * world * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM): CUDA events around every launch, 2 extra steps ----
+    import ctypes as C
+
+    _lib.check(_lib.lib().mv_profile(eng._h, 1))
+    for i in range(2):
+        step_device(i)
+    pms, pfl, pcn = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int32 * 3)()
+    _lib.check(_lib.lib().mv_profile_read(eng._h, pms, pfl, pcn))
+    _lib.check(_lib.lib().mv_profile(eng._h, 0))
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    gemm_tf = pfl[0] / (pms[0] * 1e-3) / 1e12 if pms[0] > 0 else 0.0
+    step_ms = ms / args.steps
+    enc_tf = ENC_FLOPS_PER_SAMPLE * B / (step_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_tc05_kernel (all %d launches of a step)" % (pcn[0] // 2), "achieved": gemm_tf,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                "gemm_ms_per_step": pms[0] / 2, "attn_fwd_ms_per_step": pms[1] / 2, "attn_bwd_ms_per_step": pms[2] / 2,
+                "attn_fwd_tflops_dense": pfl[1] / (pms[1] * 1e-3) / 1e12 if pms[1] > 0 else None,
+                "attn_bwd_tflops_dense": pfl[2] / (pms[2] * 1e-3) / 1e12 if pms[2] > 0 else None,
+                "encoder_dense_tflops_over_whole_step": enc_tf, "encoder_frac_of_peak_over_whole_step": enc_tf / peak_tf}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, med, cores = cpu_reference_step_rate(3, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "3 timed steps (median) of the B=2 configs[0] step on the host, oracle port of the reference, fp32"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": workload(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
+            "last_loss": out["loss"]}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

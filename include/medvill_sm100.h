@@ -126,6 +126,11 @@ int mv_itm_logits(mv_handle* h, float* host_out, int32_t B, void* stream);
 int mv_full_logits(mv_handle* h, const mv_batch* b, float* logits, int64_t ld, void* stream);  /* [B*L, ld] fp32    */
 int mv_peek(mv_handle* h, const char* name, int32_t layer, void* dst, int64_t max_bytes, int64_t* bytes, void* stream);
 
+/* ---- measurement aids (bench.py): launch counter; CUDA-event timing per kernel family on the launch stream ---- */
+long mv_launch_count(void);                                              /* kernels launched by this library so far  */
+int mv_profile(mv_handle* h, int32_t enable);
+int mv_profile_read(mv_handle* h, double ms[3], double flops[3], int32_t count[3]);  /* 0 GEMM, 1 attn fwd, 2 attn bwd */
+
 /* ---- data-parallel gradient exchange (one process per GPU) ---- */
 int mv_comm_unique_id(uint8_t out[128]);
 int mv_comm_init(mv_handle* h, const uint8_t id[128], int32_t rank, int32_t world);

@@ -77,6 +77,9 @@ SYMBOLS = {
     "mv_itm_logits": (_I, [_P, _P, _I, _P]),
     "mv_full_logits": (_I, [_P, C.POINTER(mv_batch), _P, _L, _P]),
     "mv_peek": (_I, [_P, C.c_char_p, _I, _P, _L, C.POINTER(_L), _P]),
+    "mv_launch_count": (C.c_long, []),
+    "mv_profile": (_I, [_P, _I]),
+    "mv_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
     "mv_comm_unique_id": (_I, [_P]),
     "mv_comm_init": (_I, [_P, _P, _I, _I]),
     "mv_comm_allreduce_f32": (_I, [_P, _P, _L, _P]),

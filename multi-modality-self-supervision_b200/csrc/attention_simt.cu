@@ -161,7 +161,7 @@ int attention_fwd_simt(const AttnArgs& a, cudaStream_t s) {
   MV_REQUIRE(a.qkv && a.ctx && a.lse && a.mode && a.t_len, "attention_fwd: null argument");
   dim3 grid(a.L, a.nh, a.B);
   attn_fwd_simt_kernel<<<grid, 128, a.L * sizeof(float), s>>>(a);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -169,9 +169,9 @@ int attention_bwd_simt(const AttnArgs& a, cudaStream_t s) {
   MV_REQUIRE(a.qkv && a.ctx && a.lse && a.dctx && a.dqkv && a.delta, "attention_bwd: null argument");
   dim3 grid(a.L, a.nh, a.B);
   attn_bwd_dq_simt_kernel<<<grid, 128, a.L * sizeof(float), s>>>(a);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   attn_bwd_dkv_simt_kernel<<<grid, 128, 2 * a.L * sizeof(float), s>>>(a);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 

@@ -463,7 +463,7 @@ int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s) {
   }
   dim3 grid((a.L + TQ - 1) / TQ, a.nh, a.B);
   attn_fwd_tc05_kernel<<<grid, 128, kFwdSmem, s>>>(tm, a);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -485,12 +485,12 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
   attn_delta_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, s>>>(static_cast<const bf16*>(a.dctx),
                                                                              static_cast<const bf16*>(a.ctx), a.delta,
                                                                              static_cast<int>(rows), a.L, a.nh);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
   attn_bwd_tc05_kernel<<<grid, 128, kBwdSmem, s>>>(tmQKV, tmDO, a);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 

@@ -169,6 +169,29 @@ int mv_peek(mv_handle* h, const char* name, int32_t layer, void* dst, int64_t ma
   return 0;
 }
 
+long mv_launch_count(void) { return mv::launch_count(); }
+
+int mv_profile(mv_handle* h, int32_t enable) {
+  MV_CHECK_HANDLE(h);
+  h->eng.profiling = enable != 0;
+  return 0;
+}
+
+// Sum the recorded event pairs per tag (0 GEMM, 1 attention fwd, 2 attention bwd); syncs, then clears the records.
+int mv_profile_read(mv_handle* h, double ms[3], double flops[3], int32_t count[3]) {
+  MV_CHECK_HANDLE(h);
+  MV_CUDA_CHECK(cudaDeviceSynchronize());
+  for (int i = 0; i < 3; ++i) { ms[i] = 0; flops[i] = 0; count[i] = 0; }
+  for (auto& r : h->eng.prof) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.tag >= 0 && r.tag < 3) { ms[r.tag] += t; flops[r.tag] += r.flops; count[r.tag] += 1; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  h->eng.prof.clear();
+  return 0;
+}
+
 int mv_comm_unique_id(uint8_t out[128]) { return nccl_unique_id(out); }
 int mv_comm_init(mv_handle* h, const uint8_t id[128], int32_t rank, int32_t world) {
   MV_CHECK_HANDLE(h);

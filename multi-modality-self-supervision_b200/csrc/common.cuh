@@ -15,6 +15,8 @@ namespace mv {
 void set_error(const char* fmt, ...);
 const char* last_error();
 int device_sm_count();
+void count_launch();          // every kernel launch of this library bumps one process-wide counter
+long launch_count();
 
 #define MV_CUDA_CHECK(expr)                                                                         \
   do {                                                                                              \
@@ -23,6 +25,13 @@ int device_sm_count();
       mv::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);    \
       return -2;                                                                                    \
     }                                                                                               \
+  } while (0)
+
+// after every <<<...>>>: count the launch, surface launch-configuration errors
+#define MV_LAUNCH_CHECK()                        \
+  do {                                           \
+    mv::count_launch();                          \
+    MV_CUDA_CHECK(cudaGetLastError());           \
   } while (0)
 
 #define MV_REQUIRE(cond, ...)          \

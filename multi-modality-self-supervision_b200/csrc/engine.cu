@@ -138,6 +138,22 @@ int engine_comm_sync(Engine* e, cudaStream_t s) {
 }
 
 // --------------------------------------------------------------------------------------------------------------------
+int Engine::prof_begin(int tag, double flops, cudaStream_t s) {
+  if (!profiling) return 0;
+  ProfRec r;
+  r.tag = tag; r.flops = flops;
+  MV_CUDA_CHECK(cudaEventCreate(&r.a));
+  MV_CUDA_CHECK(cudaEventCreate(&r.b));
+  MV_CUDA_CHECK(cudaEventRecord(r.a, s));
+  prof.push_back(r);
+  return 0;
+}
+int Engine::prof_end(cudaStream_t s) {
+  if (!profiling) return 0;
+  MV_CUDA_CHECK(cudaEventRecord(prof.back().b, s));
+  return 0;
+}
+
 int Engine::alloc(void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
@@ -294,7 +310,9 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     memset(&aa, 0, sizeof(aa));
     aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
     aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
+    MV_TRY(prof_begin(1, 4.0 * B * nh * static_cast<double>(L) * L * 64, s));
     MV_TRY(f32 ? attention_fwd_simt(aa, s) : attention_fwd_tc05(aa, s));
+    MV_TRY(prof_end(s));
     MV_TRY(linear_fwd(w.ctx, M, H, base + lay.l_wo, H, base + lay.l_bo, w.y1, EPI_BIAS_RESID, nullptr, x[l], drop, site_h1(l), dc, s));
     MV_TRY(ln_fwd(w.y1, w.x1, params + base + lay.l_ln1_g, params + base + lay.l_ln1_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s));
     MV_TRY(linear_fwd(w.x1, M, H, base + lay.l_w1, I, base + lay.l_b1, w.g1, EPI_BIAS_GELU, w.h1, nullptr, 0, 0, dc, s));
@@ -404,7 +422,9 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
     aa.dctx = dctx; aa.dqkv = dqkv; aa.dq_acc = dq_acc; aa.delta = delta;
     aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
+    MV_TRY(prof_begin(2, 10.0 * B * nh * static_cast<double>(L) * L * 64, s));
     MV_TRY(f32 ? attention_bwd_simt(aa, s) : attention_bwd_tc05(aa, s));
+    MV_TRY(prof_end(s));
     MV_TRY(colsum_add(dqkv, 3 * H, M, 3 * H, g + lay.l_bqkv, f32, s));
     MV_TRY(linear_wgrad(dqkv, 3 * H, x[l], M, 3 * H, H, base + lay.l_wqkv, s));
     MV_TRY(linear_dgrad(dqkv, 3 * H, M, 3 * H, base + lay.l_wqkv, H, P, EPI_RESID, Q, s));   // P = d(x[l])

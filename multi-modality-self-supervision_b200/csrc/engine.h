@@ -55,13 +55,26 @@ struct Engine {
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool comm_pending = false;
   std::vector<Bucket> buckets;
 
+  // optional per-kernel-family timing (CUDA events on the launch stream): tag 0 = tcgen05/SIMT GEMM, 1 = attention fwd,
+  // 2 = attention bwd.  Used by bench.py for the live roofline numbers; off by default.
+  struct ProfRec { cudaEvent_t a, b; int tag; double flops; };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  int prof_begin(int tag, double flops, cudaStream_t s);
+  int prof_end(cudaStream_t s);
+
   int init(const mv_config& c);
   void destroy();
   int ensure_mlm(int n);
   int alloc(void** p, size_t bytes);
 
   const void* W(int64_t off) const { return f32 ? static_cast<const void*>(params + off) : static_cast<const void*>(shadow + off); }
-  int gemm(const GemmDesc& d, cudaStream_t s) { return f32 ? gemm_f32_simt(d, s) : gemm_bf16_tc05(d, s); }
+  int gemm(const GemmDesc& d, cudaStream_t s) {
+    if (prof_begin(0, 2.0 * d.M * d.N * d.K, s)) return -2;
+    const int rc = f32 ? gemm_f32_simt(d, s) : gemm_bf16_tc05(d, s);
+    if (rc) return rc;
+    return prof_end(s);
+  }
   int linear_fwd(const void* X, int M, int K, int64_t w_off, int N, int64_t b_off, void* Y, int epi, void* pre,
                  const void* resid, int drop_on, uint32_t site, const DropoutCfg& dc, cudaStream_t s, int y_f32 = 0, long ldy = 0);
   int linear_dgrad(const void* dY, long lddy, int M, int N, int64_t w_off, int K, void* dX, int epi, const void* extra, cudaStream_t s);

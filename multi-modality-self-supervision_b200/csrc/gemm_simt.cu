@@ -107,7 +107,7 @@ int gemm_f32_simt(const GemmDesc& d, cudaStream_t stream) {
   p.drop_on = d.drop_on; p.drop_site = d.drop_site; p.drop = d.drop;
   dim3 grid((d.N + TN - 1) / TN, (d.M + TM - 1) / TM);
   gemm_f32_kernel<<<grid, 256, 0, stream>>>(p);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 

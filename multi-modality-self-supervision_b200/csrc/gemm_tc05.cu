@@ -377,7 +377,7 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
     attr_set = true;
   }
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmC2, p);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 

@@ -161,7 +161,7 @@ int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s) {
   if (a.n <= 0) return 0;
   MV_REQUIRE(a.logits && a.labels && a.loss_sum && a.correct, "mlm_ce: null argument");
   if (f32) mlm_ce_kernel<float><<<a.n, 256, 0, s>>>(a); else mlm_ce_kernel<bf16><<<a.n, 256, 0, s>>>(a);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -170,7 +170,7 @@ int itm_head_fwd_bwd(const ItmArgs& a, int f32, cudaStream_t s) {
   MV_REQUIRE(a.pooled && a.w && a.b && a.logits && a.loss_sum && a.correct, "itm: null argument");
   MV_REQUIRE(a.labels || !a.d_pre, "itm: backward needs labels");
   if (f32) itm_kernel<float><<<a.B, 256, 0, s>>>(a); else itm_kernel<bf16><<<a.B, 256, 0, s>>>(a);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -181,7 +181,7 @@ int adamw_step(const AdamArgs& a, cudaStream_t s) {
   const double bc2 = 1.0 - pow(static_cast<double>(a.beta2), a.step);
   const float step_size = static_cast<float>(a.lr * sqrt(bc2) / bc1);
   adamw_kernel<<<148 * 8, 256, 0, s>>>(a, step_size);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 

@@ -428,7 +428,7 @@ int embed_ln_fwd(const EmbedArgs& a, int f32, cudaStream_t s) {
   if (check_h(a.H)) return -1;
   const int rows = a.B * a.L;
   MV_DISPATCH_T(f32, (embed_ln_fwd_kernel<T><<<rows_grid(rows), 256, 0, s>>>(a)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -436,7 +436,7 @@ int embed_bwd_scatter(const EmbedBwdArgs& a, int f32, cudaStream_t s) {
   if (check_h(a.H)) return -1;
   const int rows = a.B * a.L;
   MV_DISPATCH_T(f32, (embed_bwd_scatter_kernel<T><<<rows_grid(rows), 256, 0, s>>>(a)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -446,7 +446,7 @@ int ln_fwd(const void* x, void* y, const float* gamma, const float* beta, int ro
   if (rows <= 0) return 0;
   MV_DISPATCH_T(f32, (ln_fwd_kernel<T><<<rows_grid(rows), 256, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(y), gamma,
                                                                        beta, rows, H, eps, drop_on, drop_site, drop)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -463,7 +463,7 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx
   MV_DISPATCH_T(f32, (ln_bwd_kernel<T><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
                                                                static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
                                                                dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -474,7 +474,7 @@ int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, 
   if (ysplit > 64) ysplit = 64;
   dim3 grid((cols + 255) / 256, ysplit);
   MV_DISPATCH_T(f32, (colsum_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, rows, cols, out)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -484,7 +484,7 @@ int gather_rows(const void* src, void* dst, const int64_t* idx, int n, int perio
   MV_REQUIRE(H % 8 == 0, "gather_rows: H %% 8");
   MV_DISPATCH_T(f32, (gather_rows_kernel<T><<<rows_grid(n), 256, 0, s>>>(static_cast<const T*>(src), static_cast<T*>(dst), idx, n,
                                                                          period, stride, H)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -494,7 +494,7 @@ int scatter_rows(const void* src, void* dst, const int64_t* idx, int n, int peri
   MV_REQUIRE(H % 8 == 0, "scatter_rows: H %% 8");
   MV_DISPATCH_T(f32, (scatter_rows_kernel<T><<<rows_grid(n), 256, 0, s>>>(static_cast<const T*>(src), static_cast<T*>(dst), idx, n,
                                                                           period, stride, H, add)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -505,26 +505,26 @@ int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaSt
   int grid = static_cast<int>((n8 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   MV_DISPATCH_T(f32, (dgelu_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(pre), static_cast<T*>(dx), n8)));
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
 int cast_f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t s) {
   if (n <= 0) return 0;
   cast_f2b_kernel<<<148 * 8, 256, 0, s>>>(src, dst, n);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 int cast_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t s) {
   if (n <= 0) return 0;
   cast_b2f_kernel<<<148 * 8, 256, 0, s>>>(src, dst, n);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
 int mask_dump(const unsigned char* mode, const int* t_len, int B, int A, int L, unsigned char* out, cudaStream_t s) {
   mask_dump_kernel<<<148 * 4, 256, 0, s>>>(mode, t_len, B, A, L, out);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 
@@ -533,7 +533,7 @@ int mask_classify(const int64_t* mask, int dims, int B, int A, int L, unsigned c
   MV_REQUIRE(dims == 2 || dims == 3, "mask_classify: mask must be [B,L] or [B,L,L]");
   MV_CUDA_CHECK(cudaMemsetAsync(mismatches, 0, sizeof(int), s));
   mask_classify_kernel<<<B, 256, 0, s>>>(mask, dims, B, A, L, mode, t_len, mismatches);
-  MV_CUDA_CHECK(cudaGetLastError());
+  MV_LAUNCH_CHECK();
   return 0;
 }
 

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -77,6 +78,10 @@ int tmap_encode_3d(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t d0
   MV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r);
   return 0;
 }
+
+static std::atomic<long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int device_sm_count() {
   static int sms = 0;

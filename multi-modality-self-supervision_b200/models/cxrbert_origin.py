@@ -1,0 +1,425 @@
+"""Drop-in mirror of /root/reference/models/cxrbert_origin.py for the pre-training path.
+
+Same class names, constructor / forward signatures, attribute tree and `state_dict` keys as the reference
+(`CXRBERT`, `CXRBertEncoder`, `ImageBertEmbeddings`, `BertPreTrainingHeads`, `ImageTextMatching`), but the
+modules are *parameter containers*: every trainable tensor is a view into the flat arena of a `PretrainEngine` and all
+arithmetic runs in libmedvill_sm100.so (tcgen05 GEMMs, fused masked attention, fused LN / embedding / CE kernels).
+There is no PyTorch fallback: on a CPU device `forward` raises.
+
+What differs from the reference, deliberately:
+  * the attention mask tensor is accepted for compatibility, but is reduced on the device to (mode, t_len) per sample
+    and *validated* against the closed-form predicate; arbitrary masks are rejected loudly;
+  * `CXRBertEncoder.forward` returns `None` for the attentions slot (the reference keeps 7 GB of them and drops them);
+  * training uses `CXRBERT.pretrain_step` (fused forward + losses + backward + all-reduce + AdamW); `forward` returns
+    detached tensors.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..config import BertConfig
+from ..engine import EngineDims, PretrainEngine
+from .image import ImageEncoder_cnn
+
+_FUSED_MSG = ("%s.forward is fused into libmedvill_sm100 (mv_forward); call CXRBERT / CXRBertEncoder.forward or "
+              "CXRBERT.pretrain_step instead")
+
+
+# ---- parameter containers with the upstream (HF BertModel) attribute names -------------------------------------------
+class _Embeddings(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size, padding_idx=getattr(config, "pad_token_id", 0))
+        self.position_embeddings = nn.Embedding(config.max_position_embeddings, config.hidden_size)
+        self.token_type_embeddings = nn.Embedding(config.type_vocab_size, config.hidden_size)
+        self.LayerNorm = nn.LayerNorm(config.hidden_size, eps=config.layer_norm_eps)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+
+    def forward(self, *a, **k):
+        raise RuntimeError(_FUSED_MSG % "txt_embeddings")
+
+
+class ImageBertEmbeddings(nn.Module):
+    """reference: models/cxrbert_origin.py:12-35 (shares LayerNorm / position / type tables with the text embeddings)"""
+
+    def __init__(self, args, embeddings):
+        super().__init__()
+        self.args = args
+        self.img_embeddings = nn.Linear(args.img_hidden_sz, args.embedding_size)
+        self.token_type_embeddings = embeddings.token_type_embeddings
+        self.LayerNorm = embeddings.LayerNorm
+        self.dropout = nn.Dropout(args.dropout_prob)
+        self.position_embeddings = embeddings.position_embeddings
+
+    def forward(self, input_imgs, img_pos, token_type_ids):
+        raise RuntimeError(_FUSED_MSG % "ImageBertEmbeddings")
+
+
+class _Dense(nn.Module):
+    def __init__(self, i, o):
+        super().__init__()
+        self.dense = nn.Linear(i, o)
+
+
+class _DenseLN(nn.Module):
+    def __init__(self, i, o, eps):
+        super().__init__()
+        self.dense = nn.Linear(i, o)
+        self.LayerNorm = nn.LayerNorm(o, eps=eps)
+
+
+class _SelfAttention(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.query, self.key, self.value = nn.Linear(H, H), nn.Linear(H, H), nn.Linear(H, H)
+
+
+class _Attention(nn.Module):
+    def __init__(self, H, eps):
+        super().__init__()
+        self.self = _SelfAttention(H)
+        self.output = _DenseLN(H, H, eps)
+
+
+class _Layer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        H, I = config.hidden_size, config.intermediate_size
+        self.attention = _Attention(H, config.layer_norm_eps)
+        self.intermediate = _Dense(H, I)
+        self.output = _DenseLN(I, H, config.layer_norm_eps)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.layer = nn.ModuleList([_Layer(config) for _ in range(config.num_hidden_layers)])
+
+
+def _init_bert_weights(module, std):
+    """upstream BertPreTrainedModel._init_weights: N(0, 0.02) linears/embeddings, zero biases, unit LayerNorm."""
+    for m in module.modules():
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(mean=0.0, std=std)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, nn.Embedding):
+            m.weight.data.normal_(mean=0.0, std=std)
+            if m.padding_idx is not None:
+                m.weight.data[m.padding_idx].zero_()
+        elif isinstance(m, nn.LayerNorm):
+            m.bias.data.zero_()
+            m.weight.data.fill_(1.0)
+
+
+class CXRBertEncoder(nn.Module):
+    """reference: models/cxrbert_origin.py:37-130"""
+
+    def __init__(self, config, args):
+        super().__init__()
+        self.config, self.args = config, args
+        self.txt_embeddings = _Embeddings(config)
+        self.img_embeddings = ImageBertEmbeddings(args, self.txt_embeddings)
+        if getattr(args, "img_encoder", "random-pixel") == "ViT":
+            raise NotImplementedError("the ViT image path is broken in the reference (models/image.py:105-110) and out of scope")
+        self.img_encoder = ImageEncoder_cnn(args)
+        for p in self.img_encoder.parameters():     # entire trunk frozen (cxrbert_origin.py:66-70)
+            p.requires_grad = False
+        self.encoder = _Encoder(config)
+        self.pooler = _Dense(config.hidden_size, config.hidden_size)
+        std = getattr(config, "initializer_range", 0.02)
+        for m in (self.txt_embeddings, self.encoder, self.pooler):
+            _init_bert_weights(m, std)
+        self._owner = None   # set by CXRBERT: the engine lives on the top-level module
+
+    def get_extended_attn_mask(self, attn_mask):
+        """models/cxrbert_origin.py:75-85 — kept for API compatibility; the CUDA path never materialises it."""
+        if attn_mask.dim() == 2:
+            ext = attn_mask.unsqueeze(1).unsqueeze(2)
+        elif attn_mask.dim() == 3:
+            ext = attn_mask.unsqueeze(1)
+        else:
+            raise NotImplementedError
+        return (1.0 - ext.to(dtype=torch.float16)) * -10000.0
+
+    def forward(self, cls_tok, input_txt, attn_mask, segment, input_img, sep_tok):
+        if self._owner is None:
+            raise RuntimeError("CXRBertEncoder must be owned by a CXRBERT (the engine lives on the top-level module)")
+        owner = self._owner()
+        eng, batch = owner._encode(cls_tok, input_txt, attn_mask, segment, input_img, sep_tok, train=self.training)
+        d = eng.dims
+        seq = torch.empty(batch.B * d.L, d.hidden, dtype=eng.act_dtype, device=eng.device)
+        owner._peek_into("x", d.layers, seq)
+        pooled = torch.empty(batch.B, d.hidden, dtype=eng.act_dtype, device=eng.device)
+        owner._peek_into("pooled", 0, pooled)
+        return seq.view(batch.B, d.L, d.hidden).float(), pooled.float(), None
+
+
+class ImageTextMatching(nn.Module):
+    """reference: models/cxrbert_origin.py:164-173"""
+
+    def __init__(self, hidden):
+        super().__init__()
+        self.linear = nn.Linear(hidden, 2)
+
+    def forward(self, x):
+        raise RuntimeError(_FUSED_MSG % "ImageTextMatching")
+
+
+class BertLayerNorm(nn.Module):
+    """TF-style LayerNorm container, eps inside the sqrt (models/cxrbert_origin.py:189-202)"""
+
+    def __init__(self, hidden_size, eps=1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.bias = nn.Parameter(torch.zeros(hidden_size))
+        self.variance_epsilon = eps
+
+
+class BertPredictionHeadTransform(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.dense = nn.Linear(config.hidden_size, config.hidden_size)
+        self.LayerNorm = BertLayerNorm(config.hidden_size, eps=1e-5)
+
+
+class BertLMPredictionHead(nn.Module):
+    """decoder weight IS the word-embedding Parameter (models/cxrbert_origin.py:225-233)"""
+
+    def __init__(self, config, bert_model_embedding_weights):
+        super().__init__()
+        self.transform = BertPredictionHeadTransform(config)
+        self.decoder = nn.Linear(bert_model_embedding_weights.size(1), bert_model_embedding_weights.size(0), bias=False)
+        self.decoder.weight = bert_model_embedding_weights
+        self.bias = nn.Parameter(torch.zeros(bert_model_embedding_weights.size(0)))
+
+
+class BertPreTrainingHeads(nn.Module):
+    def __init__(self, config, bert_model_embedding_weights):
+        super().__init__()
+        self.predictions = BertLMPredictionHead(config, bert_model_embedding_weights)
+
+    def forward(self, sequence_output):
+        raise RuntimeError(_FUSED_MSG % "BertPreTrainingHeads")
+
+
+# ---- the model ---------------------------------------------------------------------------------------------------------
+class CXRBERT(nn.Module):
+    """Multimodal BERT: Masked Language Model + Image Text Matching (models/cxrbert_origin.py:132-149)."""
+
+    def __init__(self, config, args):
+        super().__init__()
+        import weakref
+
+        self.config, self.args = config, args
+        self.enc = CXRBertEncoder(config, args)
+        self.mlm = BertPreTrainingHeads(config, self.enc.txt_embeddings.word_embeddings.weight)
+        self.itm = ImageTextMatching(args.hidden_size)
+        self.enc._owner = weakref.ref(self)
+        self._engine = None
+        self._dropout_step = 0
+
+    # -- engine plumbing --
+    def dims(self):
+        c, a = self.config, self.args
+        if getattr(c, "hidden_act", "gelu") != "gelu":
+            raise _lib.MedvillError("only the exact-erf GELU of the reference is implemented")
+        grid = (a.img_size // 32) ** 2
+        return EngineDims(hidden=c.hidden_size, heads=c.num_attention_heads, layers=c.num_hidden_layers, inter=c.intermediate_size,
+                          vocab=c.vocab_size, max_pos=c.max_position_embeddings, type_vocab=c.type_vocab_size,
+                          num_image_embeds=a.num_image_embeds, seq_len=a.seq_len, img_hidden=a.img_hidden_sz, grid=grid,
+                          ln_eps=c.layer_norm_eps, head_ln_eps=1e-5, dropout_p=float(a.dropout_prob))
+
+    def _trainable(self):
+        """reference-named trainable parameters (aliases de-duplicated, ResNet excluded)"""
+        return {n: p for n, p in self.named_parameters() if not n.startswith("enc.img_encoder.")}
+
+    def _release_engine(self):
+        if self._engine is not None:
+            for p in self._trainable().values():
+                p.data = p.data.clone()
+                p.grad = None
+            self._engine.close()
+            self._engine = None
+
+    def _apply(self, fn, *a, **k):
+        self._release_engine()      # .to() / .cuda() / .float() re-allocate parameters: re-adopt lazily afterwards
+        return super()._apply(fn, *a, **k)
+
+    def engine(self, min_batch=1):
+        dev = self.enc.pooler.dense.weight.device
+        if dev.type != "cuda":
+            raise _lib.MedvillError("CXRBERT needs its parameters on a CUDA device (sm_100a): there is no CPU fallback; "
+                                    "call .to('cuda') first")
+        cap = max(min_batch, int(getattr(self.args, "max_micro_batch", 64)))
+        if self._engine is not None and self._engine.max_batch < min_batch:
+            self._release_engine()
+        if self._engine is None:
+            eng = PretrainEngine(self.dims(), dev, precision=getattr(self.args, "precision", "bf16"), max_batch=cap)
+            named = self._trainable()
+            missing = set(eng.pmap) - set(named)
+            if missing:
+                raise _lib.MedvillError("parameters missing from the module tree: %s" % sorted(missing)[:4])
+            with torch.no_grad():
+                for n, p in named.items():
+                    v = eng.view(n)
+                    v.copy_(p.data.to(torch.float32))
+                    p.data = v                      # the nn.Parameter now IS the arena slice
+                    p.grad = eng.view(n, eng.grads)
+            eng.refresh_shadow()
+            self.enc.img_encoder.model.to(memory_format=torch.channels_last)
+            self._engine = eng
+        return self._engine
+
+    def sync_params(self):
+        """Call after mutating parameters from Python (e.g. load_state_dict): refreshes the bf16 GEMM-operand shadow."""
+        if self._engine is not None:
+            self._engine.refresh_shadow()
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        sd = {k: v for k, v in state_dict.items() if not k.endswith("position_ids")}   # transformers-3.x buffer, ignored
+        out = super().load_state_dict(sd, strict=strict, **kw)
+        self.sync_params()
+        return out
+
+    def _peek_into(self, name, layer, dst):
+        import ctypes as C
+
+        eng = self._engine
+        got = C.c_int64(0)
+        _lib.check(_lib.lib().mv_peek(eng._h, name.encode(), layer, _lib.ptr(dst), dst.numel() * dst.element_size(), C.byref(got),
+                                      _lib.stream_ptr(eng.device)), "mv_peek")
+        return dst
+
+    def grid_features(self, input_img, eng):
+        """ResNet-50 trunk on cuDNN: frozen, train-mode BN when the module is training, bf16 autocast in bf16 mode."""
+        with torch.no_grad():
+            if eng.act_dtype == torch.bfloat16:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    f = self.enc.img_encoder.grid_features(input_img)
+            else:
+                f = self.enc.img_encoder.grid_features(input_img.float())
+        return f
+
+    def classify_mask(self, attn_mask, eng):
+        """[B,L,L] / [B,L] int mask -> (mode u8[B], t_len i32[B]) on the device, validated cell by cell."""
+        import ctypes as C
+
+        d = eng.dims
+        m = attn_mask.to(device=eng.device, dtype=torch.int64).contiguous()
+        B = m.shape[0]
+        if m.dim() not in (2, 3) or m.shape[-1] != d.L:
+            raise _lib.MedvillError("attn_mask must be [B, %d, %d] or [B, %d]" % (d.L, d.L, d.L))
+        mode = torch.empty(B, dtype=torch.uint8, device=eng.device)
+        t_len = torch.empty(B, dtype=torch.int32, device=eng.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=eng.device)
+        _lib.check(_lib.lib().mv_mask_classify(_lib.ptr(m), m.dim(), B, d.A, d.L, _lib.ptr(mode), _lib.ptr(t_len), _lib.ptr(bad),
+                                               _lib.stream_ptr(eng.device)), "mv_mask_classify")
+        nbad = int(bad.item())
+        if nbad:
+            raise _lib.MedvillError("attention mask is not one of MedViLL's modes (Bidirectional / Seq2Seq / Bidirectional "
+                                    "Auto-Regressive / Non-cross): %d cells differ from the predicate" % nbad)
+        return mode, t_len
+
+    def _encode(self, cls_tok, input_txt, attn_mask, segment, input_img, sep_tok, train, mode=None, t_len=None, txt_labels=None,
+                is_aligned=None, feats=None, **kw):
+        B = input_txt.shape[0]
+        eng = self.engine(B)
+        if feats is None:
+            feats = self.grid_features(input_img.to(eng.device, non_blocking=True), eng)
+        ridx = self.enc.img_encoder.sample_regions(feats.shape[1])
+        if mode is None:
+            mode, t_len = self.classify_mask(attn_mask, eng)
+        self._dropout_step += 1
+        seed = (int(getattr(self.args, "seed", 123)) << 32) ^ (self._dropout_step * 0x9E3779B1) ^ (eng.rank << 20)
+        batch = eng.make_batch(cls_tok=cls_tok, input_ids=input_txt, segment=segment, sep_tok=sep_tok, mode=mode, t_len=t_len,
+                               region_idx=ridx, feats=feats, txt_labels=txt_labels, is_aligned=is_aligned, seed=seed, train=train, **kw)
+        eng.forward(batch)
+        return eng, batch
+
+    def forward(self, cls_tok, input_txt, attn_mask, segment, input_img, sep_tok):
+        """-> (prediction_scores [B, L, V] fp32, itm_logits [B, 2] fp32), detached.  Signature: cxrbert_origin.py:144."""
+        eng, batch = self._encode(cls_tok, input_txt, attn_mask, segment, input_img, sep_tok, train=False)
+        logits = eng.full_logits(batch)
+        itm = torch.empty(batch.B, 2, dtype=torch.float32, device=eng.device)
+        self._peek_into("itm_logits", 0, itm)
+        return logits, itm
+
+    def pretrain_step(self, cls_tok, input_ids, txt_labels, attn_masks, image, segment, is_aligned, sep_tok, lr=None,
+                      mode=None, t_len=None, optimizer_step=True, feats=None):
+        """One fused MLM+ITM step == models/train_origin.py:106-131 (forward, CE losses, zero_grad, backward, AdamW.step)
+        plus the metrics of :133-146.  Tensors may live on the host (pinned) or the device.  Under torch.distributed
+        (one process per GPU) gradients are all-reduced in buckets overlapped with backward and the loss normalisers
+        are global, so N ranks x B samples reproduce a single-process batch of N*B."""
+        B = int(input_ids.shape[0])
+        eng = self.engine(min(B, int(getattr(self.args, "max_micro_batch", 64))))
+        lab = torch.as_tensor(txt_labels)
+        n_lab = int((lab != -100).sum())
+        n_lab_g, b_g = float(n_lab), float(B)
+        if eng.world > 1:
+            cnt = torch.tensor([n_lab_g, b_g], dtype=torch.float32, device=eng.device)
+            eng.allreduce_f32(cnt)
+            n_lab_g, b_g = (float(x) for x in cnt.tolist())
+        if mode is None:
+            mode, t_len = self.classify_mask(torch.as_tensor(attn_masks), eng)
+        cap = eng.max_batch
+        eng.stats_reset()
+        chunks = [(s, min(B, s + cap)) for s in range(0, B, cap)]
+        for ci, (s, e) in enumerate(chunks):
+            sl = slice(s, e)
+            _, batch = self._encode(cls_tok[sl], input_ids[sl], None, segment[sl], None if image is None else image[sl], sep_tok[sl],
+                                    train=True, mode=mode[sl], t_len=t_len[sl], txt_labels=lab[sl], is_aligned=is_aligned[sl],
+                                    feats=None if feats is None else feats[sl], n_lab_global=n_lab_g, batch_global=b_g)
+            eng.backward(batch, allreduce=(eng.world > 1 and ci == len(chunks) - 1))
+        if optimizer_step:
+            eng.adamw_step(lr=float(self.args.lr if lr is None else lr))
+        st = eng.read_stats()
+        mlm = st["mlm_loss_sum"] / max(1, n_lab)
+        itm = st["itm_loss_sum"] / B
+        return dict(loss=mlm + itm, mlm_loss=mlm, itm_loss=itm, itm_correct=st["itm_correct"], mlm_correct=st["mlm_correct"],
+                    n_labelled=n_lab, batch=B)
+
+    def eval_step(self, cls_tok, input_ids, txt_labels, attn_masks, image, segment, is_aligned, sep_tok, mode=None, t_len=None,
+                  feats=None):
+        """Validation step (models/train_origin.py:171-231): forward + both losses + accuracy counts, no gradients."""
+        B = int(input_ids.shape[0])
+        eng = self.engine(min(B, int(getattr(self.args, "max_micro_batch", 64))))
+        lab = torch.as_tensor(txt_labels)
+        n_lab = int((lab != -100).sum())
+        if mode is None:
+            mode, t_len = self.classify_mask(torch.as_tensor(attn_masks), eng)
+        eng.stats_reset()
+        for s in range(0, B, eng.max_batch):
+            sl = slice(s, min(B, s + eng.max_batch))
+            self._encode(cls_tok[sl], input_ids[sl], None, segment[sl], None if image is None else image[sl], sep_tok[sl],
+                         train=False, mode=mode[sl], t_len=t_len[sl], txt_labels=lab[sl], is_aligned=is_aligned[sl],
+                         feats=None if feats is None else feats[sl])
+        st = eng.read_stats()
+        mlm = st["mlm_loss_sum"] / max(1, n_lab)
+        itm = st["itm_loss_sum"] / B
+        return dict(loss=mlm + itm, mlm_loss=mlm, itm_loss=itm, itm_correct=st["itm_correct"], mlm_correct=st["mlm_correct"],
+                    n_labelled=n_lab, batch=B)
+
+    # -- HF-style persistence used by the trainer (models/train_origin.py:28-34,254-266) --
+    def save_pretrained(self, save_directory):
+        os.makedirs(save_directory, exist_ok=True)
+        cfg = self.config.to_dict() if hasattr(self.config, "to_dict") else dict(self.config.__dict__)
+        cfg = {k: v for k, v in cfg.items() if isinstance(v, (int, float, str, bool, type(None), list, dict))}
+        with open(os.path.join(save_directory, "config.json"), "w") as f:
+            json.dump(cfg, f, indent=2, sort_keys=True)
+        torch.save({k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
+                   os.path.join(save_directory, "pytorch_model.bin"))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, state_dict=None, config=None, args=None, **kw):
+        if config is None:
+            config = BertConfig.from_pretrained(pretrained_model_name_or_path)
+        model = cls(config, args)
+        if state_dict is None:
+            state_dict = torch.load(os.path.join(pretrained_model_name_or_path, "pytorch_model.bin"), map_location="cpu")
+        model.load_state_dict(state_dict, strict=False)
+        return model

