@@ -154,6 +154,13 @@ int mv_layernorm_bwd(const void* dy, const void* x, const float* gamma, void* dx
                      int32_t rows, int32_t H, float eps, int32_t precision, void* stream);
 int mv_mlm_ce(const float* logits, int64_t ld, const int64_t* labels, int32_t n, int32_t V, void* dlogits, float gscale,
               float* loss_sum, int32_t* correct, float* row_lse, int32_t* row_argmax, int32_t precision, void* stream);
+/* BatchNorm2d (+residual add) (+ReLU) of the frozen ResNet-50 trunk on channels-last [rows = B*H*W, C] activations:
+ * replaces torch.nn.BatchNorm2d inside ImageEncoder_cnn (models/image.py:50-56; train-mode statistics per
+ * models/train_origin.py:72).  workspace: mv_bn_workspace_floats(rows, C) floats. */
+int64_t mv_bn_workspace_floats(int64_t rows, int32_t C);
+int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32_t C, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, int32_t training, int32_t relu,
+                  float* workspace, int64_t ws_floats, int32_t precision, void* stream);
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
 

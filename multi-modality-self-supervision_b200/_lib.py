@@ -92,6 +92,8 @@ SYMBOLS = {
     "mv_layernorm_fwd": (_I, [_P, _P, _P, _P, _I, _I, _F, _I, _P]),
     "mv_layernorm_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P]),
     "mv_mlm_ce": (_I, [_P, _L, _P, _I, _I, _P, _F, _P, _P, _P, _P, _I, _P]),
+    "mv_bn_workspace_floats": (_L, [_L, _I]),
+    "mv_bn_forward": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _P, _L, _I, _P]),
     "mv_adamw": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _I, _P]),
 }
 

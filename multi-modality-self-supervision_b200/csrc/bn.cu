@@ -1,0 +1,200 @@
+// bn.cu — BatchNorm2d for the frozen ResNet-50 trunk on channels-last activations [rows = B*H*W, C] (bf16 or fp32):
+// train-mode batch statistics (models/train_origin.py:72 runs model.train() on frozen weights) + affine + optional
+// residual add + ReLU in one apply pass.  The convolutions stay on cuDNN (BASELINE.json north_star (4)); these two
+// HBM-bound passes replace PyTorch's native channels-last batch-norm kernels, which ran at ~1/7 of the HBM roofline
+// (profiles/r01_launches_step.txt).  Algorithmic traffic: stats 1 read, apply 1 read (+1 residual read) + 1 write.
+//
+// Numerics: per-thread fp32 sum / sum-of-squares over <= a few thousand rows, converted to (n, mean, M2) and merged with
+// Chan's parallel update across threads and CTAs; running stats use the unbiased variance (PyTorch semantics).
+#include "kernels.h"
+
+namespace mv {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&v)[8]);
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void st8<bf16>(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float meanb, float m2b) {
+  if (nb == 0.f) return;
+  const float nt = n + nb, d = meanb - mean;
+  mean += d * (nb / nt);
+  m2 += m2b + d * d * (n * nb / nt);
+  n = nt;
+}
+
+// 256 threads; thread t owns channels [8*(t % cpr), +8) and rows (t / cpr) + k * rpi of the CTA's row slab, where
+// cpr = C/8 threads per row and rpi = 256 / cpr rows per iteration (C >= 2048 handled by gridDim.y channel blocks).
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long rows, int C, long rows_per_cta,
+                                                       float* __restrict__ partial /* [gridDim.x][C][3] */) {
+  __shared__ float red[256][3 * 8 + 1];
+  const int cpr = min(C >> 3, 256);
+  const int rpi = 256 / cpr;
+  const int cch = (threadIdx.x % cpr) + blockIdx.y * 256;   // 8-channel chunk index
+  const int roff = threadIdx.x / cpr;
+  const long r0 = static_cast<long>(blockIdx.x) * rows_per_cta;
+  const long r1 = min(rows, r0 + rows_per_cta);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float cnt = 0.f;
+  if (roff < rpi && cch * 8 < C) {
+    for (long r = r0 + roff; r < r1; r += rpi) {
+      float v[8];
+      ld8<T>(x + r * C + cch * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
+      cnt += 1.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float mean = cnt > 0.f ? s[j] / cnt : 0.f;
+    red[threadIdx.x][3 * j] = cnt;
+    red[threadIdx.x][3 * j + 1] = mean;
+    red[threadIdx.x][3 * j + 2] = cnt > 0.f ? fmaxf(q[j] - s[j] * mean, 0.f) : 0.f;
+  }
+  __syncthreads();
+  // threads [0, cpr) merge the rpi row-lanes of their channel chunk
+  if (threadIdx.x < cpr && cch * 8 < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float n = 0.f, mean = 0.f, m2 = 0.f;
+      for (int k = 0; k < rpi; ++k) {
+        const float* e = &red[threadIdx.x + k * cpr][3 * j];
+        chan_merge(n, mean, m2, e[0], e[1], e[2]);
+      }
+      float* o = partial + (static_cast<long>(blockIdx.x) * C + cch * 8 + j) * 3;
+      o[0] = n; o[1] = mean; o[2] = m2;
+    }
+  }
+}
+
+// one thread per channel: merge the per-CTA partials, produce scale/shift, update the running statistics
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
+                                   float eps, int update_running, float* __restrict__ scale_shift /* [2][C] */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int p = 0; p < nparts; ++p) {
+    const float* e = partial + (static_cast<long>(p) * C + c) * 3;
+    chan_merge(n, mean, m2, e[0], e[1], e[2]);
+  }
+  const float var = m2 / n;                      // biased: what normalisation uses
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = beta[c] - mean * sc;
+  if (update_running) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (n > 1.f ? m2 / (n - 1.f) : var);
+  }
+}
+
+__global__ void bn_eval_scale_kernel(int C, const float* gamma, const float* beta, const float* running_mean,
+                                     const float* running_var, float eps, float* scale_shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(running_var[c] + eps);
+  scale_shift[c] = sc;
+  scale_shift[C + c] = beta[c] - running_mean[c] * sc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ resid, T* __restrict__ y,
+                                                       long n8, int C, const float* __restrict__ scale_shift, int relu) {
+  const int c8 = C >> 3;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c8) * 8;
+    float v[8], sc[8], sh[8];
+    ld8<T>(x + i * 8, v);
+    ld8<float>(scale_shift + ch, sc);
+    ld8<float>(scale_shift + C + ch, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+    if (resid) {
+      float r[8];
+      ld8<T>(resid + i * 8, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    st8<T>(y + i * 8, v);
+  }
+}
+
+}  // namespace
+
+// workspace: [nparts * C * 3] partials followed by [2 * C] scale/shift; nparts = bn_num_parts(rows)
+int bn_num_parts(long rows, int C) {
+  const int sms = device_sm_count();
+  const int cpr = (C >> 3) < 256 ? (C >> 3) : 256;
+  const int rpi = 256 / cpr;
+  long parts = sms * 4 / ((C + 2047) / 2048);
+  const long max_parts = (rows + rpi * 8 - 1) / (rpi * 8);     // at least 8 rows per thread
+  if (parts > max_parts) parts = max_parts;
+  if (parts < 1) parts = 1;
+  return static_cast<int>(parts);
+}
+
+int bn_forward(const void* x, const void* resid, void* y, long rows, int C, const float* gamma, const float* beta,
+               float* running_mean, float* running_var, float momentum, float eps, int training, int relu, float* workspace,
+               long ws_floats, int f32, cudaStream_t s) {
+  MV_REQUIRE(x && y && gamma && beta && running_mean && running_var && workspace, "bn_forward: null argument");
+  MV_REQUIRE(C % 8 == 0 && C >= 8 && rows > 0, "bn_forward: C must be a multiple of 8 (got %d)", C);
+  MV_REQUIRE(C <= 2048 || C % 2048 == 0, "bn_forward: C > 2048 must be a multiple of 2048");
+  const int nparts = bn_num_parts(rows, C);
+  MV_REQUIRE(ws_floats >= static_cast<long>(nparts) * C * 3 + 2 * C, "bn_forward: workspace too small");
+  float* scale_shift = workspace + static_cast<long>(nparts) * C * 3;
+  if (training) {
+    const long rows_per_cta = (rows + nparts - 1) / nparts;
+    dim3 grid(nparts, (C + 2047) / 2048);
+    if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
+    else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
+    MV_LAUNCH_CHECK();
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
+                                                      scale_shift);
+    MV_LAUNCH_CHECK();
+  } else {
+    bn_eval_scale_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, gamma, beta, running_mean, running_var, eps, scale_shift);
+    MV_LAUNCH_CHECK();
+  }
+  const long n8 = rows * (C >> 3);
+  long blocks = (n8 + 255) / 256;
+  const long cap = static_cast<long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (f32) bn_apply_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const float*>(x), static_cast<const float*>(resid),
+                                                                          static_cast<float*>(y), n8, C, scale_shift, relu);
+  else bn_apply_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(resid),
+                                                                      static_cast<bf16*>(y), n8, C, scale_shift, relu);
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace mv

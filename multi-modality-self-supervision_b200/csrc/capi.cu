@@ -274,6 +274,15 @@ int mv_mlm_ce(const float* logits, int64_t ld, const int64_t* labels, int32_t n,
   return mlm_ce_fwd_bwd(a, precision == MV_PREC_FP32, S(stream));
 }
 
+int64_t mv_bn_workspace_floats(int64_t rows, int32_t C) { return static_cast<int64_t>(bn_num_parts(rows, C)) * C * 3 + 2 * C; }
+
+int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32_t C, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float momentum, float eps, int32_t training, int32_t relu,
+                  float* workspace, int64_t ws_floats, int32_t precision, void* stream) {
+  return bn_forward(x, resid, y, rows, C, gamma, beta, running_mean, running_var, momentum, eps, training, relu, workspace,
+                    ws_floats, precision == MV_PREC_FP32, S(stream));
+}
+
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream) {
   AdamArgs a;

@@ -97,6 +97,12 @@ struct AdamArgs {
 };
 int adamw_step(const AdamArgs& a, cudaStream_t s);
 
+// ---- BatchNorm2d of the frozen ResNet trunk, channels-last [rows, C]: batch statistics + affine (+ residual) (+ ReLU)
+int bn_num_parts(long rows, int C);
+int bn_forward(const void* x, const void* resid, void* y, long rows, int C, const float* gamma, const float* beta,
+               float* running_mean, float* running_var, float momentum, float eps, int training, int relu, float* workspace,
+               long ws_floats, int f32, cudaStream_t s);
+
 // ---- fused masked attention (upstream BertSelfAttention; twin .../pytorch_pretrained_bert/model.py:301-320)
 struct AttnArgs {
   int B, L, nh, A;                   // head dim fixed at 64; H = nh * 64

@@ -283,6 +283,7 @@ class CXRBERT(nn.Module):
     def load_state_dict(self, state_dict, strict=True, **kw):
         sd = {k: v for k, v in state_dict.items() if not k.endswith("position_ids")}   # transformers-3.x buffer, ignored
         out = super().load_state_dict(sd, strict=strict, **kw)
+        self.enc.img_encoder._exec = None
         self.sync_params()
         return out
 
@@ -297,13 +298,7 @@ class CXRBERT(nn.Module):
 
     def grid_features(self, input_img, eng):
         """ResNet-50 trunk on cuDNN: frozen, train-mode BN when the module is training, bf16 autocast in bf16 mode."""
-        with torch.no_grad():
-            if eng.act_dtype == torch.bfloat16:
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    f = self.enc.img_encoder.grid_features(input_img)
-            else:
-                f = self.enc.img_encoder.grid_features(input_img.float())
-        return f
+        return self.enc.img_encoder.grid_features(input_img, dtype=eng.act_dtype)
 
     def classify_mask(self, attn_mask, eng):
         """[B,L,L] / [B,L] int mask -> (mode u8[B], t_len i32[B]) on the device, validated cell by cell."""

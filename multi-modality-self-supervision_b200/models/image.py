@@ -6,29 +6,106 @@ north_star and Classification/mmbt/models/image.py:16 use).  The convolutions st
 the [B, 2048, g, g] feature map *is* the [B, g*g, 2048] region matrix with no flatten/transpose copies; region gather +
 2048->768 projection + position/type add + LayerNorm run in libmedvill_sm100 (mv_forward).
 """
+import ctypes as C
+
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 import torchvision
+
+from .. import _lib
+
+
+class TrunkExecutor:
+    """Runs the (frozen) torchvision ResNet-50 trunk with cuDNN convolutions on channels-last activations and the
+    library's fused BatchNorm(+residual)(+ReLU) kernels (mv_bn_forward).  Parameters and BN buffers stay the module's
+    own tensors (state_dict-compatible); only dtype/layout-converted copies of the frozen conv weights are cached."""
+
+    def __init__(self, seq, act_dtype):
+        self.seq, self.act_dtype = seq, act_dtype
+        self.w = {}
+        self.ws = None
+        self.refresh()
+
+    def refresh(self):
+        self.w = {}
+        for name, m in self.seq.named_modules():
+            if isinstance(m, nn.Conv2d):
+                self.w[name] = m.weight.detach().to(self.act_dtype).contiguous(memory_format=torch.channels_last)
+
+    def _conv(self, name, m, x):
+        y = F.conv2d(x, self.w[name], None, m.stride, m.padding)
+        return y if y.is_contiguous(memory_format=torch.channels_last) else y.contiguous(memory_format=torch.channels_last)
+
+    def _bn(self, m, x, relu, training, resid=None):
+        B, Cc, H, W = x.shape
+        rows = B * H * W
+        need = int(_lib.lib().mv_bn_workspace_floats(rows, Cc))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=torch.float32, device=x.device)
+        prec = _lib.MV_PREC_FP32 if self.act_dtype == torch.float32 else _lib.MV_PREC_BF16
+        _lib.check(_lib.lib().mv_bn_forward(_lib.ptr(x), _lib.ptr(resid), _lib.ptr(x), rows, Cc, _lib.ptr(m.weight), _lib.ptr(m.bias),
+                                            _lib.ptr(m.running_mean), _lib.ptr(m.running_var), float(m.momentum), float(m.eps),
+                                            1 if training else 0, 1 if relu else 0, _lib.ptr(self.ws), self.ws.numel(), prec,
+                                            _lib.stream_ptr(x.device)), "mv_bn_forward")
+        if training:
+            m.num_batches_tracked.add_(1)
+        return x
+
+    def __call__(self, x, training):
+        s = self.seq
+        x = x.to(self.act_dtype).contiguous(memory_format=torch.channels_last)
+        x = self._bn(s[1], self._conv("0", s[0], x), True, training)
+        x = s[3](x)
+        for li in (4, 5, 6, 7):
+            for bi, blk in enumerate(s[li]):
+                pre = "%d.%d." % (li, bi)
+                idt = x
+                out = self._bn(blk.bn1, self._conv(pre + "conv1", blk.conv1, x), True, training)
+                out = self._bn(blk.bn2, self._conv(pre + "conv2", blk.conv2, out), True, training)
+                out = self._conv(pre + "conv3", blk.conv3, out)
+                if blk.downsample is not None:
+                    idt = self._bn(blk.downsample[1], self._conv(pre + "downsample.0", blk.downsample[0], x), False, training)
+                x = self._bn(blk.bn3, out, True, training, resid=idt)      # relu(bn3(out) + identity)
+        return x
 
 
 class ImageEncoder_cnn(nn.Module):
     def __init__(self, args):
         super().__init__()
         self.args = args
-        try:
-            model = torchvision.models.resnet50(weights="IMAGENET1K_V1")      # reference: pretrained=True (image.py:50)
-        except Exception:                                                     # offline: random init, same architecture
-            model = torchvision.models.resnet50(weights=None)
+        # reference: resnet50(pretrained=True) (image.py:50).  Use the ImageNet checkpoint only when it is already in the
+        # local torch-hub cache (no network here); otherwise the same architecture with random init.
+        import os
+
+        ckpt = os.path.join(torch.hub.get_dir(), "checkpoints", "resnet50-0676ba61.pth")
+        model = torchvision.models.resnet50(weights=None)
+        if os.path.isfile(ckpt):
+            model.load_state_dict(torch.load(ckpt, map_location="cpu"))
         self.model = nn.Sequential(*list(model.children())[:-2])
         self.region_idx_override = None     # parity runs inject the sampled regions (the reference uses the CPU RNG)
+        self._exec = None
+
+    def executor(self, act_dtype):
+        if self._exec is None or self._exec.act_dtype != act_dtype:
+            self._exec = TrunkExecutor(self.model, act_dtype)
+        return self._exec
+
+    def _apply(self, fn, *a, **k):
+        self._exec = None                   # weights moved / cast: rebuild the cached conv-weight copies lazily
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._exec = None
+        return super().load_state_dict(*a, **k)
 
     def grid_features(self, x, dtype=None):
         """[B, 3, h, w] -> [B, (h/32)*(w/32), 2048], contiguous, channels-last under the hood."""
-        if dtype is not None and x.dtype != dtype:
-            x = x.to(dtype)
         if x.is_cuda:
-            x = x.contiguous(memory_format=torch.channels_last)
-        out = self.model(x)                                    # [B, 2048, g, g]
+            with torch.no_grad():
+                out = self.executor(dtype or x.dtype)(x, self.training)       # cuDNN convs + mv_bn_forward
+        else:
+            out = self.model(x if dtype is None else x.to(dtype))             # host-side use of the container only
         B, Cc = out.shape[0], out.shape[1]
         return out.permute(0, 2, 3, 1).reshape(B, -1, Cc)      # free view when `out` is channels-last
 

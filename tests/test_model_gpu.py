@@ -1,0 +1,168 @@
+"""GPU parity of the drop-in Python surface (CXRBERT / ImageEncoder_cnn / trainer) against the reference-derived
+golden fixtures: ResNet trunk with the library's BatchNorm kernels, mask tensor -> (mode, t_len) classification,
+full [B, L, V] logits, fused pretrain_step, state_dict compatibility, loud failures."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import medvill_oracle as orc
+from tests.util import golden_batch, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(cfg, precision, dropout=0.0):
+    import medvill_b200  # noqa: F401
+    from medvill_b200.config import BertConfig
+    from medvill_b200.models import CXRBERT
+
+    bc = BertConfig(vocab_size=cfg.vocab, hidden_size=cfg.hidden, num_hidden_layers=cfg.layers, num_attention_heads=cfg.heads,
+                    intermediate_size=cfg.inter, max_position_embeddings=cfg.max_pos, type_vocab_size=cfg.type_vocab,
+                    hidden_dropout_prob=dropout, attention_probs_dropout_prob=dropout, layer_norm_eps=cfg.ln_eps)
+    args = types.SimpleNamespace(img_hidden_sz=cfg.img_hidden, embedding_size=cfg.hidden, hidden_size=cfg.hidden, dropout_prob=dropout,
+                                 img_encoder="random-pixel", num_image_embeds=cfg.num_image_embeds, img_size=cfg.img_size,
+                                 seq_len=cfg.seq_len, lr=1e-5, precision=precision, max_micro_batch=8, seed=123)
+    model = CXRBERT(bc, args)
+    params = orc.synth_params(cfg, seed=0)
+    sd = {}
+    for k in model.state_dict():
+        sd[k] = params[orc.canonical_key(k)]
+    model.load_state_dict(sd, strict=True)
+    return model.to("cuda:0"), params
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_resnet_trunk_with_library_batchnorm(precision, tol):
+    g, cfg = load_golden("tiny_bar")
+    batch = golden_batch(g, cfg)
+    model, params = make_model(cfg, precision)
+    model.train()
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    feats = model.enc.img_encoder.grid_features(batch["image"].to("cuda:0"), dtype=dt).float().cpu()
+    assert feats.shape == (3, cfg.grid, 2048)
+    ref = g["feats_sample"]
+    got = feats[:, :: max(1, cfg.grid // 8), ::64].numpy()
+    assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
+    # running statistics were updated once with momentum 0.1 (train-mode BN on frozen weights)
+    bn1 = model.enc.img_encoder.model[1]
+    assert int(bn1.num_batches_tracked) == 1
+    with torch.no_grad():
+        x = torch.nn.functional.conv2d(batch["image"], params["enc.img_encoder.model.0.weight"], stride=2, padding=3)
+        mean = x.mean(dim=(0, 2, 3))
+    assert torch.allclose(bn1.running_mean.cpu(), 0.1 * mean, atol=5e-3 if precision == "bf16" else 1e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny_bar", "tiny_s2s", "tiny_noncross", "tiny_bidir", "tiny_mixed"])
+def test_forward_dropin_full_logits_fp32(name):
+    """CXRBERT.forward(cls_tok, input_txt, attn_mask[B,L,L], segment, input_img, sep_tok) -> ([B,L,V], [B,2])"""
+    g, cfg = load_golden(name)
+    batch = golden_batch(g, cfg)
+    model, _ = make_model(cfg, "fp32")
+    model.train()                       # reference runs BN with batch statistics; dropout p = 0
+    model.enc.img_encoder.region_idx_override = batch["region_idx"]
+    t = lambda k: torch.as_tensor(batch[k]).to("cuda:0")
+    logits, itm = model(t("cls_tok"), t("input_ids"), t("attn_masks"), t("segment"), batch["image"].to("cuda:0"), t("sep_tok"))
+    assert logits.shape == (int(g["B"]), cfg.L, cfg.vocab) and itm.shape == (int(g["B"]), 2)
+    rows = g["lab_rows"]
+    got = logits[rows[:, 0], rows[:, 1]][:, torch.as_tensor(g["lab_cols"]).to("cuda:0")].cpu().numpy()
+    assert np.abs(got - g["lab_logits"]).max() <= 2e-4 * np.abs(g["lab_logits"]).max()
+    assert np.abs(itm.cpu().numpy() - g["itm_logits"]).max() <= 2e-4
+    seq, pooled, att = model.enc(t("cls_tok"), t("input_ids"), t("attn_masks"), t("segment"), batch["image"].to("cuda:0"), t("sep_tok"))
+    assert att is None and pooled.shape == (int(g["B"]), cfg.hidden)
+    ref = g["seq_sample"]
+    got = seq[:, :: max(1, cfg.L // 16), :: max(1, cfg.hidden // 32)].cpu().numpy()
+    assert np.abs(got - ref).max() <= 3e-4 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_pretrain_step_matches_reference_loss(precision, tol):
+    g, cfg = load_golden("tiny_mixed")
+    batch = golden_batch(g, cfg)
+    model, _ = make_model(cfg, precision)
+    model.train()
+    model.enc.img_encoder.region_idx_override = batch["region_idx"]
+    t = lambda k: torch.as_tensor(batch[k])
+    out = model.pretrain_step(t("cls_tok"), t("input_ids"), t("txt_labels"), t("attn_masks"), batch["image"], t("segment"),
+                              t("is_aligned"), t("sep_tok"), lr=1e-5)
+    assert abs(out["loss"] - float(g["loss"])) <= tol * float(g["loss"])
+    assert abs(out["mlm_loss"] - float(g["mlm_loss"])) <= tol * float(g["mlm_loss"])
+    assert out["n_labelled"] == int(g["n_labelled"]) and out["itm_correct"] == int(g["itm_correct"])
+    if precision == "fp32":
+        assert out["mlm_correct"] == int(g["mlm_correct"])
+    # parameters moved (AdamW ran) and the nn.Parameters are live views of the arena
+    w = model.enc.pooler.dense.weight
+    assert w.data_ptr() == model._engine.view("enc.pooler.dense.weight").data_ptr()
+    out2 = model.eval_step(t("cls_tok"), t("input_ids"), t("txt_labels"), t("attn_masks"), batch["image"], t("segment"),
+                           t("is_aligned"), t("sep_tok"))
+    assert np.isfinite(out2["loss"])
+
+
+def test_arbitrary_mask_is_rejected_loudly():
+    import medvill_b200 as m
+
+    g, cfg = load_golden("tiny_bar")
+    batch = golden_batch(g, cfg)
+    model, _ = make_model(cfg, "fp32")
+    bad = torch.as_tensor(batch["attn_masks"]).clone()
+    bad[1, cfg.A + 3, 2] = 0          # a text row that cannot see one image column: not a MedViLL mode
+    t = lambda k: torch.as_tensor(batch[k]).to("cuda:0")
+    with pytest.raises(m.MedvillError, match="not one of MedViLL"):
+        model(t("cls_tok"), t("input_ids"), bad.to("cuda:0"), t("segment"), batch["image"].to("cuda:0"), t("sep_tok"))
+
+
+def test_cpu_module_fails_loudly_and_state_dict_roundtrip(tmp_path):
+    import medvill_b200 as m
+    from medvill_b200.models import CXRBERT
+
+    g, cfg = load_golden("tiny_bar")
+    model, _ = make_model(cfg, "fp32")
+    model.engine()                                 # adopt the arena
+    keys_gpu = list(model.state_dict().keys())
+    model.save_pretrained(str(tmp_path))
+    again = CXRBERT.from_pretrained(str(tmp_path), args=model.args)
+    assert list(again.state_dict().keys()) == keys_gpu
+    for k, v in again.state_dict().items():
+        assert torch.equal(v.cpu(), model.state_dict()[k].cpu()), k
+    with pytest.raises(m.MedvillError, match="no CPU fallback"):
+        again.engine()                              # parameters on the CPU: no fallback path
+
+
+@pytest.mark.parametrize("L,A", [(436, 182), (512, 258), (32, 11)])
+def test_mask_dump_bit_exact_all_modes(L, A):
+    import ctypes as C
+
+    from medvill_b200 import _lib
+
+    modes = np.array([0, 1, 2, 3, 0, 0], dtype=np.uint8)
+    tlens = np.array([L - A, L - A, L - A, L - A, 1, max(1, (L - A) // 3)], dtype=np.int32)
+    dm, dt = torch.from_numpy(modes).cuda(), torch.from_numpy(tlens).cuda()
+    out = torch.empty(len(modes), L, L, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().mv_attn_mask_dump(_lib.ptr(dm), _lib.ptr(dt), len(modes), A, L, _lib.ptr(out), _lib.stream_ptr()))
+    ref = np.stack([orc.attention_mask(int(m), A, L, int(t)) for m, t in zip(modes, tlens)])
+    assert np.array_equal(out.cpu().numpy(), ref)               # bit-exact
+    # and the classifier inverts it
+    mask = torch.from_numpy(ref).cuda()
+    mo, tl, bad = torch.empty(len(modes), dtype=torch.uint8, device="cuda"), torch.empty(len(modes), dtype=torch.int32, device="cuda"), \
+        torch.zeros(1, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().mv_mask_classify(_lib.ptr(mask), 3, len(modes), A, L, _lib.ptr(mo), _lib.ptr(tl), _lib.ptr(bad), _lib.stream_ptr()))
+    assert int(bad.item()) == 0
+    assert np.array_equal(mo.cpu().numpy(), modes)
+    assert np.array_equal(tl.cpu().numpy()[[0, 4, 5]], tlens[[0, 4, 5]])     # t_len only matters for the Bidirectional mode
+
+
+def test_dropout_training_step_runs_and_is_seed_deterministic():
+    g, cfg = load_golden("tiny_bar")
+    batch = golden_batch(g, cfg)
+    losses = []
+    for _ in range(2):
+        model, _ = make_model(cfg, "bf16", dropout=0.1)
+        model.train()
+        model.enc.img_encoder.region_idx_override = batch["region_idx"]
+        t = lambda k: torch.as_tensor(batch[k])
+        out = model.pretrain_step(t("cls_tok"), t("input_ids"), t("txt_labels"), t("attn_masks"), batch["image"], t("segment"),
+                                  t("is_aligned"), t("sep_tok"), lr=1e-5)
+        losses.append(out["loss"])
+    assert np.isfinite(losses[0]) and abs(losses[0] - float(g["loss"])) < 0.5     # perturbed by dropout, same ballpark
+    assert losses[0] == losses[1]                                                 # counter-based RNG: same seed, same masks
