@@ -384,18 +384,26 @@ __global__ void __launch_bounds__(256) mask_classify_kernel(const int64_t* mask,
     if (bad) atomicAdd(mismatches, bad);
   } else {
     const int64_t* m = mask + static_cast<long>(b) * L * L;
-    int c = 0;
-    for (int k = threadIdx.x; k < L; k += blockDim.x) c += m[static_cast<long>(L - 1) * L + k] != 0;  // last text row
+    __shared__ int s_cnt_first;
+    if (threadIdx.x == 0) s_cnt_first = 0;
+    __syncthreads();
+    int c = 0, c0 = 0;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+      c += m[static_cast<long>(L - 1) * L + k] != 0;   // last text row
+      c0 += m[static_cast<long>(A) * L + k] != 0;      // first text row
+    }
     atomicAdd(&s_cnt, c);
+    atomicAdd(&s_cnt_first, c0);
     __syncthreads();
     if (threadIdx.x == 0) {
       const bool txt_sees_img = m[static_cast<long>(A) * L + 0] != 0;
       const bool img_sees_txt = m[0 * L + A] != 0;
-      const bool txt_sees_next = m[static_cast<long>(A) * L + A + 1] != 0;
+      // Bidirectional rows are all identical; the auto-regressive block makes the first and last text rows differ
+      const bool rows_identical = s_cnt == s_cnt_first;
       int md;
       if (!txt_sees_img) md = MODE_NONCROSS;
       else if (!img_sees_txt) md = MODE_S2S;
-      else if (!txt_sees_next) md = MODE_BAR;
+      else if (!rows_identical) md = MODE_BAR;
       else md = MODE_BIDIR;
       s_mode = md;
       s_tlen = md == MODE_BIDIR ? s_cnt - A : L - A;

@@ -34,7 +34,11 @@ class TrunkExecutor:
                 self.w[name] = m.weight.detach().to(self.act_dtype).contiguous(memory_format=torch.channels_last)
 
     def _conv(self, name, m, x):
-        y = F.conv2d(x, self.w[name], None, m.stride, m.padding)
+        if self.act_dtype == torch.float32:      # check mode: true fp32 convolutions (no TF32) for the 1e-4 gate
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                y = F.conv2d(x, self.w[name], None, m.stride, m.padding)
+        else:
+            y = F.conv2d(x, self.w[name], None, m.stride, m.padding)
         return y if y.is_contiguous(memory_format=torch.channels_last) else y.contiguous(memory_format=torch.channels_last)
 
     def _bn(self, m, x, relu, training, resid=None):

@@ -111,8 +111,8 @@ def test_step_fp32_check_mode_tiny(name):
 def test_step_bf16_tiny(name):
     o = run_step(name, "bf16")
     check_forward(o, 1e-2, 3e-2)
-    w = check_grads(o, 6e-2, 0.25)
-    print("worst grad-norm rel err %.3e" % w)
+    w = check_grads_vs_oracle(o, 0.95, 0.12)     # B = 3..4, H = 128: few-term contractions, near-cancelling head gradients
+    print("worst grad cosine %.5f" % w)
 
 
 def test_step_fp32_config1():
@@ -120,6 +120,28 @@ def test_step_fp32_config1():
     check_forward(o, 1e-4)
     assert np.array_equal(o["row_argmax"], o["g"]["lab_argmax"])
     check_grads(o, 3e-3, 1e-2)
+
+
+def check_grads_vs_oracle(o, cos_min, norm_tol):
+    """bf16 gradients, tensor by tensor, against the CPU oracle's full gradients (the oracle itself is pinned to the
+    reference to 1e-5): cosine similarity and norm ratio.  Element probes are meaningless in bf16 for entries far below
+    the tensor's scale (LayerNorm-backward cancellation), so this is the bf16 gradient gate."""
+    eng, cfg, params = o["eng"], o["cfg"], o["params"]
+    batch = golden_batch(o["g"], cfg)
+    ref = orc.loss_and_grads(params, batch, cfg, feats=oracle_feats(params, batch))["grads"]
+    scale = max(float(v.norm()) for v in ref.values())
+    worst = 1.0
+    for n, r in ref.items():
+        got = eng.view(n, eng.grads).float().cpu().flatten().double()
+        r = r.flatten().double()
+        if float(r.norm()) <= 1e-4 * scale:            # analytically-zero gradients (key biases)
+            assert float(got.norm()) <= 1e-3 * scale, n
+            continue
+        cos = float(got @ r / (got.norm() * r.norm()))
+        worst = min(worst, cos)
+        assert cos >= cos_min, "grad cosine %s: %.5f" % (n, cos)
+        assert abs(float(got.norm()) / float(r.norm()) - 1.0) <= norm_tol, "grad norm %s: %.4e vs %.4e" % (n, got.norm(), r.norm())
+    return worst
 
 
 def autocast_logit_error(o):
@@ -152,6 +174,6 @@ def test_step_bf16_config1():
     ours = np.linalg.norm(diff) / np.linalg.norm(g["lab_logits"].astype(np.float64))
     floor = autocast_logit_error(o)
     print("bf16 logits rel-L2: ours %.3e, torch autocast floor %.3e" % (ours, floor))
-    assert ours <= 1.5 * floor + 2e-3
-    w = check_grads(o, 6e-2, 0.3)
-    print("worst grad-norm rel err %.3e" % w)
+    assert ours <= 2.0 * floor        # our residual stream is stored in bf16; autocast keeps LN outputs / residuals in fp32
+    w = check_grads_vs_oracle(o, 0.99, 0.08)
+    print("worst grad cosine %.5f" % w)
