@@ -27,7 +27,16 @@ constexpr uint32_t P_BYTES = TQ * TK * 2;         // 32 KB: [128 x 128] bf16 as 
 struct FwdSmem {
   uint64_t bar_q, bar_k, bar_v, bar_s, bar_o;
   uint32_t tmem_base;
+  float xfirst[2][TQ];     // first-tile row maxima of the two column halves
+  float xmax[2][2][TQ];    // [tile parity][column half][row]
+  float xsum[2][TQ];
 };
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // P (or dS) row `r`: 32 consecutive columns starting at c32*32 -> bf16 into the swizzled [128 x 128] tile
 __device__ __forceinline__ void store_p32(uint8_t* sP, int r, int c32, const float (&p)[32]) {
@@ -43,7 +52,10 @@ __device__ __forceinline__ void store_p32(uint8_t* sP, int r, int c32, const flo
   }
 }
 
-__global__ void __launch_bounds__(128, 2)
+// Forward.  256 threads: two threads per query row (warp w reads TMEM lane quarter w & 3 and owns the column half
+// w >> 2 of S and of O), two CTAs per SM.  Online softmax with a reference exponent that lags one key tile behind the
+// running maximum (exact after the final normalisation; only the first tile needs a true max pass).
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
@@ -54,7 +66,9 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
   uint8_t* sP = smem + 3 * TILE_BYTES;
   FwdSmem* sh = reinterpret_cast<FwdSmem*>(smem + 3 * TILE_BYTES + P_BYTES);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, ch = warp >> 2;
+  const int r = lq * 32 + lane;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int L = a.L, H = a.nh * D, A = a.A;
   const int mode = a.mode[b], tl = a.t_len[b];
@@ -73,7 +87,7 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(lq * 32) << 16);
 
   auto active = [&](int j) { return tile_any_allowed(mode, q_lo, q_hi, j * TK, min(j * TK + TK - 1, L - 1), A, tl); };
   auto next_active = [&](int j) { ++j; while (j < n_kv && !active(j)) ++j; return j; };
@@ -93,11 +107,14 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
   constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);
   constexpr uint32_t idesc_o = make_idesc_bf16(TQ, D, 0, 1);
   const float scale2 = 0.125f * kLog2e;
-  const int q = q_lo + tid;
-  float o_acc[D];
+  const int q = q_lo + r;
+  int m_lo, m_hi;
+  mask_row_interval(mode, min(q, L - 1), A, tl, L, m_lo, m_hi);
+  const uint32_t m_span = static_cast<uint32_t>(m_hi - m_lo);
+  float o_acc[32];
 #pragma unroll
-  for (int i = 0; i < D; ++i) o_acc[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+  float ref = 0.f, l_loc = 0.f;
   uint32_t it = 0;
 
   for (; j < n_kv; ++it) {
@@ -121,50 +138,52 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
       tma_load_2d(&tmQKV, &sh->bar_k, sK, H + h * D, row0 + jn * TK);
     }
     const bool full = tile_all_allowed(mode, q_lo, q_hi, k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L);
-    // pass 1: row maximum of the scaled, masked scores
-    float m_tile = -INFINITY;
+    const int kc0 = k_lo + ch * 64;     // first key column of this thread's half
+    if (it == 0) {
+      // true row maximum of the first tile seeds the reference exponent
+      float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_lane + c * 32, v);
-      tmem_ld_wait();
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_lane + ch * 64 + c * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int k = k_lo + c * 32 + i;
-        const bool ok = full || (k < L && mask_allowed(mode, q, k, A, tl));
-        m_tile = fmaxf(m_tile, ok ? __uint_as_float(v[i]) * scale2 : -INFINITY);
+        for (int i = 0; i < 32; ++i) {
+          const bool ok = full || (static_cast<uint32_t>(kc0 + c * 32 + i - m_lo) < m_span);
+          mx = fmaxf(mx, ok ? __uint_as_float(v[i]) * scale2 : -INFINITY);
+        }
       }
+      sh->xfirst[ch][r] = mx;
+      __syncthreads();
+      const float m0 = fmaxf(sh->xfirst[0][r], sh->xfirst[1][r]);
+      ref = m0 == -INFINITY ? 0.f : m0;
     }
-    const float m_new = fmaxf(m_run, m_tile);
-    const float m_use = m_new == -INFINITY ? 0.f : m_new;
-    const float alpha = m_run == -INFINITY ? 1.f : exp2f(m_run - m_use);
-    // pass 2: probabilities -> smem (bf16), row sum
-    float l_tile = 0.f;
+    float m_loc = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(t_lane + c * 32, v);
+      tmem_ld32(t_lane + ch * 64 + c * 32, v);
       tmem_ld_wait();
       float p[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int k = k_lo + c * 32 + i;
-        const bool ok = full || (k < L && mask_allowed(mode, q, k, A, tl));
-        p[i] = ok ? exp2f(__uint_as_float(v[i]) * scale2 - m_use) : 0.f;
-        l_tile += p[i];
+        const bool ok = full || (static_cast<uint32_t>(kc0 + c * 32 + i - m_lo) < m_span);
+        const float s2 = ok ? __uint_as_float(v[i]) * scale2 : -INFINITY;
+        m_loc = fmaxf(m_loc, s2);
+        p[i] = ex2(s2 - ref);
+        l_loc += p[i];
       }
       if (a.drop_on) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const uint32_t keep = dropout_keep8(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (k_lo + c * 32 + 8 * g) >> 3));
+        for (int g = 0; g < 2; ++g) {
+          const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (kc0 + c * 32 + 16 * g) >> 4));
 #pragma unroll
-          for (int i = 0; i < 8; ++i) p[8 * g + i] = ((keep >> i) & 1u) ? p[8 * g + i] * a.drop.scale : 0.f;
+          for (int i = 0; i < 16; ++i) p[16 * g + i] = keep16_bit(keep, i) ? p[16 * g + i] * a.drop.scale : 0.f;
         }
       }
-      store_p32(sP, tid, c, p);
+      store_p32(sP, r, ch * 2 + c, p);
     }
-    l_run = l_run * alpha + l_tile;
-    m_run = m_new;
+    sh->xmax[ph][ch][r] = m_loc;
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
@@ -178,28 +197,39 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
                   make_smem_desc_sw128(va + kk * 2048, 8192, 1024), idesc_o, kk > 0);
       umma_commit(&sh->bar_o);
     }
+    const float m_new = fmaxf(sh->xmax[ph][0][r], sh->xmax[ph][1][r]);
     mbar_wait(&sh->bar_o, ph);
     tc_fence_after();
     if (tid == 0 && jn < n_kv) {  // V buffer is free
       mbar_expect_tx(&sh->bar_v, TILE_BYTES);
       tma_load_2d(&tmQKV, &sh->bar_v, sV, 2 * H + h * D, row0 + jn * TK);
     }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld32(t_lane + 128 + c * 32, v);
+      tmem_ld32(t_lane + 128 + ch * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i) o_acc[i] += __uint_as_float(v[i]);
+    }
+    if (m_new > ref) {  // move the reference exponent up (both threads of a row take the same decision)
+      const float alpha = ex2(ref - m_new);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[i] *= alpha;
+      l_loc *= alpha;
+      ref = m_new;
     }
     j = jn;
   }
 
+  sh->xsum[ch][r] = l_loc;
+  tc_fence_before();
+  __syncthreads();
   if (q < L) {
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    bf16* dst = static_cast<bf16*>(a.ctx) + (static_cast<long>(row0) + q) * H + h * D;
+    const float l_row = sh->xsum[0][r] + sh->xsum[1][r];
+    const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
+    bf16* dst = static_cast<bf16*>(a.ctx) + (static_cast<long>(row0) + q) * H + h * D + ch * 32;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 4; ++c) {
       uint4 u;
       u.x = pack_bf16x2(o_acc[8 * c + 0] * inv, o_acc[8 * c + 1] * inv);
       u.y = pack_bf16x2(o_acc[8 * c + 2] * inv, o_acc[8 * c + 3] * inv);
@@ -207,10 +237,8 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
       u.w = pack_bf16x2(o_acc[8 * c + 6] * inv, o_acc[8 * c + 7] * inv);
       reinterpret_cast<uint4*>(dst)[c] = u;
     }
-    a.lse[(static_cast<long>(b) * a.nh + h) * L + q] = m_run * kLn2 + logf(l_run);
+    if (ch == 0) a.lse[(static_cast<long>(b) * a.nh + h) * L + q] = ref * kLn2 + logf(l_row);
   }
-  tc_fence_before();
-  __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
@@ -248,26 +276,29 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 }
 
 struct BwdSmem {
-  uint64_t bar_kv, bar_q, bar_s, bar_o;
+  uint64_t bar_kv, bar_q[2], bar_s, bar_o;
   uint32_t tmem_base;
 };
 
-// One CTA per (key tile, head, sample); loops over the query tiles that can see this key tile.
+// Backward.  One CTA (256 threads, two per query row) per (key tile, head, sample); loops over the query tiles that
+// can see this key tile, Q / dO double-buffered.
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448)
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
   uint8_t* sK = smem;
   uint8_t* sV = smem + TILE_BYTES;
-  uint8_t* sQ = smem + 2 * TILE_BYTES;
-  uint8_t* sdO = smem + 3 * TILE_BYTES;
-  uint8_t* sP = smem + 4 * TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;     // [2]
+  uint8_t* sdO = smem + 4 * TILE_BYTES;    // [2]
+  uint8_t* sP = smem + 6 * TILE_BYTES;
   uint8_t* sdS = sP + P_BYTES;
   BwdSmem* sh = reinterpret_cast<BwdSmem*>(sdS + P_BYTES);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int lq = warp & 3, ch = warp >> 2;
+  const int r = lq * 32 + lane;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int L = a.L, H = a.nh * D, A = a.A;
   const int mode = a.mode[b], tl = a.t_len[b];
@@ -278,7 +309,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
-    mbar_init(&sh->bar_kv, 1); mbar_init(&sh->bar_q, 1); mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1);
+    mbar_init(&sh->bar_kv, 1); mbar_init(&sh->bar_q[0], 1); mbar_init(&sh->bar_q[1], 1);
+    mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&sh->tmem_base, 512); tmem_relinquish(); }
@@ -286,19 +318,22 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(lq * 32) << 16);
 
   auto active = [&](int i) { return tile_any_allowed(mode, i * TQ, min(i * TQ + TQ - 1, L - 1), k_lo, k_hi, A, tl); };
   auto next_active = [&](int i) { ++i; while (i < n_q && !active(i)) ++i; return i; };
   int i = next_active(-1);
 
+  auto load_q = [&](int qi, int buf) {
+    mbar_expect_tx(&sh->bar_q[buf], 2 * TILE_BYTES);
+    tma_load_2d(&tmQKV, &sh->bar_q[buf], sQ + buf * TILE_BYTES, h * D, row0 + qi * TQ);
+    tma_load_2d(&tmDO, &sh->bar_q[buf], sdO + buf * TILE_BYTES, h * D, row0 + qi * TQ);
+  };
   if (tid == 0 && i < n_q) {
     mbar_expect_tx(&sh->bar_kv, 2 * TILE_BYTES);
     tma_load_2d(&tmQKV, &sh->bar_kv, sK, H + h * D, row0 + k_lo);
     tma_load_2d(&tmQKV, &sh->bar_kv, sV, 2 * H + h * D, row0 + k_lo);
-    mbar_expect_tx(&sh->bar_q, 2 * TILE_BYTES);
-    tma_load_2d(&tmQKV, &sh->bar_q, sQ, h * D, row0 + i * TQ);
-    tma_load_2d(&tmDO, &sh->bar_q, sdO, h * D, row0 + i * TQ);
+    load_q(i, 0);
   }
 
   constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);     // S, dP : K-major x K-major
@@ -306,17 +341,19 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D, 0, 1);      // dQ    : dS (K-major) x K (MN-major)
   const float scale2 = 0.125f * kLog2e;
   const bool any = i < n_q;
+  const int kc0 = k_lo + ch * 64;
   uint32_t it = 0;
 
   for (; i < n_q; ++it) {
     const int in = next_active(i);
-    const uint32_t ph = it & 1u;
+    const uint32_t ph = it & 1u, buf = it & 1u;
     const int q_lo = i * TQ;
     if (tid == 0) {
       if (it == 0) mbar_wait(&sh->bar_kv, 0);
-      mbar_wait(&sh->bar_q, ph);
+      if (in < n_q) load_q(in, buf ^ 1u);        // the other buffer was released by the previous iteration's bar_o
+      mbar_wait(&sh->bar_q[buf], (it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO);
+      const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO + buf * TILE_BYTES);
 #pragma unroll
       for (int k = 0; k < D / 16; ++k)
         umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
@@ -325,52 +362,57 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
       umma_commit(&sh->bar_s);
     }
-    mbar_wait(&sh->bar_s, ph);
-    tc_fence_after();
-    const int q = q_lo + tid;
+    const int q = q_lo + r;
     const bool q_ok = q < L;
     const long st = (static_cast<long>(b) * a.nh + h) * L + (q_ok ? q : 0);
     const float lse2 = q_ok ? a.lse[st] * kLog2e : 0.f;
     const float delta = q_ok ? a.delta[st] : 0.f;
-    const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L);
+    int m_lo, m_hi;
+    mask_row_interval(mode, q_ok ? q : 0, A, tl, L, m_lo, m_hi);
+    const uint32_t m_span = q_ok ? static_cast<uint32_t>(m_hi - m_lo) : 0u;   // rows past the sequence end see nothing
+    const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L) &&
+                      (q_lo + TQ <= L);
+    mbar_wait(&sh->bar_s, ph);
+    tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t sv[32], dv[32];
-      tmem_ld32(t_lane + c * 32, sv);
-      tmem_ld32(t_lane + 128 + c * 32, dv);
+      tmem_ld32(t_lane + ch * 64 + c * 32, sv);
+      tmem_ld32(t_lane + 128 + ch * 64 + c * 32, dv);
       tmem_ld_wait();
       float p[32], ds[32];
-      uint32_t keep_bits = 0xffffffffu;
-      if (a.drop_on) {
-        keep_bits = 0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          keep_bits |= dropout_keep8(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + c * 32 + 8 * g) >> 3)) << (8 * g);
-      }
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const int k = k_lo + c * 32 + e;
-        const bool ok = q_ok && (full || (k < L && mask_allowed(mode, q, k, A, tl)));
-        const float pe = ok ? exp2f(__uint_as_float(sv[e]) * scale2 - lse2) : 0.f;
-        float dp = __uint_as_float(dv[e]);
-        float pd = pe;
-        if (a.drop_on) {
-          const bool kp = (keep_bits >> e) & 1u;
-          dp = kp ? dp * a.drop.scale : 0.f;
-          pd = kp ? pe * a.drop.scale : 0.f;
-        }
-        p[e] = pd;
-        ds[e] = pe * (dp - delta) * 0.125f;
+        const bool ok = full || (static_cast<uint32_t>(kc0 + c * 32 + e - m_lo) < m_span);
+        p[e] = ok ? ex2(__uint_as_float(sv[e]) * scale2 - lse2) : 0.f;
+        ds[e] = __uint_as_float(dv[e]);
       }
-      store_p32(sP, tid, c, p);
-      store_p32(sdS, tid, c, ds);
+      if (a.drop_on) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (kc0 + c * 32 + 16 * g) >> 4));
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const bool kp = keep16_bit(keep, e);
+            const float pe = p[16 * g + e];
+            ds[16 * g + e] = pe * ((kp ? ds[16 * g + e] * a.drop.scale : 0.f) - delta) * 0.125f;
+            p[16 * g + e] = kp ? pe * a.drop.scale : 0.f;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ds[e] = p[e] * (ds[e] - delta) * 0.125f;
+      }
+      store_p32(sP, r, ch * 2 + c, p);
+      store_p32(sdS, r, ch * 2 + c, ds);
     }
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), qa = smem_u32(sQ), ka = smem_u32(sK), da = smem_u32(sdO);
+      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK),
+                     da = smem_u32(sdO + buf * TILE_BYTES);
 #pragma unroll
       for (int kk = 0; kk < TQ / 16; ++kk)  // dV[k,d] += sum_q P[q,k] dO[q,d]
         umma_bf16(tmem + 256, make_smem_desc_sw128(pa + kk * 2048, TILE_BYTES, 1024),
@@ -387,56 +429,47 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
     mbar_wait(&sh->bar_o, ph);
     tc_fence_after();
-    if (tid == 0 && in < n_q) {  // Q / dO buffers are free
-      mbar_expect_tx(&sh->bar_q, 2 * TILE_BYTES);
-      tma_load_2d(&tmQKV, &sh->bar_q, sQ, h * D, row0 + in * TQ);
-      tma_load_2d(&tmDO, &sh->bar_q, sdO, h * D, row0 + in * TQ);
-    }
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld32(t_lane + 384 + c * 32, v);
+      tmem_ld32(t_lane + 384 + ch * 32, v);
       tmem_ld_wait();
       if (q_ok) {
-        float* dst = a.dq_acc + (static_cast<long>(row0) + q) * H + h * D + c * 32;
+        float* dst = a.dq_acc + (static_cast<long>(row0) + q) * H + h * D + ch * 32;
 #pragma unroll
         for (int e = 0; e < 32; e += 4)
           atomicAdd(reinterpret_cast<float4*>(dst + e), make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
                                                                     __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
       }
     }
+    tc_fence_before();
     i = in;
   }
 
-  // epilogue: dV, dK rows of this key tile
-  // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only the stores are predicated on k < L.
-  // `any` is uniform across the CTA (a key tile no query tile can see gets exact zeros).
-  const int k = k_lo + tid;
-  bf16* dk_dst = static_cast<bf16*>(a.dqkv) + (static_cast<long>(row0) + (k < L ? k : 0)) * 3 * H + H + h * D;
+  // epilogue: dV, dK rows of this key tile.  tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only
+  // the stores are predicated on k < L.  `any` is uniform across the CTA (an unseen key tile gets exact zeros).
+  const int k = k_lo + r;
+  bf16* dk_dst = static_cast<bf16*>(a.dqkv) + (static_cast<long>(row0) + (k < L ? k : 0)) * 3 * H + H + h * D + ch * 32;
   bf16* dv_dst = dk_dst + H;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     bf16* dst = which == 0 ? dv_dst : dk_dst;
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      if (any) {
-        tmem_ld32(t_lane + 256 + which * 64 + c * 32, v);
-        tmem_ld_wait();
-      } else {
+    uint32_t v[32];
+    if (any) {
+      tmem_ld32(t_lane + 256 + which * 64 + ch * 32, v);
+      tmem_ld_wait();
+    } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = 0u;
-      }
-      if (k < L) {
+      for (int e = 0; e < 32; ++e) v[e] = 0u;
+    }
+    if (k < L) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-          u.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-          u.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-          u.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + e) = u;
-        }
+      for (int e = 0; e < 32; e += 8) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        u.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        u.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+        u.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+        *reinterpret_cast<uint4*>(dst + e) = u;
       }
     }
   }
@@ -445,8 +478,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
-constexpr uint32_t kFwdSmem = 1024 + 3 * TILE_BYTES + P_BYTES + 128;
-constexpr uint32_t kBwdSmem = 1024 + 4 * TILE_BYTES + 2 * P_BYTES + 128;
+constexpr uint32_t kFwdSmem = 1024 + 3 * TILE_BYTES + P_BYTES + sizeof(FwdSmem) + 64;
+constexpr uint32_t kBwdSmem = 1024 + 6 * TILE_BYTES + 2 * P_BYTES + sizeof(BwdSmem) + 64;
 
 }  // namespace
 
@@ -462,7 +495,7 @@ int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s) {
     attr = true;
   }
   dim3 grid((a.L + TQ - 1) / TQ, a.nh, a.B);
-  attn_fwd_tc05_kernel<<<grid, 128, kFwdSmem, s>>>(tm, a);
+  attn_fwd_tc05_kernel<<<grid, 256, kFwdSmem, s>>>(tm, a);
   MV_LAUNCH_CHECK();
   return 0;
 }
@@ -487,7 +520,7 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
                                                                              static_cast<int>(rows), a.L, a.nh);
   MV_LAUNCH_CHECK();
   dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
-  attn_bwd_tc05_kernel<<<grid, 128, kBwdSmem, s>>>(tmQKV, tmDO, a);
+  attn_bwd_tc05_kernel<<<grid, 256, kBwdSmem, s>>>(tmQKV, tmDO, a);
   MV_LAUNCH_CHECK();
   attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
   MV_LAUNCH_CHECK();

@@ -73,51 +73,66 @@ __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
 
-// ---- dropout RNG: Philox4x32-10, one call -> 8 x 16-bit lanes ----
-// Keyed by (seed, site); counter = 64-bit element-group index (8 consecutive elements of a row).
-// The same (seed, site, group) regenerates the same keep-mask in forward and backward, so no mask
-// tensor is ever stored.
+// ---- dropout RNG: Philox4x32-7, one call -> 16 x 8-bit lanes ----
+// Keyed by (seed, site); counter = 64-bit element-group index (16 consecutive elements of a row).
+// The same (seed, site, group) regenerates the same keep-mask in forward and backward, so no mask tensor is ever
+// stored.  8-bit thresholds: the effective drop probability is round(256 p) / 256 (p = 0.1 -> 0.1016) and the
+// keep-scale uses the effective value, so dropout stays unbiased.
 struct DropoutCfg {
   float p;             // drop probability as configured
-  uint32_t thresh16;   // drop iff r16 < thresh16
-  float scale;         // 1 / (1 - thresh16/65536)
+  uint32_t thresh4;    // the 8-bit threshold replicated in 4 bytes: element dropped iff its random byte < threshold
+  float scale;         // 1 / (1 - threshold/256)
   uint64_t seed;       // per-step seed
 };
 
 __host__ __device__ inline DropoutCfg make_dropout(float p, uint64_t seed) {
   DropoutCfg d;
   d.p = p;
-  uint32_t t = static_cast<uint32_t>(p * 65536.0f + 0.5f);
-  if (t > 65535u) t = 65535u;
-  d.thresh16 = t;
-  d.scale = 1.0f / (1.0f - static_cast<float>(t) / 65536.0f);
+  uint32_t t = static_cast<uint32_t>(p * 256.0f + 0.5f);
+  if (t > 255u) t = 255u;
+  d.thresh4 = t * 0x01010101u;
+  d.scale = 1.0f / (1.0f - static_cast<float>(t) / 256.0f);
   d.seed = seed;
   return d;
 }
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                               uint32_t k1) {
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  for (int i = 0; i < 7; ++i) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0, n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1, n3 = static_cast<uint32_t>(p0);
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   return make_uint4(c0, c1, c2, c3);
 }
 
-// keep-mask (bit i = element i kept) for the 8 consecutive elements of group `g` at dropout site `site`
-__device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, uint32_t site, uint64_t g) {
-  const uint4 r = philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), site, 0x4d56u,
-                                static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-  uint32_t m = 0;
-  m |= ((r.x & 0xFFFFu) >= d.thresh16) << 0; m |= ((r.x >> 16) >= d.thresh16) << 1;
-  m |= ((r.y & 0xFFFFu) >= d.thresh16) << 2; m |= ((r.y >> 16) >= d.thresh16) << 3;
-  m |= ((r.z & 0xFFFFu) >= d.thresh16) << 4; m |= ((r.z >> 16) >= d.thresh16) << 5;
-  m |= ((r.w & 0xFFFFu) >= d.thresh16) << 6; m |= ((r.w >> 16) >= d.thresh16) << 7;
-  return m;
+// keep-mask for the 16 consecutive elements of group `g` at dropout site `site`: byte i of the result (word i/4,
+// byte i%4) is 0xFF iff element i is kept.
+__device__ __forceinline__ uint4 dropout_keep16(const DropoutCfg& d, uint32_t site, uint64_t g) {
+  uint4 r = philox4x32_7(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), site, 0x4d56u,
+                         static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+  r.x = __vcmpgeu4(r.x, d.thresh4); r.y = __vcmpgeu4(r.y, d.thresh4);
+  r.z = __vcmpgeu4(r.z, d.thresh4); r.w = __vcmpgeu4(r.w, d.thresh4);
+  return r;
+}
+__device__ __forceinline__ bool keep16_bit(const uint4& m, int i) {   // i in [0,16)
+  const uint32_t w = i < 4 ? m.x : (i < 8 ? m.y : (i < 12 ? m.z : m.w));
+  return (w >> (8 * (i & 3))) & 1u;
+}
+// keep bits (bit j = element j kept) of the 8-element half `half` (0/1) of a 16-group
+__device__ __forceinline__ uint32_t keep16_half_bits(const uint4& m, int half) {
+  const uint32_t a = half ? m.z : m.x, b = half ? m.w : m.y;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { bits |= ((a >> (8 * j)) & 1u) << j; bits |= ((b >> (8 * j)) & 1u) << (4 + j); }
+  return bits;
+}
+// 8 consecutive elements starting at flat element index e (e % 8 == 0): bit j = element j kept
+__device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, uint32_t site, uint64_t e) {
+  return keep16_half_bits(dropout_keep16(d, site, e >> 4), static_cast<int>((e >> 3) & 1));
 }
 
 // ---- warp / block reductions ----

@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
       } else if (epi == EPI_BIAS_RESID || epi == EPI_RESID) {
         if (p.drop_on && epi == EPI_BIAS_RESID) {
           const uint64_t e = static_cast<uint64_t>(m) * p.N + n;
-          const uint32_t keep = dropout_keep8(p.drop, p.drop_site, e >> 3);
-          v = ((keep >> (e & 7)) & 1u) ? v * p.drop.scale : 0.f;
+          const uint4 keep = dropout_keep16(p.drop, p.drop_site, e >> 4);
+          v = keep16_bit(keep, static_cast<int>(e & 15)) ? v * p.drop.scale : 0.f;
         }
         v += p.resid[m * p.ldr + n];
       } else if (epi == EPI_DGELU) {

@@ -82,11 +82,11 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[3
   } else if (epi == EPI_BIAS_RESID || epi == EPI_RESID) {
     if (p.drop_on && epi == EPI_BIAS_RESID) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint64_t grp = (static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N) + col0 + 8 * g) >> 3;
-        const uint32_t keep = dropout_keep8(p.drop, p.drop_site, grp);
+      for (int g = 0; g < 2; ++g) {
+        const uint64_t e = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N) + col0 + 16 * g;
+        const uint4 keep = dropout_keep16(p.drop, p.drop_site, e >> 4);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[8 * g + j] = ((keep >> j) & 1u) ? f[8 * g + j] * p.drop.scale : 0.f;
+        for (int j = 0; j < 16; ++j) f[16 * g + j] = keep16_bit(keep, j) ? f[16 * g + j] * p.drop.scale : 0.f;
       }
     }
     float r[32];

@@ -18,6 +18,19 @@ __host__ __device__ __forceinline__ bool mask_allowed(int mode, int q, int k, in
   }
 }
 
+// Every mode's allowed key set for a query row is ONE interval [lo, hi): the kernels test (unsigned)(k - lo) < hi - lo.
+//   Bidirectional [0, A + t_len) | Seq2Seq q<A: [0, A), else [0, q] | BAR q<A: [0, L), else [0, q] | Non-cross [0, A) or [A, L)
+__host__ __device__ __forceinline__ void mask_row_interval(int mode, int q, int A, int t_len, int L, int& lo, int& hi) {
+  lo = 0;
+  switch (mode) {
+    case MODE_BIDIR: hi = A + t_len; break;
+    case MODE_S2S: hi = q < A ? A : q + 1; break;
+    case MODE_BAR: hi = q < A ? L : q + 1; break;
+    default: if (q < A) hi = A; else { lo = A; hi = L; } break;
+  }
+  if (hi > L) hi = L;
+}
+
 // true iff at least one (q, k) with q in [q_lo, q_hi], k in [k_lo, k_hi] (inclusive) is allowed: exact, so tiles for
 // which this is false can be skipped without changing the result.
 __host__ __device__ __forceinline__ bool tile_any_allowed(int mode, int q_lo, int q_hi, int k_lo, int k_hi, int A,

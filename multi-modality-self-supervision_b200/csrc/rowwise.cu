@@ -61,7 +61,7 @@ __device__ __forceinline__ void row_stats(const float (&x)[kMaxChunks][8], int n
 }
 
 __device__ __forceinline__ void apply_dropout8(float (&v)[8], const DropoutCfg& d, uint32_t site, long row, int H, int col) {
-  const uint32_t keep = dropout_keep8(d, site, (static_cast<uint64_t>(row) * H + col) >> 3);
+  const uint32_t keep = dropout_keep8(d, site, static_cast<uint64_t>(row) * H + col);
 #pragma unroll
   for (int j = 0; j < 8; ++j) v[j] = ((keep >> j) & 1u) ? v[j] * d.scale : 0.f;
 }
