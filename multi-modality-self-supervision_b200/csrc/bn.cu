@@ -92,17 +92,28 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   }
 }
 
-// one thread per channel: merge the per-CTA partials, produce scale/shift, update the running statistics
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
-                                   float eps, int update_running, float* __restrict__ scale_shift /* [2][C] */) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per channel: lanes merge strided subsets of the per-CTA partials, then a shuffle tree of Chan updates;
+// lane 0 produces scale/shift and updates the running statistics
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* running_mean, float* running_var, float momentum, float eps,
+                                                          int update_running, float* __restrict__ scale_shift /* [2][C] */) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (c >= C) return;
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int p = 0; p < nparts; ++p) {
+  for (int p = lane; p < nparts; p += 32) {
     const float* e = partial + (static_cast<long>(p) * C + c) * 3;
     chan_merge(n, mean, m2, e[0], e[1], e[2]);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+    const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+    const float qb = __shfl_xor_sync(0xffffffffu, m2, o);
+    chan_merge(n, mean, m2, nb, mb, qb);
+  }
+  if (lane != 0) return;
   const float var = m2 / n;                      // biased: what normalisation uses
   const float invstd = rsqrtf(var + eps);
   const float sc = gamma[c] * invstd;
@@ -178,7 +189,7 @@ int bn_forward(const void* x, const void* resid, void* y, long rows, int C, cons
     if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
     else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
     MV_LAUNCH_CHECK();
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
+    bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
                                                       scale_shift);
     MV_LAUNCH_CHECK();
   } else {

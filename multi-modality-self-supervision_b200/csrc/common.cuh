@@ -60,6 +60,25 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// Fast exact-form GELU for the tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below
+// bf16 resolution), sharing ONE exponential between erf(x/sqrt2) and the Gaussian pdf: exp(-(x/sqrt2)^2) == exp(-x^2/2).
+// The fp32 check-mode kernels keep erff().
+__device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));   // exp(-x^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);            // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) { float c, p; gelu_fast_parts(x, c, p); return x * c; }
+__device__ __forceinline__ float gelu_fast_grad(float x) { float c, p; gelu_fast_parts(x, c, p); return fmaf(x, p, c); }
+
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>

@@ -21,10 +21,10 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 two epilogue groups (one per accumulator stage)
 constexpr int kMaxStages = 8;
 constexpr uint32_t STG_BYTES = 4096;  // one staging buffer: 32 rows x 128 B (swizzled)
-constexpr uint32_t STG_TOTAL = 4 /*warps*/ * 2 /*outputs*/ * 2 /*double buffer*/ * STG_BYTES;
+constexpr uint32_t STG_TOTAL = 8 /*epilogue warps*/ * 2 /*double buffer*/ * STG_BYTES;
 
 struct GemmParams {
   int M, N, K;
@@ -34,6 +34,7 @@ struct GemmParams {
   const bf16* resid; long ldr;
   const bf16* aux; long ldaux;
   int has_c2, accumulate;
+  bf16* c2; long ldc2;
   int drop_on; uint32_t drop_site; DropoutCfg drop;
 };
 
@@ -75,7 +76,7 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[3
   }
   if (epi == EPI_BIAS_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { pre[j] = f[j]; f[j] = gelu_erf(f[j]); }
+    for (int j = 0; j < 32; ++j) { pre[j] = f[j]; f[j] = gelu_fast(f[j]); }
   } else if (epi == EPI_BIAS_TANH) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
@@ -97,7 +98,7 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[3
     float a[32];
     load_row32(p.aux, p.ldaux, row, col0, row_ok && col0 < p.N, a);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] *= gelu_erf_grad(a[j]);
+    for (int j = 0; j < 32; ++j) f[j] *= gelu_fast_grad(a[j]);
   }
 }
 
@@ -124,8 +125,7 @@ __device__ __forceinline__ void stage_f32(uint8_t* stg, int lane, const float (&
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -147,7 +147,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
-    if (p.has_c2) tma_prefetch_desc(&tmC2);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
@@ -245,16 +244,22 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
-    uint8_t* my_stg = stg_base + static_cast<uint32_t>(q) * (4 * STG_BYTES);
-    int acc = 0;
+    // Two groups of four warps; group g drains accumulator stage g, i.e. every other work unit of this CTA, so two
+    // tiles' epilogues (bias / GELU / dropout / residual math) are in flight while the MMA warp runs ahead.
+    const int q = warp & 3;             // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;    // == accumulator stage
+    uint8_t* my_stg = stg_base + static_cast<uint32_t>((warp - 2)) * (2 * STG_BYTES);
     uint32_t acc_phase = 0;
     int buf = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    int it = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int acc = grp;
       const int tile = unit / p.splits;
       const int m0 = (tile % p.m_tiles) * BM;
       const int n0 = (tile / p.m_tiles) * BN;
       mbar_wait(&bars->tfull[acc], acc_phase);
+      acc_phase ^= 1u;
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
@@ -264,7 +269,6 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) tma_wait_group_read<1>();  // staging buffer `buf` (used two chunks ago) is free again
         __syncwarp();
         uint8_t* s1 = my_stg + static_cast<uint32_t>(buf) * STG_BYTES;
-        uint8_t* s2 = my_stg + static_cast<uint32_t>(2 + buf) * STG_BYTES;
         if constexpr (!OUT_F32) {
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
@@ -274,9 +278,20 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float f[32], pre[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            epilogue_apply(p, f, pre, row, n0 + c * 64 + half * 32, row_ok);
+            const int col0 = n0 + c * 64 + half * 32;
+            epilogue_apply(p, f, pre, row, col0, row_ok);
             stage_bf16_half(s1, lane, half, f);
-            if (p.has_c2) stage_bf16_half(s2, lane, half, pre);
+            if (p.has_c2 && row_ok && col0 < p.N) {
+              // pre-activation (second output): straight from registers, 64 contiguous bytes per row
+              uint4* dst = reinterpret_cast<uint4*>(p.c2 + static_cast<long>(row) * p.ldc2 + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 u;
+                u.x = pack_bf16x2(pre[8 * j + 0], pre[8 * j + 1]); u.y = pack_bf16x2(pre[8 * j + 2], pre[8 * j + 3]);
+                u.z = pack_bf16x2(pre[8 * j + 4], pre[8 * j + 5]); u.w = pack_bf16x2(pre[8 * j + 6], pre[8 * j + 7]);
+                dst[j] = u;
+              }
+            }
           }
         } else {
           uint32_t v[32];
@@ -302,14 +317,11 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (r0 < p.M && c0 < p.N) {
             if (p.accumulate) tma_reduce_add_2d(&tmC, s1, c0, r0);
             else tma_store_2d(&tmC, s1, c0, r0);
-            if (p.has_c2) tma_store_2d(&tmC2, s2, c0, r0);
           }
           tma_commit_group();
         }
         buf ^= 1;
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
     if (lane == 0) tma_wait_group<0>();
     __syncwarp();
@@ -335,7 +347,7 @@ inline int pick_stages(uint32_t stage_b) {
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
-  CUtensorMap tmA, tmB, tmC, tmC2;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
   if (!d.a_mn) rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.K, d.M, d.lda * 2, BK, BM);
   else rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.M, d.K, d.lda * 2, 64, BK);
@@ -346,12 +358,6 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   if (OUT_F32) rc = tmap_encode_2d(&tmC, TMAP_F32, d.C, d.N, d.M, d.ldc * 4, 32, 32);
   else rc = tmap_encode_2d(&tmC, TMAP_BF16, d.C, d.N, d.M, d.ldc * 2, 64, 32);
   if (rc) return rc;
-  if (d.C2) {
-    rc = tmap_encode_2d(&tmC2, TMAP_BF16, d.C2, d.N, d.M, d.ldc2 * 2, 64, 32);
-    if (rc) return rc;
-  } else {
-    tmC2 = tmC;
-  }
   p.n_tiles = (d.N + BN - 1) / BN;
   p.stages = pick_stages(stage_bytes<BN>());
   // split-K only for fp32 reduce-add outputs (weight gradients): fill ~2 waves of SMs
@@ -376,7 +382,7 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
     MV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmC2, p);
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, p);
   MV_LAUNCH_CHECK();
   return 0;
 }
@@ -414,6 +420,7 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   MV_REQUIRE(d.A && d.B && d.C, "gemm: null operand");
   MV_REQUIRE(!d.accumulate || d.c_f32, "gemm: accumulate requires fp32 output");
   MV_REQUIRE(!(d.C2 && d.c_f32), "gemm: pre-activation output only with activation-dtype C");
+  MV_REQUIRE(!d.C2 || (d.epi == EPI_BIAS_GELU && d.N % 32 == 0 && d.ldc2 % 8 == 0), "gemm: C2 needs EPI_BIAS_GELU, N %% 32 == 0");
   if (d.epi == EPI_BIAS || d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_RESID || d.epi == EPI_BIAS_TANH)
     MV_REQUIRE(d.bias != nullptr, "gemm: epilogue %d needs bias", d.epi);
   if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID)
@@ -431,6 +438,7 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   p.resid = static_cast<const bf16*>(d.resid); p.ldr = d.ldr;
   p.aux = static_cast<const bf16*>(d.aux); p.ldaux = d.ldaux;
   p.has_c2 = d.C2 != nullptr; p.accumulate = d.accumulate;
+  p.c2 = static_cast<bf16*>(d.C2); p.ldc2 = d.ldc2;
   p.drop_on = d.drop_on; p.drop_site = d.drop_site; p.drop = d.drop;
   const int bn = pick_bn(p.m_tiles, d.N, device_sm_count(), d.accumulate != 0);
   switch (bn) {

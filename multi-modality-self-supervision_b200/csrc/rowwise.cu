@@ -153,26 +153,22 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T*
   }
 }
 
-// LayerNorm backward. 8 warps / CTA, each warp strides over rows; per-lane partial sums of dgamma / dbeta / dbias are
-// reduced across the CTA's warps through shared memory, then one fp32 atomicAdd per column per CTA.
+// LayerNorm backward.  8 warps / CTA, each warp strides over rows.  The column reductions (dgamma, dbeta, dbias) are
+// accumulated in WARP-PRIVATE shared-memory rows (each lane owns its columns, so no synchronisation), which keeps the
+// register budget low enough for two CTAs per SM; at the end the 8 rows are summed and one fp32 atomicAdd per column
+// per CTA goes to the gradient arena.  Algorithmic traffic: read dy, x; write dx (+ dx_drop).
 template <typename T>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
-                                                     const float* __restrict__ gamma, T* __restrict__ dx,
-                                                     T* __restrict__ dx_drop, float* dgamma, float* dbeta, float* dbias,
-                                                     int rows, int H, float eps, int in_drop, int out_drop, uint32_t site,
-                                                     DropoutCfg drop) {
-  extern __shared__ float red[];  // [8][H]
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                        const float* __restrict__ gamma, T* __restrict__ dx,
+                                                        T* __restrict__ dx_drop, float* dgamma, float* dbeta, float* dbias,
+                                                        int rows, int H, float eps, int in_drop, int out_drop, uint32_t site,
+                                                        DropoutCfg drop) {
+  extern __shared__ float red[];  // [8 warps][3][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = H >> 3;
-  float g[kMaxChunks][8];
-  float ag[kMaxChunks][8], ab[kMaxChunks][8], abias[kMaxChunks][8];
-#pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nch) load8<float>(gamma + ch * 8, g[c]);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ag[c][j] = 0.f; ab[c][j] = 0.f; abias[c][j] = 0.f; }
-  }
+  float* my = red + static_cast<size_t>(warp) * 3 * H;
+  for (int i = lane; i < 3 * H; i += 32) my[i] = 0.f;
+  __syncwarp();
   for (long row = static_cast<long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long>(gridDim.x) * 8) {
     float xv[kMaxChunks][8], dv[kMaxChunks][8];
 #pragma unroll
@@ -189,16 +185,24 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < kMaxChunks; ++c) {
-      if (lane + 32 * c < nch) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        float g[8], ag[8], ab[8];
+        load8<float>(gamma + ch * 8, g);
+        load8<float>(my + ch * 8, ag);
+        load8<float>(my + H + ch * 8, ab);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (xv[c][j] - mean) * rstd;
-          const float gy = dv[c][j] * g[c][j];
-          s1 += gy; s2 += gy * xh;
-          ag[c][j] += dv[c][j] * xh;
-          ab[c][j] += dv[c][j];
+          ag[j] += dv[c][j] * xh;
+          ab[j] += dv[c][j];
+          dv[c][j] *= g[j];              // dv <- dy * gamma
+          s1 += dv[c][j];
+          s2 += dv[c][j] * xh;
           xv[c][j] = xh;
         }
+        store8<float>(my + ch * 8, ag);
+        store8<float>(my + H + ch * 8, ab);
       }
     }
     s1 = warp_sum(s1) / H;
@@ -209,37 +213,31 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T* __restrict__ dy, c
       if (ch < nch) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[c][j] * g[c][j] - s1 - xv[c][j] * s2);
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[c][j] - s1 - xv[c][j] * s2);
         store8<T>(dx + row * H + ch * 8, o);
         if (out_drop) {
           apply_dropout8(o, drop, site, row, H, ch * 8);
           store8<T>(dx_drop + row * H + ch * 8, o);
         }
+        if (dbias) {
+          float acc[8];
+          load8<float>(my + 2 * H + ch * 8, acc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) abias[c][j] += o[j];
+          for (int j = 0; j < 8; ++j) acc[j] += o[j];
+          store8<float>(my + 2 * H + ch * 8, acc);
+        }
       }
     }
   }
-  // cross-warp reduction, one quantity at a time
-  for (int which = 0; which < 3; ++which) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+    const int which = i / H, col = i - which * H;
     float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dbias);
-    if (dst == nullptr) continue;  // uniform across the CTA
-    __syncthreads();
+    if (dst == nullptr) continue;
+    float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nch)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          red[warp * H + ch * 8 + j] = which == 0 ? ag[c][j] : (which == 1 ? ab[c][j] : abias[c][j]);
-    }
-    __syncthreads();
-    for (int col = threadIdx.x; col < H; col += blockDim.x) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w * H + col];
-      atomicAdd(dst + col, s);
-    }
+    for (int w = 0; w < 8; ++w) s += red[static_cast<size_t>(w) * 3 * H + i];
+    atomicAdd(dst + col, s);
   }
 }
 
@@ -465,9 +463,15 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx
   if (rows <= 0) return 0;
   MV_REQUIRE(!out_drop || dx_drop != nullptr, "ln_bwd: out_drop needs dx_drop");
   int grid = (rows + 7) / 8;
-  const int cap = device_sm_count() * 4;
+  const int cap = device_sm_count() * 2;
   if (grid > cap) grid = cap;
-  const size_t smem = static_cast<size_t>(8) * H * sizeof(float);
+  const size_t smem = static_cast<size_t>(8) * 3 * H * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    attr = true;
+  }
   MV_DISPATCH_T(f32, (ln_bwd_kernel<T><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
                                                                static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
                                                                dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
