@@ -65,7 +65,8 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // The fp32 check-mode kernels keep erff().
 __device__ __forceinline__ void gelu_fast_parts(float x, float& cdf, float& pdf) {
   const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));   // exp(-x^2/2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);

@@ -7,8 +7,8 @@
 // (SURVEY.md §2b K1,K4-K6,K8-K11,K13): Q/K/V, attention-output, FFN, image projection, pooler, MLM transform and
 // decoder, in forward / dgrad / wgrad form (see gemm.h for the three operand-major combinations).
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = epilogue (TMEM lane
-// quarter = warp_id % 4). Grid = min(#SMs, work units); unit = (m_tile, n_tile, k_split), m fastest so that CTAs
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 and 6-9 = two epilogue groups,
+// one per TMEM accumulator stage (TMEM lane quarter = warp_id % 4); residual / GELU-backward operand tiles are TMA-prefetched one chunk ahead into the staging ring. Grid = min(#SMs, work units); unit = (m_tile, n_tile, k_split), m fastest so that CTAs
 // running concurrently share the weight tile through L2.
 #include "gemm.h"
 #include "tc05.cuh"
@@ -21,20 +21,19 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 two epilogue groups (one per accumulator stage)
+constexpr int kThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
 constexpr int kMaxStages = 8;
 constexpr uint32_t STG_BYTES = 4096;  // one staging buffer: 32 rows x 128 B (swizzled)
-constexpr uint32_t STG_TOTAL = 8 /*epilogue warps*/ * 2 /*double buffer*/ * STG_BYTES;
+// per epilogue warp: out[2] + second[2], where `second` is either the pre-activation output (EPI_BIAS_GELU) or the
+// TMA-loaded epilogue INPUT tile (residual / GELU-backward operand) — the two never coexist
+constexpr uint32_t STG_TOTAL = 8 /*epilogue warps*/ * 2 * STG_BYTES;
 
 struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles, splits, kb_total, kb_per_split, stages;
   int epi;
   const float* bias;
-  const bf16* resid; long ldr;
-  const bf16* aux; long ldaux;
-  int has_c2, accumulate;
-  bf16* c2; long ldc2;
+  int has_c2, has_in, accumulate;
   int drop_on; uint32_t drop_site; DropoutCfg drop;
 };
 
@@ -43,35 +42,40 @@ struct Barriers {
   uint64_t empty[kMaxStages];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t in_bar[8][2];    // per epilogue warp, per input buffer
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void load_row32(const bf16* base, long ld, int row, int col, bool ok, float (&out)[32]) {
-  if (ok) {
-    const uint4* p = reinterpret_cast<const uint4*>(base + static_cast<long>(row) * ld + col);
+// read 32 bf16 (columns half*32 .. +32 of row `lane`) from a swizzled [32 x 64] staging tile
+__device__ __forceinline__ void unstage_bf16_half(const uint8_t* stg, int lane, int half, float (&out)[32]) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 u = __ldg(p + j);
-      float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-      out[8 * j + 0] = a.x; out[8 * j + 1] = a.y; out[8 * j + 2] = b.x; out[8 * j + 3] = b.y;
-      out[8 * j + 4] = c.x; out[8 * j + 5] = c.y; out[8 * j + 6] = d.x; out[8 * j + 7] = d.y;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) out[j] = 0.f;
+  for (int j = 0; j < 4; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + sw128_off(lane, half * 4 + j));
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    out[8 * j + 0] = a.x; out[8 * j + 1] = a.y; out[8 * j + 2] = b.x; out[8 * j + 3] = b.y;
+    out[8 * j + 4] = c.x; out[8 * j + 5] = c.y; out[8 * j + 6] = d.x; out[8 * j + 7] = d.y;
   }
 }
 
 // Epilogue math on 32 consecutive columns [col0, col0+32) of output row `row`.
-// f: accumulators in, final values out; pre: pre-activation (only written for EPI_BIAS_GELU).
-__device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[32], float (&pre)[32], int row, int col0,
-                                               bool row_ok) {
+// f: accumulators in, final values out; pre: pre-activation (EPI_BIAS_GELU); in: residual / GELU-backward operand.
+__device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[32], float (&pre)[32], const float (&in)[32],
+                                               int row, int col0) {
   const int epi = p.epi;
   if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH) {
+    if (col0 + 32 <= p.N) {      // 8 x 16-byte broadcast loads (col0 % 32 == 0, arena tensors are 256 B aligned)
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int c = col0 + j;
-      f[j] += (c < p.N) ? __ldg(p.bias + c) : 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(bp + j);
+        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int c = col0 + j;
+        f[j] += (c < p.N) ? __ldg(p.bias + c) : 0.f;
+      }
     }
   }
   if (epi == EPI_BIAS_GELU) {
@@ -90,15 +94,11 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[3
         for (int j = 0; j < 16; ++j) f[16 * g + j] = keep16_bit(keep, j) ? f[16 * g + j] * p.drop.scale : 0.f;
       }
     }
-    float r[32];
-    load_row32(p.resid, p.ldr, row, col0, row_ok && col0 < p.N, r);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] += r[j];
+    for (int j = 0; j < 32; ++j) f[j] += in[j];
   } else if (epi == EPI_DGELU) {
-    float a[32];
-    load_row32(p.aux, p.ldaux, row, col0, row_ok && col0 < p.N, a);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] *= gelu_fast_grad(a[j]);
+    for (int j = 0; j < 32; ++j) f[j] *= gelu_fast_grad(in[j]);
   }
 }
 
@@ -125,7 +125,9 @@ __device__ __forceinline__ void stage_f32(uint8_t* stg, int lane, const float (&
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
+                 const GemmParams p) {
+  // tmX: the second epilogue tensor — pre-activation OUTPUT (has_c2) or residual / aux INPUT (has_in); [M, N] bf16
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -147,6 +149,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if (p.has_c2 || p.has_in) tma_prefetch_desc(&tmX);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], 1);
@@ -155,6 +158,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&bars->tfull[a], 1);
       mbar_init(&bars->tempty[a], 4);
     }
+    for (int w = 0; w < 8; ++w) { mbar_init(&bars->in_bar[w][0], 1); mbar_init(&bars->in_bar[w][1], 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -244,63 +248,81 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncwarp();
   } else {
     // ===================== epilogue warps =====================
-    // Two groups of four warps; group g drains accumulator stage g, i.e. every other work unit of this CTA, so two
-    // tiles' epilogues (bias / GELU / dropout / residual math) are in flight while the MMA warp runs ahead.
+    // Two groups of four warps (2-5 and 6-9).  Group g drains accumulator stage g, i.e. every other work unit of this
+    // CTA, so two tiles' epilogues overlap each other and the MMA warp's next mainloop.  Staging per warp: 2 x 4 KB.
+    //   plain epilogues : out double-buffered
+    //   residual / dGELU: the TMA-prefetched INPUT tile is overwritten in place by the output, double-buffered
+    //   GELU + pre-act  : buffer 0 = output, buffer 1 = pre-activation (single-buffered; the other group fills the gap)
     const int q = warp & 3;             // TMEM lane quarter this warp may read
-    const int grp = (warp - 2) >> 2;    // == accumulator stage
-    uint8_t* my_stg = stg_base + static_cast<uint32_t>((warp - 2)) * (2 * STG_BYTES);
+    const int ew = warp - 2;            // epilogue warp index 0..7
+    const int grp = ew >> 2;            // == accumulator stage
+    uint8_t* my_stg = stg_base + static_cast<uint32_t>(ew) * (2 * STG_BYTES);
+    uint64_t* in_bar = bars->in_bar[ew];
+    const int acc = grp;
     uint32_t acc_phase = 0;
-    int buf = 0;
+    uint32_t cnt = 0;            // chunks processed so far by this warp: buffer = cnt & 1, input parity = (cnt >> 1) & 1
+    const bool has_in = p.has_in != 0, has_c2 = p.has_c2 != 0;
+    auto issue_in = [&](uint32_t chunk_cnt, int m0, int n0, int c) {   // lane 0 only: prefetch the epilogue input tile
+      const uint32_t b = chunk_cnt & 1u;
+      mbar_expect_tx(&in_bar[b], STG_BYTES);
+      tma_load_2d(&tmX, &in_bar[b], my_stg + b * STG_BYTES, n0 + c * 64, m0 + q * 32);
+    };
     int it = 0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
-      const int acc = grp;
       const int tile = unit / p.splits;
       const int m0 = (tile % p.m_tiles) * BM;
       const int n0 = (tile / p.m_tiles) * BN;
+      if (has_in && lane == 0) {       // overlaps the wait for the accumulator
+        tma_wait_group_read<0>();      // every store that read my two buffers has drained
+        issue_in(cnt, m0, n0, 0);
+      }
       mbar_wait(&bars->tfull[acc], acc_phase);
       acc_phase ^= 1u;
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c) {
-        if (lane == 0) tma_wait_group_read<1>();  // staging buffer `buf` (used two chunks ago) is free again
+      for (int c = 0; c < NCHUNK; ++c, ++cnt) {
+        const uint32_t buf = has_c2 ? 0u : (cnt & 1u);
+        if (lane == 0) {
+          if (has_in) {
+            if (c + 1 < NCHUNK) {
+              tma_wait_group_read<0>();              // the other buffer's last store has been read out
+              issue_in(cnt + 1, m0, n0, c + 1);      // input tile of the next chunk
+            }
+          } else if (has_c2) {
+            tma_wait_group_read<0>();
+          } else {
+            tma_wait_group_read<1>();                // out[buf] (stored two chunks ago) is free again
+          }
+        }
         __syncwarp();
-        uint8_t* s1 = my_stg + static_cast<uint32_t>(buf) * STG_BYTES;
+        uint8_t* s1 = my_stg + buf * STG_BYTES;
+        uint8_t* s2 = has_c2 ? my_stg + STG_BYTES : s1;     // pre-activation out, or the in-place input tile
+        if (has_in) mbar_wait(&in_bar[buf], (cnt >> 1) & 1u);
         if constexpr (!OUT_F32) {
 #pragma unroll 1
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
             tmem_ld32(t_row + static_cast<uint32_t>(c * 64 + half * 32), v);
             tmem_ld_wait();
-            float f[32], pre[32];
+            float f[32], pre[32], in[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            const int col0 = n0 + c * 64 + half * 32;
-            epilogue_apply(p, f, pre, row, col0, row_ok);
+            if (has_in) unstage_bf16_half(s2, lane, half, in);
+            epilogue_apply(p, f, pre, in, row, n0 + c * 64 + half * 32);
             stage_bf16_half(s1, lane, half, f);
-            if (p.has_c2 && row_ok && col0 < p.N) {
-              // pre-activation (second output): straight from registers, 64 contiguous bytes per row
-              uint4* dst = reinterpret_cast<uint4*>(p.c2 + static_cast<long>(row) * p.ldc2 + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 u;
-                u.x = pack_bf16x2(pre[8 * j + 0], pre[8 * j + 1]); u.y = pack_bf16x2(pre[8 * j + 2], pre[8 * j + 3]);
-                u.z = pack_bf16x2(pre[8 * j + 4], pre[8 * j + 5]); u.w = pack_bf16x2(pre[8 * j + 6], pre[8 * j + 7]);
-                dst[j] = u;
-              }
-            }
+            if (p.has_c2) stage_bf16_half(s2, lane, half, pre);
           }
         } else {
           uint32_t v[32];
           tmem_ld32(t_row + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
-          float f[32], pre[32];
+          float f[32], pre[32], in[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          epilogue_apply(p, f, pre, row, n0 + c * 32, row_ok);
+          epilogue_apply(p, f, pre, in, row, n0 + c * 32);
           stage_f32(s1, lane, f);
         }
         if (c == NCHUNK - 1) {
@@ -317,10 +339,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (r0 < p.M && c0 < p.N) {
             if (p.accumulate) tma_reduce_add_2d(&tmC, s1, c0, r0);
             else tma_store_2d(&tmC, s1, c0, r0);
+            if (p.has_c2) tma_store_2d(&tmX, s2, c0, r0);
           }
           tma_commit_group();
         }
-        buf ^= 1;
       }
     }
     if (lane == 0) tma_wait_group<0>();
@@ -347,7 +369,7 @@ inline int pick_stages(uint32_t stage_b) {
 
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmX;
   int rc;
   if (!d.a_mn) rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.K, d.M, d.lda * 2, BK, BM);
   else rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.M, d.K, d.lda * 2, 64, BK);
@@ -357,6 +379,15 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   if (rc) return rc;
   if (OUT_F32) rc = tmap_encode_2d(&tmC, TMAP_F32, d.C, d.N, d.M, d.ldc * 4, 32, 32);
   else rc = tmap_encode_2d(&tmC, TMAP_BF16, d.C, d.N, d.M, d.ldc * 2, 64, 32);
+  if (rc) return rc;
+  tmX = tmC;
+  if (d.C2) {
+    rc = tmap_encode_2d(&tmX, TMAP_BF16, d.C2, d.N, d.M, d.ldc2 * 2, 64, 32);
+  } else if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID) {
+    rc = tmap_encode_2d(&tmX, TMAP_BF16, d.resid, d.N, d.M, d.ldr * 2, 64, 32);
+  } else if (d.epi == EPI_DGELU) {
+    rc = tmap_encode_2d(&tmX, TMAP_BF16, d.aux, d.N, d.M, d.ldaux * 2, 64, 32);
+  }
   if (rc) return rc;
   p.n_tiles = (d.N + BN - 1) / BN;
   p.stages = pick_stages(stage_bytes<BN>());
@@ -382,7 +413,7 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
     MV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, p);
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmX, p);
   MV_LAUNCH_CHECK();
   return 0;
 }
@@ -424,9 +455,9 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_BIAS || d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_RESID || d.epi == EPI_BIAS_TANH)
     MV_REQUIRE(d.bias != nullptr, "gemm: epilogue %d needs bias", d.epi);
   if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID)
-    MV_REQUIRE(d.resid != nullptr && d.N % 32 == 0 && d.ldr % 8 == 0, "gemm: residual epilogue needs resid, N%%32==0");
+    MV_REQUIRE(d.resid != nullptr && d.N % 32 == 0 && d.ldr % 8 == 0 && !d.c_f32, "gemm: residual epilogue needs resid, N%%32==0, bf16 out");
   if (d.epi == EPI_DGELU)
-    MV_REQUIRE(d.aux != nullptr && d.N % 32 == 0 && d.ldaux % 8 == 0, "gemm: DGELU epilogue needs aux, N%%32==0");
+    MV_REQUIRE(d.aux != nullptr && d.N % 32 == 0 && d.ldaux % 8 == 0 && !d.c_f32, "gemm: DGELU epilogue needs aux, N%%32==0, bf16 out");
   GemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.m_tiles = (d.M + BM - 1) / BM;
@@ -435,10 +466,8 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   p.splits = 1; p.kb_per_split = p.kb_total; p.stages = 0;
   p.epi = d.epi;
   p.bias = d.bias;
-  p.resid = static_cast<const bf16*>(d.resid); p.ldr = d.ldr;
-  p.aux = static_cast<const bf16*>(d.aux); p.ldaux = d.ldaux;
   p.has_c2 = d.C2 != nullptr; p.accumulate = d.accumulate;
-  p.c2 = static_cast<bf16*>(d.C2); p.ldc2 = d.ldc2;
+  p.has_in = (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID || d.epi == EPI_DGELU) ? 1 : 0;
   p.drop_on = d.drop_on; p.drop_site = d.drop_site; p.drop = d.drop;
   const int bn = pick_bn(p.m_tiles, d.N, device_sm_count(), d.accumulate != 0);
   switch (bn) {

@@ -163,7 +163,23 @@ static void perf(const char* name, int M, int N, int K, int a_mn, int b_mn, int 
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dR); cudaFree(dbias);
 }
 
+static void perf_one(int which) {
+  switch (which) {
+    case 0: perf("QKV fwd", 27904, 2304, 768, 0, 0, 0, 0, EPI_BIAS); break;
+    case 1: perf("out-proj fwd", 27904, 768, 768, 0, 0, 0, 0, EPI_BIAS_RESID); break;
+    case 2: perf("FFN1 fwd", 27904, 3072, 768, 0, 0, 0, 0, EPI_BIAS_GELU); break;
+    case 3: perf("FFN2 fwd", 27904, 768, 3072, 0, 0, 0, 0, EPI_BIAS_RESID); break;
+    case 4: perf("FFN2 dgrad", 27904, 3072, 768, 0, 1, 0, 0, EPI_DGELU); break;
+    case 5: perf("FFN1 dgrad", 27904, 768, 3072, 0, 1, 0, 0, EPI_RESID); break;
+    case 6: perf("FFN1 wgrad", 3072, 768, 27904, 1, 1, 1, 1, EPI_NONE); break;
+    case 7: perf("QKV wgrad", 2304, 768, 27904, 1, 1, 1, 1, EPI_NONE); break;
+    case 8: perf("FFN1 fwd bias only", 27904, 3072, 768, 0, 0, 0, 0, EPI_BIAS); break;
+    default: perf("out wgrad", 768, 768, 27904, 1, 1, 1, 1, EPI_NONE); break;
+  }
+}
+
 int main(int argc, char** argv) {
+  if (argc > 2 && !strcmp(argv[1], "--perf-one")) { perf_one(atoi(argv[2])); return 0; }
   bool do_perf = argc > 1 && !strcmp(argv[1], "--perf");
   int fails = 0;
   const Case cases[] = {
