@@ -30,6 +30,7 @@ def workload(args, n):
     return {"workload": "MedViLL pretrain step (MLM+ITM), BERT-base, Bidirectional Auto-Regressive mask, batch %d/GPU, synthetic "
                         "512x512 CXR + random report tokens, N=180 regions, S=253 (L=436), dropout 0.1, AdamW" % args.batch,
             "global_batch": args.batch * n, "joint_len": 436, "parallelism": "dp%d" % n,
+            "images": "uint8 [B,3,512,512] on the wire, ToTensor+Normalize fused on the device (mv_normalize_u8)",
             "l2": "no flush needed: one step streams ~10 GB of saved activations (>> 126 MB L2)"}
 
 
@@ -154,7 +155,7 @@ def run_ours(args):
         model.sync_params()
 
     # a small pool of distinct synthetic batches (pinned host memory), cycled
-    pool = [synthetic_batch(B, seed=123 + 17 * rank + i, pin=True) for i in range(2)]
+    pool = [synthetic_batch(B, seed=123 + 17 * rank + i, pin=True, image_dtype=torch.uint8) for i in range(2)]
     dev_pool = [{k: (v if k == "txt_labels" else v.to(dev)) for k, v in b.items()} for b in pool]
 
     def step_device(i):

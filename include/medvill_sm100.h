@@ -161,6 +161,10 @@ int64_t mv_bn_workspace_floats(int64_t rows, int32_t C);
 int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32_t C, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, int32_t training, int32_t relu,
                   float* workspace, int64_t ws_floats, int32_t precision, void* stream);
+/* uint8 image [B,3,H,W] -> (x/255 - mean)/std in the activation dtype, channels-last [B,H,W,3]: the device-side form of
+ * get_transforms (data/helper.py:20-27), so a step ships uint8 pixels over PCIe.  mean3/std3 are HOST pointers. */
+int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, const float* mean3, const float* std3,
+                    int32_t precision, void* stream);
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
 

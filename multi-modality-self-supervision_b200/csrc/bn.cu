@@ -209,3 +209,39 @@ int bn_forward(const void* x, const void* resid, void* y, long rows, int C, cons
 }
 
 }  // namespace mv
+
+// ---- uint8 CXR -> normalised channels-last activation ------------------------------------------------------------------
+// Fuses data/helper.py's ToTensor (u8 -> [0,1]) + Normalize(mean, std) with the NCHW -> NHWC layout change the cuDNN
+// convolutions want, so a step ships 0.75 MB per image over PCIe instead of 3 MB of fp32.
+namespace mv {
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const unsigned char* __restrict__ src, T* __restrict__ dst, long pixels,
+                                                           long hw, float m0, float m1, float m2, float s0, float s1, float s2) {
+  // src: [B, 3, H, W] u8 ; dst: [B, H, W, 3]
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pixels; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long b = i / hw, p = i - b * hw;
+    const unsigned char* s = src + b * 3 * hw + p;
+    const float r = (static_cast<float>(s[0]) * (1.f / 255.f) - m0) * s0;
+    const float g = (static_cast<float>(s[hw]) * (1.f / 255.f) - m1) * s1;
+    const float bl = (static_cast<float>(s[2 * hw]) * (1.f / 255.f) - m2) * s2;
+    T* d = dst + i * 3;
+    d[0] = from_f32<T>(r); d[1] = from_f32<T>(g); d[2] = from_f32<T>(bl);
+  }
+}
+}  // namespace
+
+int normalize_u8(const unsigned char* src, void* dst, long B, long hw, const float mean[3], const float stdv[3], int f32,
+                 cudaStream_t s) {
+  MV_REQUIRE(src && dst && B > 0 && hw > 0, "normalize_u8: bad arguments");
+  const long pixels = B * hw;
+  long blocks = (pixels + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (f32) normalize_u8_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<float*>(dst), pixels, hw, mean[0], mean[1], mean[2],
+                                                                              1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]);
+  else normalize_u8_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<bf16*>(dst), pixels, hw, mean[0], mean[1], mean[2],
+                                                                          1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]);
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace mv

@@ -283,6 +283,12 @@ int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32
                     ws_floats, precision == MV_PREC_FP32, S(stream));
 }
 
+int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, const float* mean3, const float* std3,
+                    int32_t precision, void* stream) {
+  MV_REQUIRE(mean3 && std3, "mv_normalize_u8: null mean/std");
+  return normalize_u8(src, dst, B, hw, mean3, std3, precision == MV_PREC_FP32, S(stream));
+}
+
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream) {
   AdamArgs a;

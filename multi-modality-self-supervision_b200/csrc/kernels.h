@@ -103,6 +103,10 @@ int bn_forward(const void* x, const void* resid, void* y, long rows, int C, cons
                float* running_mean, float* running_var, float momentum, float eps, int training, int relu, float* workspace,
                long ws_floats, int f32, cudaStream_t s);
 
+// uint8 [B,3,H,W] -> normalised channels-last activation [B,H,W,3] (data/helper.py:20-27 ToTensor + Normalize)
+int normalize_u8(const unsigned char* src, void* dst, long B, long hw, const float mean[3], const float stdv[3], int f32,
+                 cudaStream_t s);
+
 // ---- fused masked attention (upstream BertSelfAttention; twin .../pytorch_pretrained_bert/model.py:301-320)
 struct AttnArgs {
   int B, L, nh, A;                   // head dim fixed at 64; H = nh * 64

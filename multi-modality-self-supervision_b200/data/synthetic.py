@@ -47,7 +47,8 @@ def synthetic_batch(B, vocab=30522, seq_len=253, num_image_embeds=180, img_size=
         input_ids=torch.from_numpy(ids), txt_labels=torch.from_numpy(labels), segment=torch.ones(B, T, dtype=torch.long),
         is_aligned=torch.from_numpy(nrng.randint(0, 2, size=B).astype(np.int64)),
         mode=torch.from_numpy(modes), t_len=torch.from_numpy(t_len),
-        image=torch.randn(B, 3, img_size, img_size, generator=g).to(image_dtype),
+        image=(torch.randint(0, 256, (B, 3, img_size, img_size), generator=g, dtype=torch.uint8) if image_dtype == torch.uint8
+               else torch.randn(B, 3, img_size, img_size, generator=g).to(image_dtype)),
     )
     if full_masks:
         out["attn_masks"] = torch.stack([build_mask(int(modes[b]), A, L, int(t_len[b])) for b in range(B)])

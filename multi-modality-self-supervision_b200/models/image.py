@@ -56,9 +56,26 @@ class TrunkExecutor:
             m.num_batches_tracked.add_(1)
         return x
 
+    def _normalize_u8(self, x):
+        """uint8 [B,3,H,W] pixels -> ImageNet-normalised channels-last activation (data/helper.py:20-27 on the device)"""
+        B, Cc, H, W = x.shape
+        if Cc != 3:
+            raise _lib.MedvillError("uint8 images must be [B, 3, H, W]")
+        x = x.contiguous()
+        out = torch.empty((B, 3, H, W), dtype=self.act_dtype, device=x.device, memory_format=torch.channels_last)
+        mean = (C.c_float * 3)(0.485, 0.456, 0.406)
+        std = (C.c_float * 3)(0.229, 0.224, 0.225)
+        prec = _lib.MV_PREC_FP32 if self.act_dtype == torch.float32 else _lib.MV_PREC_BF16
+        _lib.check(_lib.lib().mv_normalize_u8(_lib.ptr(x), _lib.ptr(out), B, H * W, mean, std, prec, _lib.stream_ptr(x.device)),
+                   "mv_normalize_u8")
+        return out
+
     def __call__(self, x, training):
         s = self.seq
-        x = x.to(self.act_dtype).contiguous(memory_format=torch.channels_last)
+        if x.dtype == torch.uint8:
+            x = self._normalize_u8(x)
+        else:
+            x = x.to(self.act_dtype).contiguous(memory_format=torch.channels_last)
         x = self._bn(s[1], self._conv("0", s[0], x), True, training)
         x = s[3](x)
         for li in (4, 5, 6, 7):

@@ -63,6 +63,23 @@ def test_batchnorm_kernel_vs_torch(dtype, tol, rows, C, relu, resid):
     assert torch.allclose(drm.cpu(), rm_ref, atol=1e-4, rtol=1e-4) and torch.allclose(drv.cpu(), rv_ref, atol=1e-4, rtol=1e-4)
 
 
+def test_uint8_images_are_normalised_on_the_device():
+    """mv_normalize_u8 == transforms.ToTensor() + Normalize(ImageNet) (data/helper.py:20-27), written channels-last"""
+    import medvill_b200  # noqa: F401
+    from medvill_b200.models.image import TrunkExecutor
+
+    x = torch.randint(0, 256, (3, 3, 40, 24), dtype=torch.uint8)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    ref = (x.float() / 255.0 - mean) / std
+    ex = TrunkExecutor.__new__(TrunkExecutor)
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        ex.act_dtype = dt
+        out = ex._normalize_u8(x.cuda())
+        assert out.is_contiguous(memory_format=torch.channels_last)
+        assert (out.float().cpu() - ref).abs().max() <= tol * ref.abs().max()
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 0.5)])
 def test_resnet_trunk_with_library_batchnorm(precision, tol):
     g, cfg = load_golden("tiny_bar")
