@@ -55,6 +55,14 @@ __device__ __forceinline__ void store_p32(uint8_t* sP, int r, int c32, const flo
 // Forward.  256 threads: two threads per query row (warp w reads TMEM lane quarter w & 3 and owns the column half
 // w >> 2 of S and of O), two CTAs per SM.  Online softmax with a reference exponent that lags one key tile behind the
 // running maximum (exact after the final normalisation; only the first tile needs a true max pass).
+// same, from 16 already-packed bf16x2 words
+__device__ __forceinline__ void store_pk32(uint8_t* sP, int r, int c32, const uint32_t (&pk)[16]) {
+  uint8_t* half = sP + (c32 >> 1) * TILE_BYTES;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(half + sw128_off(r, (c32 & 1) * 4 + j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+}
+
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,40 +158,63 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const bool ok = full || (static_cast<uint32_t>(kc0 + c * 32 + i - m_lo) < m_span);
-          mx = fmaxf(mx, ok ? __uint_as_float(v[i]) * scale2 : -INFINITY);
+          mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
-      sh->xfirst[ch][r] = mx;
+      sh->xfirst[ch][r] = mx * scale2;       // scale2 > 0: max commutes with the scaling
       __syncthreads();
       const float m0 = fmaxf(sh->xfirst[0][r], sh->xfirst[1][r]);
       ref = m0 == -INFINITY ? 0.f : m0;
     }
-    float m_loc = -INFINITY;
+    float m_raw = -INFINITY;                 // running max of the RAW scores of this tile
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
       tmem_ld32(t_lane + ch * 64 + c * 32, v);
       tmem_ld_wait();
       float p[32];
+      // this row's allowed keys inside the chunk are i in [rel_lo, rel_hi): all / none / a sub-range
+      const int rel_lo = m_lo - (kc0 + c * 32), rel_hi = m_hi - (kc0 + c * 32);
+      if (full || (rel_lo <= 0 && rel_hi >= 32)) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool ok = full || (static_cast<uint32_t>(kc0 + c * 32 + i - m_lo) < m_span);
-        const float s2 = ok ? __uint_as_float(v[i]) * scale2 : -INFINITY;
-        m_loc = fmaxf(m_loc, s2);
-        p[i] = ex2(s2 - ref);
-        l_loc += p[i];
+        for (int i = 0; i < 32; ++i) {
+          const float s = __uint_as_float(v[i]);
+          m_raw = fmaxf(m_raw, s);
+          p[i] = ex2(fmaf(s, scale2, -ref));        // exp2(s * scale2 - ref): one FFMA + one MUFU
+          l_loc += p[i];
+        }
+      } else if (rel_hi <= 0 || rel_lo >= 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[i] = 0.f;
+      } else {
+        const uint32_t span = static_cast<uint32_t>(rel_hi - rel_lo);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = (static_cast<uint32_t>(i - rel_lo) < span) ? __uint_as_float(v[i]) : -INFINITY;
+          m_raw = fmaxf(m_raw, s);
+          p[i] = ex2(fmaf(s, scale2, -ref));
+          l_loc += p[i];
+        }
       }
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
       if (a.drop_on) {
+        // dropped probabilities are zeroed with one AND per bf16 pair; the 1/(1-p) keep-scale is applied once to O
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (kc0 + c * 32 + 16 * g) >> 4));
+          const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
 #pragma unroll
-          for (int i = 0; i < 16; ++i) p[16 * g + i] = keep16_bit(keep, i) ? p[16 * g + i] * a.drop.scale : 0.f;
+          for (int w = 0; w < 4; ++w) {
+            pk[8 * g + 2 * w] &= __byte_perm(kw[w], 0, 0x1100);
+            pk[8 * g + 2 * w + 1] &= __byte_perm(kw[w], 0, 0x3322);
+          }
         }
       }
-      store_p32(sP, r, ch * 2 + c, p);
+      store_pk32(sP, r, ch * 2 + c, pk);
     }
-    sh->xmax[ph][ch][r] = m_loc;
+    sh->xmax[ph][ch][r] = m_raw * scale2;
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
@@ -226,7 +257,7 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
   __syncthreads();
   if (q < L) {
     const float l_row = sh->xsum[0][r] + sh->xsum[1][r];
-    const float inv = l_row > 0.f ? 1.f / l_row : 0.f;
+    const float inv = l_row > 0.f ? (a.drop_on ? a.drop.scale : 1.f) / l_row : 0.f;   // deferred dropout keep-scale
     bf16* dst = static_cast<bf16*>(a.ctx) + (static_cast<long>(row0) + q) * H + h * D + ch * 32;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -280,11 +311,21 @@ struct BwdSmem {
   uint32_t tmem_base;
 };
 
-// Backward.  One CTA (256 threads, two per query row) per (key tile, head, sample); loops over the query tiles that
-// can see this key tile, Q / dO double-buffered.
+// 16 consecutive columns starting at `col` (multiple of 16) of row `r`, from 8 packed bf16x2 words
+__device__ __forceinline__ void store_pk16(uint8_t* sP, int r, int col, const uint32_t (&pk)[8]) {
+  uint8_t* half = sP + (col >> 6) * TILE_BYTES;
+  const int j0 = (col & 63) >> 3;
+  *reinterpret_cast<uint4*>(half + sw128_off(r, j0)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(half + sw128_off(r, j0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// Backward.  One CTA (512 threads: four per query row, each owning 32 of the 128 key columns) per (key tile, head,
+// sample); loops over the query tiles that can see this key tile, Q / dO double-buffered, the next tile's S / dP
+// products issued right behind the current tile's dV / dK / dQ products.
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448)
-__global__ void __launch_bounds__(256, 1)
-attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const AttnArgs a) {
+__global__ void __launch_bounds__(512, 1)
+attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                     const __grid_constant__ CUtensorMap tmDQ, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -294,10 +335,11 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint8_t* sdO = smem + 4 * TILE_BYTES;    // [2]
   uint8_t* sP = smem + 6 * TILE_BYTES;
   uint8_t* sdS = sP + P_BYTES;
-  BwdSmem* sh = reinterpret_cast<BwdSmem*>(sdS + P_BYTES);
+  uint8_t* sDQ = sdS + P_BYTES;            // [2 halves of 32 fp32 columns][128 rows x 128 B]: dQ tile staged for TMA reduce-add
+  BwdSmem* sh = reinterpret_cast<BwdSmem*>(sDQ + P_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lq = warp & 3, ch = warp >> 2;
+  const int lq = warp & 3, cq = warp >> 2;          // TMEM lane quarter, column quarter
   const int r = lq * 32 + lane;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int L = a.L, H = a.nh * D, A = a.A;
@@ -309,6 +351,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
     mbar_init(&sh->bar_kv, 1); mbar_init(&sh->bar_q[0], 1); mbar_init(&sh->bar_q[1], 1);
     mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1);
     fence_mbar_init();
@@ -341,71 +384,100 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D, 0, 1);      // dQ    : dS (K-major) x K (MN-major)
   const float scale2 = 0.125f * kLog2e;
   const bool any = i < n_q;
-  const int kc0 = k_lo + ch * 64;
+  const int kc0 = k_lo + cq * 32;        // first key column of this thread's quarter
   uint32_t it = 0;
+
+  auto issue_s_dp = [&](uint32_t buf) {
+    const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO + buf * TILE_BYTES);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k)
+      umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k)
+      umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
+    umma_commit(&sh->bar_s);
+  };
+  auto row_stats = [&](int qi, float& lse2_o, float& delta_o) {
+    const int qq = qi * TQ + r;
+    const long st = (static_cast<long>(b) * a.nh + h) * L + (qq < L ? qq : 0);
+    lse2_o = qq < L ? a.lse[st] * kLog2e : 0.f;
+    delta_o = qq < L ? a.delta[st] : 0.f;
+  };
+  float lse2 = 0.f, delta = 0.f;
+  if (any) row_stats(i, lse2, delta);
+  if (tid == 0 && any) {
+    const int i1 = next_active(i);
+    if (i1 < n_q) load_q(i1, 1);
+    mbar_wait(&sh->bar_kv, 0);
+    mbar_wait(&sh->bar_q[0], 0);
+    tc_fence_after();
+    issue_s_dp(0);
+  }
 
   for (; i < n_q; ++it) {
     const int in = next_active(i);
     const uint32_t ph = it & 1u, buf = it & 1u;
     const int q_lo = i * TQ;
-    if (tid == 0) {
-      if (it == 0) mbar_wait(&sh->bar_kv, 0);
-      if (in < n_q) load_q(in, buf ^ 1u);        // the other buffer was released by the previous iteration's bar_o
-      mbar_wait(&sh->bar_q[buf], (it >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO + buf * TILE_BYTES);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
-#pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(&sh->bar_s);
-    }
     const int q = q_lo + r;
     const bool q_ok = q < L;
-    const long st = (static_cast<long>(b) * a.nh + h) * L + (q_ok ? q : 0);
-    const float lse2 = q_ok ? a.lse[st] * kLog2e : 0.f;
-    const float delta = q_ok ? a.delta[st] : 0.f;
+    float lse2_n = 0.f, delta_n = 0.f;
+    if (in < n_q) row_stats(in, lse2_n, delta_n);        // next tile's row statistics: latency hidden behind this tile
     int m_lo, m_hi;
     mask_row_interval(mode, q_ok ? q : 0, A, tl, L, m_lo, m_hi);
-    const uint32_t m_span = q_ok ? static_cast<uint32_t>(m_hi - m_lo) : 0u;   // rows past the sequence end see nothing
     const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L) &&
                       (q_lo + TQ <= L);
     mbar_wait(&sh->bar_s, ph);
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      uint32_t sv[32], dv[32];
-      tmem_ld32(t_lane + ch * 64 + c * 32, sv);
-      tmem_ld32(t_lane + 128 + ch * 64 + c * 32, dv);
+      const int col = cq * 32 + c * 16;                  // column inside the 128-wide tile
+      uint32_t sv[16], dv[16];
+      tmem_ld16(t_lane + col, sv);
+      tmem_ld16(t_lane + 128 + col, dv);
       tmem_ld_wait();
-      float p[32], ds[32];
+      // Work saved per element: the softmax scale 1/8 of dS is folded into the dQ / dK epilogues, the dropout
+      // keep-scale of P into the dV epilogue, and dropped entries are zeroed with integer ANDs on the keep bytes.
+      float p[16];
+      const int rel_lo = m_lo - (k_lo + col), rel_hi = m_hi - (k_lo + col);
+      if (full || (q_ok && rel_lo <= 0 && rel_hi >= 16)) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const bool ok = full || (static_cast<uint32_t>(kc0 + c * 32 + e - m_lo) < m_span);
-        p[e] = ok ? ex2(__uint_as_float(sv[e]) * scale2 - lse2) : 0.f;
-        ds[e] = __uint_as_float(dv[e]);
+        for (int e = 0; e < 16; ++e) p[e] = ex2(fmaf(__uint_as_float(sv[e]), scale2, -lse2));
+      } else if (!q_ok || rel_hi <= 0 || rel_lo >= 16) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) p[e] = 0.f;
+      } else {
+        const uint32_t span = static_cast<uint32_t>(rel_hi - rel_lo);
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          p[e] = (static_cast<uint32_t>(e - rel_lo) < span) ? ex2(fmaf(__uint_as_float(sv[e]), scale2, -lse2)) : 0.f;
       }
+      uint32_t pk[8], dk[8];
       if (a.drop_on) {
+        const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + col) >> 4));
+        const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (kc0 + c * 32 + 16 * g) >> 4));
+        for (int w = 0; w < 4; ++w) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const bool kp = keep16_bit(keep, e);
-            const float pe = p[16 * g + e];
-            ds[16 * g + e] = pe * ((kp ? ds[16 * g + e] * a.drop.scale : 0.f) - delta) * 0.125f;
-            p[16 * g + e] = kp ? pe * a.drop.scale : 0.f;
+          for (int hh = 0; hh < 2; ++hh) {
+            const int e = 4 * w + 2 * hh;
+            // dP masked by the keep bytes (all-ones / zero per element), then dS = p * (dP * keep_scale - delta)
+            const float t0 = __uint_as_float(dv[e] & __byte_perm(kw[w], 0, hh ? 0x2222 : 0x0000));
+            const float t1 = __uint_as_float(dv[e + 1] & __byte_perm(kw[w], 0, hh ? 0x3333 : 0x1111));
+            dk[e >> 1] = pack_bf16x2(p[e] * fmaf(t0, a.drop.scale, -delta), p[e + 1] * fmaf(t1, a.drop.scale, -delta));
+            pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]) & __byte_perm(kw[w], 0, hh ? 0x3322 : 0x1100);
           }
         }
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) ds[e] = p[e] * (ds[e] - delta) * 0.125f;
+        for (int e = 0; e < 16; e += 2) {
+          dk[e >> 1] = pack_bf16x2(p[e] * (__uint_as_float(dv[e]) - delta), p[e + 1] * (__uint_as_float(dv[e + 1]) - delta));
+          pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]);
+        }
       }
-      store_p32(sP, r, ch * 2 + c, p);
-      store_p32(sdS, r, ch * 2 + c, ds);
+      store_pk16(sP, r, col, pk);
+      store_pk16(sdS, r, col, dk);
     }
+    if (tid == 0) tma_wait_group_read<0>();   // the previous tile's dQ reduce has finished reading its staging buffer
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
@@ -426,60 +498,83 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
                   make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
       umma_commit(&sh->bar_o);
+      if (in < n_q) {                       // S / dP columns were released by the barrier above: start the next tile now
+        mbar_wait(&sh->bar_q[buf ^ 1u], ((it + 1) >> 1) & 1u);
+        tc_fence_after();
+        issue_s_dp(buf ^ 1u);
+      }
     }
     mbar_wait(&sh->bar_o, ph);
     tc_fence_after();
+    if (tid == 0 && in < n_q) {             // Q / dO buffer `buf` is free (this tile's products are complete)
+      const int in2 = next_active(in);
+      if (in2 < n_q) load_q(in2, buf);
+    }
     {
-      uint32_t v[32];
-      tmem_ld32(t_lane + 384 + ch * 32, v);
+      // dQ tile (x 1/8) -> swizzled fp32 staging -> ONE TMA reduce-add per 32-column half into the fp32 dQ accumulator
+      // (per-thread red.global ops were the bottleneck of this kernel).  Rows past the sequence end hold exact zeros.
+      uint32_t v[16];
+      tmem_ld16(t_lane + 384 + cq * 16, v);
       tmem_ld_wait();
-      if (q_ok) {
-        float* dst = a.dq_acc + (static_cast<long>(row0) + q) * H + h * D + ch * 32;
+      uint8_t* half = sDQ + (cq >> 1) * TILE_BYTES;
 #pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          atomicAdd(reinterpret_cast<float4*>(dst + e), make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]),
-                                                                    __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
-      }
+      for (int e = 0; e < 16; e += 4)
+        *reinterpret_cast<float4*>(half + sw128_off(r, (cq & 1) * 4 + (e >> 2))) =
+            make_float4(0.125f * __uint_as_float(v[e]), 0.125f * __uint_as_float(v[e + 1]), 0.125f * __uint_as_float(v[e + 2]),
+                        0.125f * __uint_as_float(v[e + 3]));
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tma_reduce_add_2d(&tmDQ, sDQ, h * D, row0 + q_lo);
+      tma_reduce_add_2d(&tmDQ, sDQ + TILE_BYTES, h * D + 32, row0 + q_lo);
+      tma_commit_group();
     }
     tc_fence_before();
     i = in;
+    lse2 = lse2_n;
+    delta = delta_n;
   }
 
   // epilogue: dV, dK rows of this key tile.  tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only
   // the stores are predicated on k < L.  `any` is uniform across the CTA (an unseen key tile gets exact zeros).
   const int k = k_lo + r;
-  bf16* dk_dst = static_cast<bf16*>(a.dqkv) + (static_cast<long>(row0) + (k < L ? k : 0)) * 3 * H + H + h * D + ch * 32;
+  bf16* dk_dst = static_cast<bf16*>(a.dqkv) + (static_cast<long>(row0) + (k < L ? k : 0)) * 3 * H + H + h * D + cq * 16;
   bf16* dv_dst = dk_dst + H;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     bf16* dst = which == 0 ? dv_dst : dk_dst;
-    uint32_t v[32];
+    uint32_t v[16];
     if (any) {
-      tmem_ld32(t_lane + 256 + which * 64 + ch * 32, v);
+      tmem_ld16(t_lane + 256 + which * 64 + cq * 16, v);
       tmem_ld_wait();
     } else {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) v[e] = 0u;
+      for (int e = 0; e < 16; ++e) v[e] = 0u;
     }
     if (k < L) {
+      // deferred factors: dropout keep-scale for dV (which == 0), softmax scale 1/8 for dK
+      const float fs = which == 0 ? (a.drop_on ? a.drop.scale : 1.f) : 0.125f;
 #pragma unroll
-      for (int e = 0; e < 32; e += 8) {
+      for (int e = 0; e < 16; e += 8) {
         uint4 u;
-        u.x = pack_bf16x2(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-        u.y = pack_bf16x2(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        u.z = pack_bf16x2(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-        u.w = pack_bf16x2(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+        u.x = pack_bf16x2(fs * __uint_as_float(v[e]), fs * __uint_as_float(v[e + 1]));
+        u.y = pack_bf16x2(fs * __uint_as_float(v[e + 2]), fs * __uint_as_float(v[e + 3]));
+        u.z = pack_bf16x2(fs * __uint_as_float(v[e + 4]), fs * __uint_as_float(v[e + 5]));
+        u.w = pack_bf16x2(fs * __uint_as_float(v[e + 6]), fs * __uint_as_float(v[e + 7]));
         *reinterpret_cast<uint4*>(dst + e) = u;
       }
     }
   }
+  if (tid == 0) tma_wait_group<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 constexpr uint32_t kFwdSmem = 1024 + 3 * TILE_BYTES + P_BYTES + sizeof(FwdSmem) + 64;
-constexpr uint32_t kBwdSmem = 1024 + 6 * TILE_BYTES + 2 * P_BYTES + sizeof(BwdSmem) + 64;
+constexpr uint32_t kBwdSmem = 1024 + 6 * TILE_BYTES + 3 * P_BYTES + sizeof(BwdSmem) + 64;
 
 }  // namespace
 
@@ -509,6 +604,9 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
   if (rc) return rc;
   rc = tmap_encode_2d(&tmDO, TMAP_BF16, a.dctx, H, rows, static_cast<uint64_t>(H) * 2, D, TQ);
   if (rc) return rc;
+  CUtensorMap tmDQ;
+  rc = tmap_encode_2d(&tmDQ, TMAP_F32, a.dq_acc, H, rows, static_cast<uint64_t>(H) * 4, 32, TQ);
+  if (rc) return rc;
   static bool attr = false;
   if (!attr) {
     MV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
@@ -520,7 +618,7 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
                                                                              static_cast<int>(rows), a.L, a.nh);
   MV_LAUNCH_CHECK();
   dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
-  attn_bwd_tc05_kernel<<<grid, 256, kBwdSmem, s>>>(tmQKV, tmDO, a);
+  attn_bwd_tc05_kernel<<<grid, 512, kBwdSmem, s>>>(tmQKV, tmDO, tmDQ, a);
   MV_LAUNCH_CHECK();
   attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
   MV_LAUNCH_CHECK();

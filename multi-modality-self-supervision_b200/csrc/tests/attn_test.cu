@@ -187,7 +187,46 @@ static int run_dropout(int B, int nh, int L, int A) {
   return !ok;
 }
 
-int main() {
+// timing at the bench shape (B=64, 12 heads, L=436, BAR, dropout on): no CPU reference
+static void perf(int drop) {
+  const int B = 64, nh = 12, L = 436, A = 182, H = nh * 64;
+  const size_t rows = (size_t)B * L;
+  std::vector<float> qkv(rows * 3 * H), dctx(rows * H);
+  for (auto& v : qkv) v = frand() * 2.f;
+  for (auto& v : dctx) v = frand();
+  std::vector<unsigned char> mode(B, MODE_BAR);
+  std::vector<int> tlen(B, 150);
+  bf16* d_qkv = dupload_bf16(qkv);
+  bf16* d_dctx = dupload_bf16(dctx);
+  unsigned char* d_mode = dupload(mode);
+  int* d_tlen = dupload(tlen);
+  void *d_ctx, *d_dqkv;
+  float *lse, *delta, *dq_acc;
+  cudaMalloc(&d_ctx, rows * H * 2); cudaMalloc(&d_dqkv, rows * 3 * H * 2);
+  cudaMalloc(&lse, (size_t)B * nh * L * 4); cudaMalloc(&delta, (size_t)B * nh * L * 4); cudaMalloc(&dq_acc, rows * H * 4);
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.L = L; a.nh = nh; a.A = A; a.mode = d_mode; a.t_len = d_tlen; a.qkv = d_qkv; a.ctx = d_ctx; a.lse = lse;
+  a.dctx = d_dctx; a.dqkv = d_dqkv; a.dq_acc = dq_acc; a.delta = delta; a.drop_on = drop; a.drop_site = 3; a.drop = make_dropout(0.1f, 7);
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  for (int i = 0; i < 2; ++i) { attention_fwd_tc05(a, 0); attention_bwd_tc05(a, 0); }
+  const int iters = 10;
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) attention_fwd_tc05(a, 0);
+  cudaEventRecord(e1);
+  for (int i = 0; i < iters; ++i) attention_bwd_tc05(a, 0);
+  cudaEventRecord(e2);
+  cudaEventSynchronize(e2);
+  float f, b;
+  cudaEventElapsedTime(&f, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+  const double fl = 4.0 * B * nh * (double)L * L * 64;
+  printf("  perf attention B=64 L=436 BAR dropout=%d: fwd %.3f ms (%.0f dense TFLOP/s)  bwd %.3f ms (%.0f dense TFLOP/s)\n", drop,
+         f / iters, fl / (f / iters) / 1e9, b / iters, 2.5 * fl / (b / iters) / 1e9);
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "--perf")) { perf(argc > 2 ? atoi(argv[2]) : 1); return 0; }
   int fails = 0;
   printf("== fused masked attention ==\n");
   fails += run(4, 2, 436, 182, {MODE_BAR, MODE_S2S, MODE_NONCROSS, MODE_BIDIR}, {254, 254, 254, 57}, "L=436 all modes");
