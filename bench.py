@@ -251,7 +251,21 @@ def run_ours(args):
                 "attn_bwd_tflops_dense": pfl[2] / (pms[2] * 1e-3) / 1e12 if pms[2] > 0 else None,
                 "encoder_dense_tflops_over_whole_step": enc_tf, "encoder_frac_of_peak_over_whole_step": enc_tf / peak_tf}
 
+    def teardown():
+        # identical shutdown order on every rank: engine (its NCCL communicator) first, then torch.distributed; then
+        # leave without running finalizers (a rank that exits while its peer is still inside a collective teardown hangs)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if world > 1:
+            torch.cuda.synchronize()
+            torch.distributed.barrier()
+            model._release_engine()
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+            os._exit(0)
+
     if rank != 0:
+        teardown()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -266,8 +280,7 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "last_loss": out["loss"]}
     print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    teardown()
 
 
 def main():
@@ -280,6 +293,11 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    wd = int(os.environ.get("MEDVILL_BENCH_WATCHDOG", "0"))
+    if wd > 0:      # debugging aid: dump every thread's Python stack and exit if the run is still alive after `wd` seconds
+        import faulthandler
+
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -273,6 +273,10 @@ class PretrainEngine:
         check(lib().mv_comm_init(self._h, uid, rank, world), "mv_comm_init")
         self.rank, self.world = rank, world
 
+    def comm_sync(self):
+        """Make the current stream wait for every pending gradient-bucket all-reduce."""
+        check(lib().mv_comm_sync(self._h, stream_ptr(self.device)), "mv_comm_sync")
+
     def allreduce_f32(self, t):
         check(lib().mv_comm_allreduce_f32(self._h, ptr(t), t.numel(), stream_ptr(self.device)), "mv_comm_allreduce_f32")
         return t
