@@ -20,6 +20,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 METRIC = "MLM+ITM pretrain samples/sec"
 UNIT = "samples/s"
 # dense algorithmic FLOPs per sample of one training step: encoder linears + attention, fwd + dgrad + wgrad
@@ -113,7 +114,8 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d timed steps of the B=2 (configs[0]) step after %d warm-up, median" % (steps, warm)},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def run_ours(args):
@@ -279,7 +281,8 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cpu,
             "last_loss": out["loss"]}
-    print(json.dumps(line))
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
     teardown()
 
 
@@ -293,6 +296,11 @@ def main():
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter)
+    # is routed to stderr; the JSON goes to the saved descriptor.
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     wd = int(os.environ.get("MEDVILL_BENCH_WATCHDOG", "0"))
     if wd > 0:      # debugging aid: dump every thread's Python stack and exit if the run is still alive after `wd` seconds
         import faulthandler
