@@ -163,8 +163,13 @@ int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32
                   float* workspace, int64_t ws_floats, int32_t precision, void* stream);
 /* uint8 image [B,3,H,W] -> (x/255 - mean)/std in the activation dtype, channels-last [B,H,W,3]: the device-side form of
  * get_transforms (data/helper.py:20-27), so a step ships uint8 pixels over PCIe.  mean3/std3 are HOST pointers. */
-int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, const float* mean3, const float* std3,
-                    int32_t precision, void* stream);
+int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, int32_t cpad, const float* mean3, const float* std3,
+                    int32_t precision, void* stream);        /* dst is [B,H,W,cpad], channels >= 3 zero-filled        */
+/* ResNet stem tail in one pass: BatchNorm + ReLU + MaxPool2d(3,2,1), channels-last [B,H,W,C] -> [B,H/2,W/2,C]
+ * (torchvision resnet50 children 1-3 inside ImageEncoder_cnn, models/image.py:50-56). Workspace as mv_bn_forward. */
+int mv_bn_relu_maxpool(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int32_t training, float* workspace,
+                       int64_t ws_floats, int32_t precision, void* stream);
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
 

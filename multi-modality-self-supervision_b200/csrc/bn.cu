@@ -217,29 +217,98 @@ namespace mv {
 namespace {
 template <typename T>
 __global__ void __launch_bounds__(256) normalize_u8_kernel(const unsigned char* __restrict__ src, T* __restrict__ dst, long pixels,
-                                                           long hw, float m0, float m1, float m2, float s0, float s1, float s2) {
-  // src: [B, 3, H, W] u8 ; dst: [B, H, W, 3]
+                                                           long hw, int cpad, float m0, float m1, float m2, float s0, float s1, float s2) {
+  // src: [B, 3, H, W] u8 ; dst: [B, H, W, cpad] (cpad >= 3; extra channels are zero)
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pixels; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long b = i / hw, p = i - b * hw;
     const unsigned char* s = src + b * 3 * hw + p;
     const float r = (static_cast<float>(s[0]) * (1.f / 255.f) - m0) * s0;
     const float g = (static_cast<float>(s[hw]) * (1.f / 255.f) - m1) * s1;
     const float bl = (static_cast<float>(s[2 * hw]) * (1.f / 255.f) - m2) * s2;
-    T* d = dst + i * 3;
+    T* d = dst + i * cpad;
     d[0] = from_f32<T>(r); d[1] = from_f32<T>(g); d[2] = from_f32<T>(bl);
+    for (int c = 3; c < cpad; ++c) d[c] = from_f32<T>(0.f);     // zero channels: lets cuDNN run the stem as a tensor-op conv
+  }
+}
+
+// Stem tail fused in one pass: y = maxpool3x3/s2/p1( relu( x * scale + shift ) ) on channels-last [B, H, W, C] ->
+// [B, H/2, W/2, C].  Replaces BatchNorm-apply + ReLU + nn.MaxPool2d (models/image.py:50-56, torchvision stem).
+template <typename T>
+__global__ void __launch_bounds__(256) bn_relu_maxpool_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C,
+                                                              const float* __restrict__ scale_shift) {
+  const int c8 = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long total = static_cast<long>(B) * Ho * Wo * c8;
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % c8) * 8;
+    long t = i / c8;
+    const int wo = static_cast<int>(t % Wo); t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    float sc[8], sh[8], best[8];
+    ld8<float>(scale_shift + ch, sc);
+    ld8<float>(scale_shift + C + ch, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = 0.f;               // relu output is >= 0 and every window holds >= 1 valid pixel
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int hi = 2 * ho + dy;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int wi = 2 * wo + dx;
+        if (wi < 0 || wi >= W) continue;
+        float v[8];
+        ld8<T>(x + ((static_cast<long>(b) * H + hi) * W + wi) * C + ch, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], fmaf(v[j], sc[j], sh[j]));
+      }
+    }
+    st8<T>(y + i * 8, best);
   }
 }
 }  // namespace
 
-int normalize_u8(const unsigned char* src, void* dst, long B, long hw, const float mean[3], const float stdv[3], int f32,
+int bn_relu_maxpool(const void* x, void* y, int B, int H, int W, int C, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float momentum, float eps, int training, float* workspace, long ws_floats, int f32,
+                    cudaStream_t s) {
+  MV_REQUIRE(x && y && gamma && beta && running_mean && running_var && workspace, "bn_relu_maxpool: null argument");
+  MV_REQUIRE(C % 8 == 0 && C <= 2048 && H % 2 == 0 && W % 2 == 0, "bn_relu_maxpool: need C %% 8 == 0, even H and W");
+  const long rows = static_cast<long>(B) * H * W;
+  const int nparts = bn_num_parts(rows, C);
+  MV_REQUIRE(ws_floats >= static_cast<long>(nparts) * C * 3 + 2 * C, "bn_relu_maxpool: workspace too small");
+  float* scale_shift = workspace + static_cast<long>(nparts) * C * 3;
+  if (training) {
+    const long rows_per_cta = (rows + nparts - 1) / nparts;
+    dim3 grid(nparts, 1);
+    if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
+    else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
+    MV_LAUNCH_CHECK();
+    bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
+                                                          scale_shift);
+    MV_LAUNCH_CHECK();
+  } else {
+    bn_eval_scale_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, gamma, beta, running_mean, running_var, eps, scale_shift);
+    MV_LAUNCH_CHECK();
+  }
+  const long total = static_cast<long>(B) * (H / 2) * (W / 2) * (C / 8);
+  long blocks = (total + 255) / 256;
+  const long cap = static_cast<long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (f32) bn_relu_maxpool_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y), B, H, W, C, scale_shift);
+  else bn_relu_maxpool_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), B, H, W, C, scale_shift);
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+
+int normalize_u8(const unsigned char* src, void* dst, long B, long hw, int cpad, const float mean[3], const float stdv[3], int f32,
                  cudaStream_t s) {
-  MV_REQUIRE(src && dst && B > 0 && hw > 0, "normalize_u8: bad arguments");
+  MV_REQUIRE(src && dst && B > 0 && hw > 0 && cpad >= 3 && cpad <= 8, "normalize_u8: bad arguments");
   const long pixels = B * hw;
   long blocks = (pixels + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (f32) normalize_u8_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<float*>(dst), pixels, hw, mean[0], mean[1], mean[2],
+  if (f32) normalize_u8_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<float*>(dst), pixels, hw, cpad, mean[0], mean[1], mean[2],
                                                                               1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]);
-  else normalize_u8_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<bf16*>(dst), pixels, hw, mean[0], mean[1], mean[2],
+  else normalize_u8_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<bf16*>(dst), pixels, hw, cpad, mean[0], mean[1], mean[2],
                                                                           1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]);
   MV_LAUNCH_CHECK();
   return 0;

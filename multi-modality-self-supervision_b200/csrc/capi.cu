@@ -283,10 +283,17 @@ int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32
                     ws_floats, precision == MV_PREC_FP32, S(stream));
 }
 
-int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, const float* mean3, const float* std3,
+int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, int32_t cpad, const float* mean3, const float* std3,
                     int32_t precision, void* stream) {
   MV_REQUIRE(mean3 && std3, "mv_normalize_u8: null mean/std");
-  return normalize_u8(src, dst, B, hw, mean3, std3, precision == MV_PREC_FP32, S(stream));
+  return normalize_u8(src, dst, B, hw, cpad, mean3, std3, precision == MV_PREC_FP32, S(stream));
+}
+
+int mv_bn_relu_maxpool(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int32_t training, float* workspace,
+                       int64_t ws_floats, int32_t precision, void* stream) {
+  return bn_relu_maxpool(x, y, B, H, W, C, gamma, beta, running_mean, running_var, momentum, eps, training, workspace, ws_floats,
+                         precision == MV_PREC_FP32, S(stream));
 }
 
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,

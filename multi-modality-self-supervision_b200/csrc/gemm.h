@@ -33,6 +33,8 @@ struct GemmDesc {
   const void* aux = nullptr; long ldaux = 0;            // [M,N] activation dtype
   int drop_on = 0; uint32_t drop_site = 0; DropoutCfg drop = {0.f, 0u, 1.f, 0ull};
   int splitk = 0;                                       // 0 = auto (only used when accumulate=1)
+  int pair = -1;                                        // CTA-pair (cta_group::2, 256-row tiles): -1 auto, 0 off, 1 on
+  int bn = 0;                                           // N tile: 0 auto, else 128 / 192 / 256 (tests, tuning)
 };
 
 // bf16 operands / fp32 accumulate in TMEM / bf16 or fp32 output. sm_100a only.

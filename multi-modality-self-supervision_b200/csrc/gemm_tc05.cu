@@ -122,15 +122,26 @@ __device__ __forceinline__ void stage_f32(uint8_t* stg, int lane, const float (&
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+// TWO = true: CTA-pair mode.  Two CTAs of a 2-CTA cluster compute one 256 x BN tile with tcgen05.mma.cta_group::2: CTA r
+// loads rows [m0 + 128 r, +128) of A and rows [n0 + r BN/2, +BN/2) of B, owns accumulator rows [128 r, +128) in its own
+// TMEM and runs its own epilogue.  Only the leader (rank 0) issues MMAs; every TMA load of the pair is accounted on the
+// leader's `full` barrier, MMA completion is multicast to both CTAs' `empty` / `tfull` barriers, and the peer's epilogue
+// warps release the accumulator by arriving remotely on the leader's `tempty`.  Each SM then reads only half of B from
+// shared memory per MMA — single-CTA tiles are capped at ~60 % of the tensor pipe by shared-memory bandwidth
+// (TMA fill + UMMA operand reads, profiles/r01_ncu_gemm_*).
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                  const GemmParams p) {
   // tmX: the second epilogue tensor — pre-activation OUTPUT (has_c2) or residual / aux INPUT (has_in); [M, N] bf16
+  constexpr int BNL = TWO ? BN / 2 : BN;          // B rows (or columns) held by THIS CTA
   constexpr uint32_t A_BYTES = BM * BK * 2;
-  constexpr uint32_t B_BYTES = BN * BK * 2;
+  constexpr uint32_t B_BYTES = BNL * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  const uint32_t crank = TWO ? cluster_ctarank() : 0u;
+  const int cta_id = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);      // work-unit stream index
+  const int cta_stride = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   constexpr uint32_t TMEM_COLS = (BN <= 128) ? 256u : 512u;
   constexpr uint32_t ACC_STRIDE = (BN <= 128) ? 128u : 256u;
   constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;
@@ -156,96 +167,131 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tfull[a], 1);
-      mbar_init(&bars->tempty[a], 4);
+      mbar_init(&bars->tempty[a], TWO ? 8 : 4);     // pair mode: 4 local + 4 remote epilogue warps
     }
     for (int w = 0; w < 8; ++w) { mbar_init(&bars->in_bar[w][0], 1); mbar_init(&bars->in_bar[w][1], 1); }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (TWO) { tmem_alloc_pair(&bars->tmem_base, TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(&bars->tmem_base, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_tiles * p.n_tiles;          // pair mode: m_tiles counts 256-row tiles
   const int total_units = tiles * p.splits;
+  constexpr int BMT = TWO ? 2 * BM : BM;            // rows of one work unit
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const int split = unit % p.splits;
-        const int tile = unit / p.splits;
-        const int m0 = (tile % p.m_tiles) * BM;
-        const int n0 = (tile / p.m_tiles) * BN;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&bars->empty[stage], phase ^ 1u);
-          mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
-          uint8_t* sA = smem + static_cast<uint32_t>(stage) * STAGE_BYTES;
-          uint8_t* sB = sA + A_BYTES;
-          if constexpr (!A_MN) {
-            tma_load_2d(&tmA, &bars->full[stage], sA, kb * BK, m0);
-          } else {
+    // The whole warp walks the loop (warp-uniform control flow keeps addresses / coordinates in uniform registers, which
+    // is what UTMALDG consumes); one elected lane arms the barrier and issues the copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t full0 = TWO ? mapa_cluster(smem_u32(&bars->full[0]), 0) : 0u;   // leader's full[0] (cluster address)
+    for (int unit = cta_id; unit < total_units; unit += cta_stride) {
+      const int split = unit % p.splits;
+      const int tile = unit / p.splits;
+      const int m0 = (tile % p.m_tiles) * BMT + static_cast<int>(crank) * BM;     // this CTA's 128 rows of A
+      const int n0 = (tile / p.m_tiles) * BN + static_cast<int>(crank) * BNL;     // this CTA's share of B
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&bars->empty[stage], phase ^ 1u);
+        uint8_t* sA = smem + static_cast<uint32_t>(stage) * STAGE_BYTES;
+        uint8_t* sB = sA + A_BYTES;
+        if (elect_one()) {
+          if constexpr (TWO) {
+            // the leader arms its barrier for BOTH CTAs' bytes; every load of the pair completes on that barrier
+            if (crank == 0) mbar_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
+            const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+            if constexpr (!A_MN) {
+              tma_load_2d_pair(&tmA, fb, sA, kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int g = 0; g < BM / 64; ++g) tma_load_2d(&tmA, &bars->full[stage], sA + g * 8192, m0 + g * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(&tmB, &bars->full[stage], sB, kb * BK, n0);
-          } else {
+              for (int g = 0; g < BM / 64; ++g) tma_load_2d_pair(&tmA, fb, sA + g * 8192, m0 + g * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_pair(&tmB, fb, sB, kb * BK, n0);
+            } else {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g) tma_load_2d(&tmB, &bars->full[stage], sB + g * 8192, n0 + g * 64, kb * BK);
+              for (int g = 0; g < BNL / 64; ++g) tma_load_2d_pair(&tmB, fb, sB + g * 8192, n0 + g * 64, kb * BK);
+            }
+          } else {
+            mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d(&tmA, &bars->full[stage], sA, kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int g = 0; g < BM / 64; ++g) tma_load_2d(&tmA, &bars->full[stage], sA + g * 8192, m0 + g * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(&tmB, &bars->full[stage], sB, kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int g = 0; g < BN / 64; ++g) tma_load_2d(&tmB, &bars->full[stage], sB + g * 8192, n0 + g * 64, kb * BK);
+            }
           }
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    // ===================== MMA issuer =====================
+    // Warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit (the same lane every time: commit tracks
+    // the MMAs of the issuing thread).  Pair mode: only the leader CTA issues.
+    if (crank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BMT, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      const uint32_t a_addr0 = smem_u32(smem), b_addr0 = a_addr0 + A_BYTES;          // stage 0
+      const uint64_t da0 = A_MN ? make_smem_desc_sw128(a_addr0, 8192, 1024) : make_smem_desc_sw128(a_addr0, 16, 1024);
+      const uint64_t db0 = B_MN ? make_smem_desc_sw128(b_addr0, 8192, 1024) : make_smem_desc_sw128(b_addr0, 16, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = cta_id; unit < total_units; unit += cta_stride) {
         const int split = unit % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);
+        mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);      // released by the epilogue (of both CTAs in pair mode)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&bars->full[stage], phase);
+          mbar_wait(&bars->full[stage], phase);             // TMA bytes (of both CTAs in pair mode) have landed
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + static_cast<uint32_t>(stage) * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_BYTES;
+          // Descriptors are built once (da0/db0) and advanced with one 64-bit add per MMA.  The start-address field
+          // counts 16-byte units:
+          //   K-major : 16 bf16 along K = +32 B inside the 128 B swizzle row          -> +2
+          //   MN-major: 16 K rows = +2048 B (8-row K groups 1024 B, 64-wide MN groups 8192 B apart) -> +128
+          const uint64_t da = da0 + static_cast<uint64_t>(static_cast<uint32_t>(stage) * (STAGE_BYTES >> 4));
+          const uint64_t db = db0 + static_cast<uint64_t>(static_cast<uint32_t>(stage) * (STAGE_BYTES >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: 16 bf16 along K = +32 B inside the 128 B swizzle row; 8-row groups 1024 B apart.
-            // MN-major: 16 K rows = +2048 B; 64-element MN groups 8192 B apart, 8-row K groups 1024 B apart.
-            const uint64_t da = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t dak = da + static_cast<uint64_t>(k * (A_MN ? 128 : 2)), dbk = db + static_cast<uint64_t>(k * (B_MN ? 128 : 2));
+              if constexpr (TWO) umma_bf16_pair(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, dak, dbk, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs in pair mode) once these MMAs have read it
+            if constexpr (TWO) umma_commit_pair(&bars->empty[stage]); else umma_commit(&bars->empty[stage]);
           }
-          umma_commit(&bars->empty[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&bars->tfull[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs in pair mode)
+        if (elect_one()) {
+          if constexpr (TWO) umma_commit_pair(&bars->tfull[acc]); else umma_commit(&bars->tfull[acc]);
+        }
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue warps =====================
     // Two groups of four warps (2-5 and 6-9).  Group g drains accumulator stage g, i.e. every other work unit of this
@@ -268,11 +314,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_load_2d(&tmX, &in_bar[b], my_stg + b * STG_BYTES, n0 + c * 64, m0 + q * 32);
     };
     int it = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+    const uint32_t tempty_remote = TWO ? mapa_cluster(smem_u32(&bars->tempty[acc]), 0) : 0u;   // leader's barrier
+    for (int unit = cta_id; unit < total_units; unit += cta_stride, ++it) {
       if ((it & 1) != grp) continue;
       const int tile = unit / p.splits;
-      const int m0 = (tile % p.m_tiles) * BM;
-      const int n0 = (tile / p.m_tiles) * BN;
+      const int m0 = (tile % p.m_tiles) * BMT + static_cast<int>(crank) * BM;      // this CTA's 128 accumulator rows
+      const int n0 = (tile / p.m_tiles) * BN;                                      // ... over all BN columns
       if (has_in && lane == 0) {       // overlaps the wait for the accumulator
         tma_wait_group_read<0>();      // every store that read my two buffers has drained
         issue_in(cnt, m0, n0, 0);
@@ -329,7 +376,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->tempty[acc]);
+          if (lane == 0) {
+            if constexpr (TWO) mbar_arrive_cluster(tempty_remote);     // both CTAs' warps release the leader's barrier
+            else mbar_arrive(&bars->tempty[acc]);
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -351,30 +401,36 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();   // the peer's smem / barriers / TMEM stay alive until the leader's last MMA retired
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (TWO) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-template <int BN>
-constexpr uint32_t stage_bytes() { return BM * BK * 2 + BN * BK * 2; }
+template <int BN, bool TWO>
+constexpr uint32_t stage_bytes() { return BM * BK * 2 + (TWO ? BN / 2 : BN) * BK * 2; }
 
 inline int pick_stages(uint32_t stage_b) {
   const uint32_t budget = 232448u - 1024u - STG_TOTAL - static_cast<uint32_t>(sizeof(Barriers)) - 64u;
   int s = static_cast<int>(budget / stage_b);
   if (s > kMaxStages) s = kMaxStages;
+  static int cap = -1;                       // MV_GEMM_STAGES=n caps the ring depth (pipeline-depth experiments)
+  if (cap < 0) { const char* e = getenv("MV_GEMM_STAGES"); cap = e ? atoi(e) : 0; }
+  if (cap > 0 && s > cap) s = cap;
   return s;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool TWO>
 int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
+  constexpr int BNL = TWO ? BN / 2 : BN;     // B rows / columns one CTA loads per k-block
+  constexpr int BMT = TWO ? 2 * BM : BM;     // rows of one work unit
   CUtensorMap tmA, tmB, tmC, tmX;
   int rc;
   if (!d.a_mn) rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.K, d.M, d.lda * 2, BK, BM);
   else rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.M, d.K, d.lda * 2, 64, BK);
   if (rc) return rc;
-  if (!d.b_mn) rc = tmap_encode_2d(&tmB, TMAP_BF16, d.B, d.K, d.N, d.ldb * 2, BK, BN);
+  if (!d.b_mn) rc = tmap_encode_2d(&tmB, TMAP_BF16, d.B, d.K, d.N, d.ldb * 2, BK, BNL);
   else rc = tmap_encode_2d(&tmB, TMAP_BF16, d.B, d.N, d.K, d.ldb * 2, 64, BK);
   if (rc) return rc;
   if (OUT_F32) rc = tmap_encode_2d(&tmC, TMAP_F32, d.C, d.N, d.M, d.ldc * 4, 32, 32);
@@ -389,14 +445,15 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
     rc = tmap_encode_2d(&tmX, TMAP_BF16, d.aux, d.N, d.M, d.ldaux * 2, 64, 32);
   }
   if (rc) return rc;
+  p.m_tiles = (d.M + BMT - 1) / BMT;
   p.n_tiles = (d.N + BN - 1) / BN;
-  p.stages = pick_stages(stage_bytes<BN>());
-  // split-K only for fp32 reduce-add outputs (weight gradients): fill ~2 waves of SMs
-  const int sms = device_sm_count();
+  p.stages = pick_stages(stage_bytes<BN, TWO>());
+  // split-K only for fp32 reduce-add outputs (weight gradients): fill ~2 waves of SMs (or SM pairs)
+  const int slots = TWO ? device_sm_count() / 2 : device_sm_count();
   const int tiles = p.m_tiles * p.n_tiles;
   int splits = 1;
   if (d.accumulate) {
-    splits = d.splitk > 0 ? d.splitk : (2 * sms) / tiles;
+    splits = d.splitk > 0 ? d.splitk : (2 * slots) / tiles;
     if (splits < 1) splits = 1;
     const int max_splits = (p.kb_total + 7) / 8;  // keep >= 8 k-blocks per unit
     if (splits > max_splits) splits = max_splits;
@@ -405,43 +462,70 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
   const int units = tiles * p.splits;
-  const int grid = units < sms ? units : sms;
-  const uint32_t smem = 1024u + static_cast<uint32_t>(p.stages) * stage_bytes<BN>() + STG_TOTAL + sizeof(Barriers) + 64u;
-  auto kern = gemm_tc05_kernel<BN, A_MN, B_MN, OUT_F32>;
+  const int grid = (units < slots ? units : slots) * (TWO ? 2 : 1);
+  const uint32_t smem = 1024u + static_cast<uint32_t>(p.stages) * stage_bytes<BN, TWO>() + STG_TOTAL + sizeof(Barriers) + 64u;
+  auto kern = gemm_tc05_kernel<BN, A_MN, B_MN, OUT_F32, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
     MV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     attr_set = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmX, p);
+  if constexpr (TWO) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmX, p));
+  } else {
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmX, p);
+  }
   MV_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN>
+template <int BN, bool TWO>
 int dispatch_major(const GemmDesc& d, const GemmParams& p, cudaStream_t s) {
-  if (!d.a_mn && !d.b_mn) return d.c_f32 ? launch<BN, false, false, true>(d, p, s) : launch<BN, false, false, false>(d, p, s);
-  if (!d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, false, true, true>(d, p, s) : launch<BN, false, true, false>(d, p, s);
-  if (d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, true, true, true>(d, p, s) : launch<BN, true, true, false>(d, p, s);
-  set_error("gemm_bf16_tc05: operand-major combination a_mn=1,b_mn=0 is not instantiated");
+  if (!d.a_mn && !d.b_mn) return d.c_f32 ? launch<BN, false, false, true, TWO>(d, p, s) : launch<BN, false, false, false, TWO>(d, p, s);
+  if constexpr (!TWO || (BN / 2) % 64 == 0) {      // MN-major B is loaded in 64-column groups
+    if (!d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, false, true, true, TWO>(d, p, s) : launch<BN, false, true, false, TWO>(d, p, s);
+    if (d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, true, true, true, TWO>(d, p, s) : launch<BN, true, true, false, TWO>(d, p, s);
+  }
+  set_error("gemm_bf16_tc05: operand-major combination a_mn=%d,b_mn=%d is not instantiated for this tile", d.a_mn, d.b_mn);
   return -1;
 }
 
-// pick the N tile that minimises (waves x per-tile cost) on this GPU
-int pick_bn(int m_tiles, int N, int sms, bool accumulate) {
+// pick the N tile that minimises (waves x per-tile cost) on `slots` SMs (or SM pairs)
+int pick_bn(int m_tiles, int N, int slots, bool accumulate, bool pair, bool b_mn) {
   const int cands[3] = {192, 256, 128};
-  int best = 192;
+  int best = 0;
   double best_cost = 1e30;
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
+    if (pair && b_mn && (bn / 2) % 64 != 0) continue;
     const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
-    const long waves = accumulate ? 1 : (tiles + sms - 1) / sms;
+    const long waves = accumulate ? 1 : (tiles + slots - 1) / slots;
     const double per_tile = bn + 24.0;  // MMA time ~ BN, plus fixed prologue/epilogue overhead
     const double wasted = static_cast<double>(((N + bn - 1) / bn) * bn) / N;
     const double cost = accumulate ? wasted * per_tile / bn : waves * per_tile;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
+}
+
+// MV_GEMM_PAIR=0/1 overrides the automatic choice (A/B measurements)
+int pair_env() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("MV_GEMM_PAIR");
+    v = e ? atoi(e) : -1;
+  }
+  return v;
 }
 
 }  // namespace
@@ -469,11 +553,25 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   p.has_c2 = d.C2 != nullptr; p.accumulate = d.accumulate;
   p.has_in = (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID || d.epi == EPI_DGELU) ? 1 : 0;
   p.drop_on = d.drop_on; p.drop_site = d.drop_site; p.drop = d.drop;
-  const int bn = pick_bn(p.m_tiles, d.N, device_sm_count(), d.accumulate != 0);
+  bool pair = d.M > BM;                       // a single 128-row tile gains nothing from a partner SM
+  if (pair_env() >= 0) pair = pair_env() != 0;
+  if (d.pair >= 0) pair = d.pair != 0;
+  const int sms = device_sm_count();
+  const int m_tiles = pair ? (d.M + 2 * BM - 1) / (2 * BM) : p.m_tiles;
+  int bn = d.bn;
+  if (bn == 0) bn = pick_bn(m_tiles, d.N, pair ? sms / 2 : sms, d.accumulate != 0, pair, d.b_mn != 0);
+  MV_REQUIRE(bn == 128 || bn == 192 || bn == 256, "gemm: N tile %d not instantiated", bn);
+  if (pair) {
+    switch (bn) {
+      case 128: return dispatch_major<128, true>(d, p, stream);
+      case 256: return dispatch_major<256, true>(d, p, stream);
+      default: return dispatch_major<192, true>(d, p, stream);
+    }
+  }
   switch (bn) {
-    case 128: return dispatch_major<128>(d, p, stream);
-    case 256: return dispatch_major<256>(d, p, stream);
-    default: return dispatch_major<192>(d, p, stream);
+    case 128: return dispatch_major<128, false>(d, p, stream);
+    case 256: return dispatch_major<256, false>(d, p, stream);
+    default: return dispatch_major<192, false>(d, p, stream);
   }
 }
 

@@ -29,6 +29,8 @@ static double gelu_grad_d(double x) {
   return 0.5 * (1.0 + erf(x / sqrt(2.0))) + x * exp(-0.5 * x * x) / sqrt(2.0 * M_PI);
 }
 
+static int g_pair = -1, g_bn = 0;   // forced CTA-pair mode / N tile of the tcgen05 path (-1 / 0 = automatic)
+
 static int run_case(const Case& c, bool fp32_mode, int n_samples) {
   const int M = c.M, N = c.N, K = c.K;
   // logical A[m][k], B[n][k]
@@ -78,6 +80,7 @@ static int run_case(const Case& c, bool fp32_mode, int n_samples) {
   d.C2 = dC2; d.ldc2 = N;
   d.epi = c.epi; d.bias = dbias; d.resid = dR; d.ldr = N; d.aux = dR; d.ldaux = N;
   d.drop_on = c.drop; d.drop_site = 7; d.drop = make_dropout(0.1f, 99);
+  d.pair = g_pair; d.bn = g_bn;
   int rc = fp32_mode ? gemm_f32_simt(d, 0) : gemm_bf16_tc05(d, 0);
   if (rc) { printf("  %-34s launch error: %s\n", c.name, last_error()); return 1; }
   cudaError_t e = cudaDeviceSynchronize();
@@ -146,12 +149,18 @@ static void perf(const char* name, int M, int N, int K, int a_mn, int b_mn, int 
   void *dA, *dB, *dC, *dR; float* dbias;
   cudaMalloc(&dA, (size_t)M * K * 2); cudaMalloc(&dB, (size_t)N * K * 2);
   cudaMalloc(&dC, (size_t)M * N * 4); cudaMalloc(&dR, (size_t)M * N * 2); cudaMalloc(&dbias, N * 4);
-  cudaMemset(dA, 0, (size_t)M * K * 2); cudaMemset(dB, 0, (size_t)N * K * 2); cudaMemset(dR, 0, (size_t)M * N * 2);
+  {   // random operands: all-zero inputs draw far less power and flatter the clocks
+    std::vector<bf16> h((size_t)std::max(std::max(M, N) * (size_t)K, (size_t)M * N));
+    for (auto& v : h) v = __float2bfloat16_rn(frand());
+    cudaMemcpy(dA, h.data(), (size_t)M * K * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, h.data(), (size_t)N * K * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(dR, h.data(), (size_t)M * N * 2, cudaMemcpyHostToDevice);
+  }
   cudaMemset(dbias, 0, N * 4); cudaMemset(dC, 0, (size_t)M * N * 4);
   GemmDesc d;
   d.M = M; d.N = N; d.K = K; d.A = dA; d.lda = a_mn ? M : K; d.a_mn = a_mn; d.B = dB; d.ldb = b_mn ? N : K; d.b_mn = b_mn;
   d.C = dC; d.ldc = N; d.c_f32 = c_f32; d.accumulate = acc; d.epi = epi; d.bias = dbias; d.resid = dR; d.ldr = N;
-  d.aux = dR; d.ldaux = N;
+  d.aux = dR; d.ldaux = N; d.pair = g_pair; d.bn = g_bn;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) gemm_bf16_tc05(d, 0);
   cudaEventRecord(e0);
@@ -179,8 +188,10 @@ static void perf_one(int which) {
 }
 
 int main(int argc, char** argv) {
+  if (argc > 3 && !strcmp(argv[1], "--perf-one")) g_pair = atoi(argv[3]);
   if (argc > 2 && !strcmp(argv[1], "--perf-one")) { perf_one(atoi(argv[2])); return 0; }
-  bool do_perf = argc > 1 && !strcmp(argv[1], "--perf");
+  bool do_perf = argc > 1 && (!strcmp(argv[1], "--perf") || !strcmp(argv[1], "--perf-only"));
+  const bool perf_only = argc > 1 && !strcmp(argv[1], "--perf-only");
   int fails = 0;
   const Case cases[] = {
       {"TN 128x192x64 none", 128, 192, 64, 0, 0, 0, 0, EPI_NONE, 0, 0},
@@ -201,8 +212,18 @@ int main(int argc, char** argv) {
       {"TT wgrad 768x2048x360 acc", 768, 2048, 360, 1, 1, 1, 1, EPI_NONE, 0, 0},
       {"TT 200x136x300 f32 store", 200, 136, 300, 1, 1, 1, 0, EPI_NONE, 0, 0},
   };
-  printf("== tcgen05 GEMM ==\n");
-  for (const Case& c : cases) fails += run_case(c, false, 40000);
+  for (int pair = 0; pair < 2 && !perf_only; ++pair) {
+    const int bns[4] = {0, 128, 192, 256};
+    for (int bi = 0; bi < 4; ++bi) {
+      g_pair = pair; g_bn = bns[bi];
+      printf("== tcgen05 GEMM, %s, N tile %s%d ==\n", pair ? "CTA pair (cta_group::2)" : "single CTA", g_bn ? "" : "auto ", g_bn);
+      for (const Case& c : cases) {
+        if (pair && c.b_mn && g_bn == 192) continue;      // MN-major B is loaded in 64-column groups per CTA
+        fails += run_case(c, false, bi == 0 ? 40000 : 8000);
+      }
+    }
+  }
+  g_pair = -1; g_bn = 0;
   printf("== fp32 SIMT GEMM ==\n");
   const Case fcases[] = {
       {"TN 300x200x136 bias", 300, 200, 136, 0, 0, 0, 0, EPI_BIAS, 0, 0},
@@ -211,9 +232,10 @@ int main(int argc, char** argv) {
       {"NN 300x192x136 dgelu", 300, 192, 136, 0, 1, 0, 0, EPI_DGELU, 0, 0},
       {"TT 200x136x300 acc", 200, 136, 300, 1, 1, 1, 1, EPI_NONE, 0, 0},
   };
-  for (const Case& c : fcases) fails += run_case(c, true, 40000);
-  if (do_perf) {
-    printf("== perf (B=64, L=436: M=27904) ==\n");
+  for (const Case& c : fcases) if (!perf_only) fails += run_case(c, true, 40000);
+  for (int pair = 0; pair < 2 && do_perf; ++pair) {
+    g_pair = pair;
+    printf("== perf (B=64, L=436: M=27904), %s ==\n", pair ? "CTA pair" : "single CTA");
     perf("QKV fwd", 27904, 2304, 768, 0, 0, 0, 0, EPI_BIAS);
     perf("out-proj fwd", 27904, 768, 768, 0, 0, 0, 0, EPI_BIAS_RESID);
     perf("FFN1 fwd", 27904, 3072, 768, 0, 0, 0, 0, EPI_BIAS_GELU);

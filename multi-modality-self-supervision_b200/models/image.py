@@ -21,6 +21,10 @@ class TrunkExecutor:
     library's fused BatchNorm(+residual)(+ReLU) kernels (mv_bn_forward).  Parameters and BN buffers stay the module's
     own tensors (state_dict-compatible); only dtype/layout-converted copies of the frozen conv weights are cached."""
 
+    # input channels of the stem convolution as laid out in memory.  Measured on B200 (profiles/): cuDNN's 3-channel
+    # 7x7/2 kernel takes 1.93 ms at B=64, the zero-padded 8-channel tensor-op implicit GEMM 3.64 ms -> keep 3.
+    STEM_CPAD = 3
+
     def __init__(self, seq, act_dtype):
         self.seq, self.act_dtype = seq, act_dtype
         self.w = {}
@@ -31,7 +35,11 @@ class TrunkExecutor:
         self.w = {}
         for name, m in self.seq.named_modules():
             if isinstance(m, nn.Conv2d):
-                self.w[name] = m.weight.detach().to(self.act_dtype).contiguous(memory_format=torch.channels_last)
+                w = m.weight.detach().to(self.act_dtype)
+                if name == "0" and w.shape[1] == 3:
+                    # stem: zero-pad the 3 input channels to STEM_CPAD so cuDNN runs it as a tensor-op implicit GEMM
+                    w = F.pad(w, (0, 0, 0, 0, 0, self.STEM_CPAD - 3))
+                self.w[name] = w.contiguous(memory_format=torch.channels_last)
 
     def _conv(self, name, m, x):
         if self.act_dtype == torch.float32:      # check mode: true fp32 convolutions (no TF32) for the 1e-4 gate
@@ -62,22 +70,42 @@ class TrunkExecutor:
         if Cc != 3:
             raise _lib.MedvillError("uint8 images must be [B, 3, H, W]")
         x = x.contiguous()
-        out = torch.empty((B, 3, H, W), dtype=self.act_dtype, device=x.device, memory_format=torch.channels_last)
+        cpad = self.STEM_CPAD
+        out = torch.empty((B, cpad, H, W), dtype=self.act_dtype, device=x.device, memory_format=torch.channels_last)
         mean = (C.c_float * 3)(0.485, 0.456, 0.406)
         std = (C.c_float * 3)(0.229, 0.224, 0.225)
         prec = _lib.MV_PREC_FP32 if self.act_dtype == torch.float32 else _lib.MV_PREC_BF16
-        _lib.check(_lib.lib().mv_normalize_u8(_lib.ptr(x), _lib.ptr(out), B, H * W, mean, std, prec, _lib.stream_ptr(x.device)),
+        _lib.check(_lib.lib().mv_normalize_u8(_lib.ptr(x), _lib.ptr(out), B, H * W, cpad, mean, std, prec, _lib.stream_ptr(x.device)),
                    "mv_normalize_u8")
         return out
+
+    def _stem_tail(self, m, pool, x, training):
+        """BatchNorm + ReLU + MaxPool2d(3, 2, 1) in one apply pass (mv_bn_relu_maxpool)"""
+        B, Cc, H, W = x.shape
+        fused = (isinstance(pool, nn.MaxPool2d) and pool.kernel_size == 3 and pool.stride == 2 and pool.padding == 1
+                 and H % 2 == 0 and W % 2 == 0)
+        if not fused:
+            return pool(self._bn(m, x, True, training))
+        need = int(_lib.lib().mv_bn_workspace_floats(B * H * W, Cc))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(need, dtype=torch.float32, device=x.device)
+        y = torch.empty((B, Cc, H // 2, W // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        prec = _lib.MV_PREC_FP32 if self.act_dtype == torch.float32 else _lib.MV_PREC_BF16
+        _lib.check(_lib.lib().mv_bn_relu_maxpool(_lib.ptr(x), _lib.ptr(y), B, H, W, Cc, _lib.ptr(m.weight), _lib.ptr(m.bias),
+                                                 _lib.ptr(m.running_mean), _lib.ptr(m.running_var), float(m.momentum), float(m.eps),
+                                                 1 if training else 0, _lib.ptr(self.ws), self.ws.numel(), prec,
+                                                 _lib.stream_ptr(x.device)), "mv_bn_relu_maxpool")
+        if training:
+            m.num_batches_tracked.add_(1)
+        return y
 
     def __call__(self, x, training):
         s = self.seq
         if x.dtype == torch.uint8:
             x = self._normalize_u8(x)
         else:
-            x = x.to(self.act_dtype).contiguous(memory_format=torch.channels_last)
-        x = self._bn(s[1], self._conv("0", s[0], x), True, training)
-        x = s[3](x)
+            x = F.pad(x.to(self.act_dtype), (0, 0, 0, 0, 0, self.STEM_CPAD - x.shape[1])).contiguous(memory_format=torch.channels_last)
+        x = self._stem_tail(s[1], s[3], self._conv("0", s[0], x), training)
         for li in (4, 5, 6, 7):
             for bi, blk in enumerate(s[li]):
                 pre = "%d.%d." % (li, bi)

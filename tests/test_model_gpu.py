@@ -76,8 +76,31 @@ def test_uint8_images_are_normalised_on_the_device():
     for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
         ex.act_dtype = dt
         out = ex._normalize_u8(x.cuda())
-        assert out.is_contiguous(memory_format=torch.channels_last)
-        assert (out.float().cpu() - ref).abs().max() <= tol * ref.abs().max()
+        assert out.is_contiguous(memory_format=torch.channels_last) and out.shape[1] == TrunkExecutor.STEM_CPAD
+        assert (out[:, :3].float().cpu() - ref).abs().max() <= tol * ref.abs().max()
+        if out.shape[1] > 3:
+            assert float(out[:, 3:].abs().max()) == 0.0      # zero pad channels feed zero-padded stem weights
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+def test_stem_tail_bn_relu_maxpool_vs_torch(dtype, tol):
+    from medvill_b200 import _lib
+
+    B, Cc, H, W = 3, 64, 20, 12
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(B, Cc, H, W, generator=g) * 1.5 + 0.3).to(dtype)
+    w, b = torch.rand(Cc, generator=g) - 0.3, torch.randn(Cc, generator=g)       # some negative scales on purpose
+    rm, rv = torch.zeros(Cc), torch.ones(Cc)
+    ref = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.batch_norm(x.float(), rm.clone(), rv.clone(), w, b, training=True,
+                                                                                 momentum=0.1, eps=1e-5)), 3, 2, 1)
+    dx = x.cuda().contiguous(memory_format=torch.channels_last)
+    y = torch.empty((B, Cc, H // 2, W // 2), dtype=dtype, device="cuda", memory_format=torch.channels_last)
+    ws = torch.empty(int(_lib.lib().mv_bn_workspace_floats(B * H * W, Cc)), dtype=torch.float32, device="cuda")
+    prec = _lib.MV_PREC_FP32 if dtype == torch.float32 else _lib.MV_PREC_BF16
+    dw, db, drm, drv = w.cuda(), b.cuda(), rm.cuda(), rv.cuda()          # keep the device copies alive across the call
+    _lib.check(_lib.lib().mv_bn_relu_maxpool(_lib.ptr(dx), _lib.ptr(y), B, H, W, Cc, _lib.ptr(dw), _lib.ptr(db), _lib.ptr(drm),
+                                             _lib.ptr(drv), 0.1, 1e-5, 1, _lib.ptr(ws), ws.numel(), prec, _lib.stream_ptr()))
+    assert (y.float().cpu() - ref).abs().max() <= tol * ref.abs().max()
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 0.5)])
