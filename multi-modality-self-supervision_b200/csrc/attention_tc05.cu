@@ -129,15 +129,18 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
     const int jn = next_active(j);
     const uint32_t ph = it & 1u;
     const int k_lo = j * TK;
-    if (tid == 0) {
+    if (warp == 0) {      // warp-uniform (descriptors stay in uniform registers); one elected lane issues
       if (it == 0) mbar_wait(&sh->bar_q, 0);
       mbar_wait(&sh->bar_k, ph);
       tc_fence_after();
       const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(&sh->bar_s);
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(&sh->bar_s);
+      }
+      __syncwarp();
     }
     mbar_wait(&sh->bar_s, ph);
     tc_fence_after();
@@ -218,15 +221,18 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       mbar_wait(&sh->bar_v, ph);
       const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+      if (elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < TK / 16; ++kk)
-        umma_bf16(tmem + 128, make_smem_desc_sw128(pa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(va + kk * 2048, 8192, 1024), idesc_o, kk > 0);
-      umma_commit(&sh->bar_o);
+        for (int kk = 0; kk < TK / 16; ++kk)
+          umma_bf16(tmem + 128, make_smem_desc_sw128(pa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(va + kk * 2048, 8192, 1024), idesc_o, kk > 0);
+        umma_commit(&sh->bar_o);
+      }
+      __syncwarp();
     }
     const float m_new = fmaxf(sh->xmax[ph][0][r], sh->xmax[ph][1][r]);
     mbar_wait(&sh->bar_o, ph);
@@ -388,14 +394,18 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint32_t it = 0;
 
   auto issue_s_dp = [&](uint32_t buf) {
+    // called by all of warp 0 (uniform); one elected lane issues
     const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO + buf * TILE_BYTES);
+    if (elect_one()) {
 #pragma unroll
-    for (int k = 0; k < D / 16; ++k)
-      umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
-    for (int k = 0; k < D / 16; ++k)
-      umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
-    umma_commit(&sh->bar_s);
+      for (int k = 0; k < D / 16; ++k)
+        umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
+      umma_commit(&sh->bar_s);
+    }
+    __syncwarp();
   };
   auto row_stats = [&](int qi, float& lse2_o, float& delta_o) {
     const int qq = qi * TQ + r;
@@ -405,9 +415,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   };
   float lse2 = 0.f, delta = 0.f;
   if (any) row_stats(i, lse2, delta);
-  if (tid == 0 && any) {
+  if (warp == 0 && any) {
     const int i1 = next_active(i);
-    if (i1 < n_q) load_q(i1, 1);
+    if (lane == 0 && i1 < n_q) load_q(i1, 1);
+    __syncwarp();
     mbar_wait(&sh->bar_kv, 0);
     mbar_wait(&sh->bar_q[0], 0);
     tc_fence_after();
@@ -481,23 +492,26 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     tc_fence_before();
     fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {      // warp-uniform; one elected lane issues the 24 MMAs
       tc_fence_after();
       const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK),
                      da = smem_u32(sdO + buf * TILE_BYTES);
+      if (elect_one()) {
 #pragma unroll
-      for (int kk = 0; kk < TQ / 16; ++kk)  // dV[k,d] += sum_q P[q,k] dO[q,d]
-        umma_bf16(tmem + 256, make_smem_desc_sw128(pa + kk * 2048, TILE_BYTES, 1024),
-                  make_smem_desc_sw128(da + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
+        for (int kk = 0; kk < TQ / 16; ++kk)  // dV[k,d] += sum_q P[q,k] dO[q,d]
+          umma_bf16(tmem + 256, make_smem_desc_sw128(pa + kk * 2048, TILE_BYTES, 1024),
+                    make_smem_desc_sw128(da + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
 #pragma unroll
-      for (int kk = 0; kk < TQ / 16; ++kk)  // dK[k,d] += sum_q dS[q,k] Q[q,d]
-        umma_bf16(tmem + 320, make_smem_desc_sw128(sa + kk * 2048, TILE_BYTES, 1024),
-                  make_smem_desc_sw128(qa + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
+        for (int kk = 0; kk < TQ / 16; ++kk)  // dK[k,d] += sum_q dS[q,k] Q[q,d]
+          umma_bf16(tmem + 320, make_smem_desc_sw128(sa + kk * 2048, TILE_BYTES, 1024),
+                    make_smem_desc_sw128(qa + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
 #pragma unroll
-      for (int kk = 0; kk < TK / 16; ++kk)  // dQ[q,d] = sum_k dS[q,k] K[k,d]
-        umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
-      umma_commit(&sh->bar_o);
+        for (int kk = 0; kk < TK / 16; ++kk)  // dQ[q,d] = sum_k dS[q,k] K[k,d]
+          umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+        umma_commit(&sh->bar_o);
+      }
+      __syncwarp();
       if (in < n_q) {                       // S / dP columns were released by the barrier above: start the next tile now
         mbar_wait(&sh->bar_q[buf ^ 1u], ((it + 1) >> 1) & 1u);
         tc_fence_after();

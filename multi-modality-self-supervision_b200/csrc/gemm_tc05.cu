@@ -60,23 +60,13 @@ __device__ __forceinline__ void unstage_bf16_half(const uint8_t* stg, int lane, 
 // Epilogue math on 32 consecutive columns [col0, col0+32) of output row `row`.
 // f: accumulators in, final values out; pre: pre-activation (EPI_BIAS_GELU); in: residual / GELU-backward operand.
 __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[32], float (&pre)[32], const float (&in)[32],
-                                               int row, int col0) {
+                                               int row, int col0, float bias_lane) {
+  // bias_lane: bias[col0 + lane] (0 past N), prefetched by the caller one step ahead so that its L2 latency never sits on
+  // the accumulator-drain path; column j's value is fetched from lane j.
   const int epi = p.epi;
   if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH) {
-    if (col0 + 32 <= p.N) {      // 8 x 16-byte broadcast loads (col0 % 32 == 0, arena tensors are 256 B aligned)
-      const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b4 = __ldg(bp + j);
-        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int c = col0 + j;
-        f[j] += (c < p.N) ? __ldg(p.bias + c) : 0.f;
-      }
-    }
+    for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bias_lane, j);
   }
   if (epi == EPI_BIAS_GELU) {
 #pragma unroll
@@ -120,6 +110,24 @@ __device__ __forceinline__ void stage_f32(uint8_t* stg, int lane, const float (&
   for (int j = 0; j < 8; ++j) {
     *reinterpret_cast<float4*>(stg + sw128_off(lane, j)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
   }
+}
+
+// Work unit -> (m tile, n tile, k-block range).  Units are walked by CTA (or CTA pair) c as c, c + stride, ...:
+//   plain GEMMs   : n tile fastest, so the CTAs running at the same time share a few row blocks of the (large) activation
+//                   operand through L2 while the whole weight matrix (a few MB) stays L2-resident;
+//   split-K wgrad : tile fastest / split slowest, so all output tiles walk the same K range together and every byte
+//                   of both activation operands is fetched from HBM once.
+struct Unit { int m_tile, n_tile, kb0, kb1; };
+__device__ __forceinline__ Unit decode_unit(const GemmParams& p, int unit) {
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int split = unit / tiles;
+  const int tile = unit - split * tiles;
+  Unit u;
+  u.m_tile = tile / p.n_tiles;
+  u.n_tile = tile - u.m_tile * p.n_tiles;
+  u.kb0 = split * p.kb_per_split;
+  u.kb1 = min(p.kb_total, u.kb0 + p.kb_per_split);
+  return u;
 }
 
 // TWO = true: CTA-pair mode.  Two CTAs of a 2-CTA cluster compute one 256 x BN tile with tcgen05.mma.cta_group::2: CTA r
@@ -183,7 +191,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = bars->tmem_base;
 
   const int tiles = p.m_tiles * p.n_tiles;          // pair mode: m_tiles counts 256-row tiles
-  const int total_units = tiles * p.splits;
+  const int total_units = tiles * p.splits;   // see decode_unit for the order
   constexpr int BMT = TWO ? 2 * BM : BM;            // rows of one work unit
 
   if (warp == 0) {
@@ -194,13 +202,10 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     const uint32_t full0 = TWO ? mapa_cluster(smem_u32(&bars->full[0]), 0) : 0u;   // leader's full[0] (cluster address)
     for (int unit = cta_id; unit < total_units; unit += cta_stride) {
-      const int split = unit % p.splits;
-      const int tile = unit / p.splits;
-      const int m0 = (tile % p.m_tiles) * BMT + static_cast<int>(crank) * BM;     // this CTA's 128 rows of A
-      const int n0 = (tile / p.m_tiles) * BN + static_cast<int>(crank) * BNL;     // this CTA's share of B
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const Unit u = decode_unit(p, unit);
+      const int m0 = u.m_tile * BMT + static_cast<int>(crank) * BM;     // this CTA's 128 rows of A
+      const int n0 = u.n_tile * BN + static_cast<int>(crank) * BNL;     // this CTA's share of B
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(&bars->empty[stage], phase ^ 1u);
         uint8_t* sA = smem + static_cast<uint32_t>(stage) * STAGE_BYTES;
         uint8_t* sB = sA + A_BYTES;
@@ -255,9 +260,8 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int unit = cta_id; unit < total_units; unit += cta_stride) {
-        const int split = unit % p.splits;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const Unit u = decode_unit(p, unit);
+        const int kb0 = u.kb0, kb1 = u.kb1;
         mbar_wait(&bars->tempty[acc], acc_phase ^ 1u);      // released by the epilogue (of both CTAs in pair mode)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE;
@@ -317,13 +321,16 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tempty_remote = TWO ? mapa_cluster(smem_u32(&bars->tempty[acc]), 0) : 0u;   // leader's barrier
     for (int unit = cta_id; unit < total_units; unit += cta_stride, ++it) {
       if ((it & 1) != grp) continue;
-      const int tile = unit / p.splits;
-      const int m0 = (tile % p.m_tiles) * BMT + static_cast<int>(crank) * BM;      // this CTA's 128 accumulator rows
-      const int n0 = (tile / p.m_tiles) * BN;                                      // ... over all BN columns
+      const Unit u = decode_unit(p, unit);
+      const int m0 = u.m_tile * BMT + static_cast<int>(crank) * BM;      // this CTA's 128 accumulator rows
+      const int n0 = u.n_tile * BN;                                      // ... over all BN columns
       if (has_in && lane == 0) {       // overlaps the wait for the accumulator
         tma_wait_group_read<0>();      // every store that read my two buffers has drained
         issue_in(cnt, m0, n0, 0);
       }
+      const bool has_bias = p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID || p.epi == EPI_BIAS_TANH;
+      auto bias_at = [&](int col) { return (has_bias && col < p.N) ? __ldg(p.bias + col) : 0.f; };
+      float bias_next = bias_at(n0 + lane);      // first 32 columns; later ones are fetched one step ahead
       mbar_wait(&bars->tfull[acc], acc_phase);
       acc_phase ^= 1u;
       tc_fence_after();
@@ -358,7 +365,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             if (has_in) unstage_bf16_half(s2, lane, half, in);
-            epilogue_apply(p, f, pre, in, row, n0 + c * 64 + half * 32);
+            const float bias_cur = bias_next;
+            bias_next = bias_at(n0 + c * 64 + half * 32 + 32 + lane);
+            epilogue_apply(p, f, pre, in, row, n0 + c * 64 + half * 32, bias_cur);
             stage_bf16_half(s1, lane, half, f);
             if (p.has_c2) stage_bf16_half(s2, lane, half, pre);
           }
@@ -369,7 +378,9 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float f[32], pre[32], in[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          epilogue_apply(p, f, pre, in, row, n0 + c * 32);
+          const float bias_cur = bias_next;
+          bias_next = bias_at(n0 + c * 32 + 32 + lane);
+          epilogue_apply(p, f, pre, in, row, n0 + c * 32, bias_cur);
           stage_f32(s1, lane, f);
         }
         if (c == NCHUNK - 1) {
@@ -453,11 +464,22 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   const int tiles = p.m_tiles * p.n_tiles;
   int splits = 1;
   if (d.accumulate) {
-    splits = d.splitk > 0 ? d.splitk : (2 * slots) / tiles;
+    // split-K (fp32 reduce-add outputs): pick the split count that minimises waves x (k-blocks per unit + fixed cost)
+    if (d.splitk > 0) {
+      splits = d.splitk;
+    } else {
+      const int max_splits = (p.kb_total + 7) / 8;      // keep >= 8 k-blocks per unit
+      long best = -1;
+      for (int sp = 1; sp <= max_splits && sp <= 64; ++sp) {
+        const int kbs = (p.kb_total + sp - 1) / sp;
+        const int real = (p.kb_total + kbs - 1) / kbs;
+        const long waves = (static_cast<long>(tiles) * real + slots - 1) / slots;
+        const long cost = waves * (kbs + 8);            // ~8 k-blocks worth of prologue + reduce-add epilogue per unit
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+      }
+    }
     if (splits < 1) splits = 1;
-    const int max_splits = (p.kb_total + 7) / 8;  // keep >= 8 k-blocks per unit
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
+    if (splits > p.kb_total) splits = p.kb_total;
   }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
