@@ -122,6 +122,9 @@ int mv_zero_grads(mv_handle* h, void* stream);
 int mv_adamw_step(mv_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                   float grad_scale, void* stream);                       /* waits for pending all-reduces; zeroes g */
 int mv_read_stats(mv_handle* h, mv_step_stats* host_out, void* stream);  /* D2H + stream sync                       */
+int mv_read_stats_async(mv_handle* h, mv_step_stats* pinned_out, void* stream);  /* D2H enqueue only (pinned dst):   */
+                                                                         /* lets the trainer log the loss lazily    */
+                                                                         /* (train_origin.py:118-146 syncs per step)*/
 int mv_itm_logits(mv_handle* h, float* host_out, int32_t B, void* stream);
 int mv_full_logits(mv_handle* h, const mv_batch* b, float* logits, int64_t ld, void* stream);  /* [B*L, ld] fp32    */
 int mv_peek(mv_handle* h, const char* name, int32_t layer, void* dst, int64_t max_bytes, int64_t* bytes, void* stream);

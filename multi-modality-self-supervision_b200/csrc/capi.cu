@@ -124,6 +124,16 @@ int mv_read_stats(mv_handle* h, mv_step_stats* host_out, void* stream) {
   return 0;
 }
 
+// Enqueue the device->host copy of the step statistics into caller-owned PINNED memory; no synchronisation.  The caller
+// orders its read with an event recorded on `stream` after this call (the next step's mv_stats_reset is stream-ordered
+// behind the copy, so the values cannot be overwritten early).
+int mv_read_stats_async(mv_handle* h, mv_step_stats* pinned_out, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(pinned_out, "mv_read_stats_async: null output");
+  MV_CUDA_CHECK(cudaMemcpyAsync(pinned_out, h->eng.stats, sizeof(mv_step_stats), cudaMemcpyDeviceToHost, S(stream)));
+  return 0;
+}
+
 int mv_itm_logits(mv_handle* h, float* host_out, int32_t B, void* stream) {
   MV_CHECK_HANDLE(h);
   MV_REQUIRE(host_out && B > 0 && B <= h->eng.cfg.max_batch, "mv_itm_logits: bad arguments");

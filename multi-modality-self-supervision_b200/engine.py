@@ -239,6 +239,25 @@ class PretrainEngine:
         check(lib().mv_read_stats(self._h, C.byref(st), stream_ptr(self.device)), "mv_read_stats")
         return dict(mlm_loss_sum=st.mlm_loss_sum, itm_loss_sum=st.itm_loss_sum, mlm_correct=st.mlm_correct, itm_correct=st.itm_correct)
 
+    def read_stats_async(self):
+        """Enqueue the statistics read-back into a rotating pinned slot; returns a zero-argument callable that waits for
+        that copy (only) and yields the same dict as read_stats().  Lets a trainer keep the GPU queue full and look at
+        the loss one step (or `log_freq` steps) later."""
+        if not hasattr(self, "_stat_slots"):
+            self._stat_slots = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(8)]
+            self._stat_next = 0
+        slot = self._stat_slots[self._stat_next % len(self._stat_slots)]
+        self._stat_next += 1
+        check(lib().mv_read_stats_async(self._h, ptr(slot), stream_ptr(self.device)), "mv_read_stats_async")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+
+        def resolve():
+            ev.synchronize()
+            f = slot.view(torch.float32)
+            return dict(mlm_loss_sum=float(f[0]), itm_loss_sum=float(f[1]), mlm_correct=int(slot[2]), itm_correct=int(slot[3]))
+        return resolve
+
     def itm_logits(self, B):
         out = torch.empty(B, 2, dtype=torch.float32)
         check(lib().mv_itm_logits(self._h, ptr(out), B, stream_ptr(self.device)), "mv_itm_logits")

@@ -345,11 +345,12 @@ class CXRBERT(nn.Module):
         return logits, itm
 
     def pretrain_step(self, cls_tok, input_ids, txt_labels, attn_masks, image, segment, is_aligned, sep_tok, lr=None,
-                      mode=None, t_len=None, optimizer_step=True, feats=None):
+                      mode=None, t_len=None, optimizer_step=True, feats=None, lazy=False):
         """One fused MLM+ITM step == models/train_origin.py:106-131 (forward, CE losses, zero_grad, backward, AdamW.step)
         plus the metrics of :133-146.  Tensors may live on the host (pinned) or the device.  Under torch.distributed
         (one process per GPU) gradients are all-reduced in buckets overlapped with backward and the loss normalisers
-        are global, so N ranks x B samples reproduce a single-process batch of N*B."""
+        are global, so N ranks x B samples reproduce a single-process batch of N*B.
+        lazy=True returns a callable yielding the same dict (see below)."""
         B = int(input_ids.shape[0])
         eng = self.engine(min(B, int(getattr(self.args, "max_micro_batch", 64))))
         lab = torch.as_tensor(txt_labels)
@@ -372,11 +373,18 @@ class CXRBERT(nn.Module):
             eng.backward(batch, allreduce=(eng.world > 1 and ci == len(chunks) - 1))
         if optimizer_step:
             eng.adamw_step(lr=float(self.args.lr if lr is None else lr))
-        st = eng.read_stats()
-        mlm = st["mlm_loss_sum"] / max(1, n_lab)
-        itm = st["itm_loss_sum"] / B
-        return dict(loss=mlm + itm, mlm_loss=mlm, itm_loss=itm, itm_correct=st["itm_correct"], mlm_correct=st["mlm_correct"],
-                    n_labelled=n_lab, batch=B)
+
+        def finish(st):
+            mlm = st["mlm_loss_sum"] / max(1, n_lab)
+            itm = st["itm_loss_sum"] / B
+            return dict(loss=mlm + itm, mlm_loss=mlm, itm_loss=itm, itm_correct=st["itm_correct"], mlm_correct=st["mlm_correct"],
+                        n_labelled=n_lab, batch=B)
+        if lazy:
+            # the statistics travel to pinned host memory asynchronously; calling the returned object waits for that copy
+            # only, so the caller can enqueue the next step first (the reference blocks on loss.item() every step)
+            pending = eng.read_stats_async()
+            return lambda: finish(pending())
+        return finish(eng.read_stats())
 
     def eval_step(self, cls_tok, input_ids, txt_labels, attn_masks, image, segment, is_aligned, sep_tok, mode=None, t_len=None,
                   feats=None):

@@ -89,18 +89,27 @@ class CXRBERT_Trainer():
             it = tqdm.tqdm(it, desc=f'EP_:{epoch}', total=len(loader), bar_format='{l_bar}{r_bar}')
         losses, mlm_losses, itm_losses = [], [], []
         itm_ok = itm_n = mlm_ok = mlm_n = 0
-        for i, data in it:
-            cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok, mode, t_len = self._unpack(data)
-            if train:
-                out = self.model.pretrain_step(cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok,
-                                               lr=self.lr, mode=mode, t_len=t_len)
-                self.step_cnt += 1
-            else:
-                out = self.model.eval_step(cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok,
-                                           mode=mode, t_len=t_len)
+        pending = None        # training statistics are read back asynchronously and consumed one step late
+
+        def account(out):
+            nonlocal itm_ok, itm_n, mlm_ok, mlm_n
             losses.append(out["loss"]); mlm_losses.append(out["mlm_loss"]); itm_losses.append(out["itm_loss"])
             itm_ok += out["itm_correct"]; itm_n += out["batch"]
             mlm_ok += out["mlm_correct"]; mlm_n += out["n_labelled"]
+        for i, data in it:
+            cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok, mode, t_len = self._unpack(data)
+            if train:
+                nxt = self.model.pretrain_step(cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok,
+                                               lr=self.lr, mode=mode, t_len=t_len, lazy=True)
+                self.step_cnt += 1
+                if pending is not None:
+                    account(pending())
+                pending = nxt
+            else:
+                account(self.model.eval_step(cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok,
+                                             mode=mode, t_len=t_len))
+        if pending is not None:
+            account(pending())
         return dict(loss=float(np.mean(losses)) if losses else float("nan"), mlm_loss=float(np.mean(mlm_losses)) if losses else float("nan"),
                     itm_loss=float(np.mean(itm_losses)) if losses else float("nan"), itm_acc=100.0 * itm_ok / max(1, itm_n),
                     mlm_acc=100.0 * mlm_ok / max(1, mlm_n))
