@@ -14,6 +14,8 @@
  *   mv_comm_* / bucketed all-reduce nn.DataParallel gradient reduction  models/train_origin.py:53-55
  *   mv_attn_mask_dump / classify    CXRDataset mask construction        data/dataset_origin.py:138-176
  *                                   get_extended_attn_mask              models/cxrbert_origin.py:75-85
+ *   mv_itm_match_prob               retrieval similarity                Downstream_task/Retrieval/retrieval.py:29-32,
+ *                                                                       full_dset_retrieval.py:499-509
  *   mv_full_logits                  prediction_scores [B,L,V] of CXRBERT.forward (drop-in output)
  *   mv_gemm / mv_attention_* / mv_layernorm_* / mv_mlm_ce             per-op entry points used by the parity tests
  */
@@ -126,6 +128,10 @@ int mv_read_stats_async(mv_handle* h, mv_step_stats* pinned_out, void* stream); 
                                                                          /* lets the trainer log the loss lazily    */
                                                                          /* (train_origin.py:118-146 syncs per step)*/
 int mv_itm_logits(mv_handle* h, float* host_out, int32_t B, void* stream);
+/* softmax(itm_logits)[:, 1] of the last mv_forward -> device_out[B] (device pointer, stream-ordered, no sync): the pair
+ * similarity of label-conditioned retrieval, CXRBertForRetrieval.forward + nn.Softmax(dim=1)(logits)[:, 1]
+ * (Downstream_task/Retrieval/retrieval.py:29-32, full_dset_retrieval.py:499-509). */
+int mv_itm_match_prob(mv_handle* h, float* device_out, int32_t B, void* stream);
 int mv_full_logits(mv_handle* h, const mv_batch* b, float* logits, int64_t ld, void* stream);  /* [B*L, ld] fp32    */
 int mv_peek(mv_handle* h, const char* name, int32_t layer, void* dst, int64_t max_bytes, int64_t* bytes, void* stream);
 

@@ -76,6 +76,7 @@ SYMBOLS = {
     "mv_read_stats": (_I, [_P, C.POINTER(mv_step_stats), _P]),
     "mv_read_stats_async": (_I, [_P, _P, _P]),
     "mv_itm_logits": (_I, [_P, _P, _I, _P]),
+    "mv_itm_match_prob": (_I, [_P, _P, _I, _P]),
     "mv_full_logits": (_I, [_P, C.POINTER(mv_batch), _P, _L, _P]),
     "mv_peek": (_I, [_P, C.c_char_p, _I, _P, _L, C.POINTER(_L), _P]),
     "mv_launch_count": (C.c_long, []),

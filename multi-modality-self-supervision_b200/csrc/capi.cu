@@ -142,6 +142,14 @@ int mv_itm_logits(mv_handle* h, float* host_out, int32_t B, void* stream) {
   return 0;
 }
 
+// Match probability softmax(itm_logits)[:, 1] of the last mv_forward, written to DEVICE memory (no synchronisation): the
+// retrieval scorer appends one slice of the [images x reports] similarity matrix per forward.
+int mv_itm_match_prob(mv_handle* h, float* device_out, int32_t B, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(device_out && B > 0 && B <= h->eng.cfg.max_batch, "mv_itm_match_prob: bad arguments");
+  return itm_match_prob(h->eng.itm_logits, device_out, B, S(stream));
+}
+
 int mv_full_logits(mv_handle* h, const mv_batch* b, float* logits, int64_t ld, void* stream) {
   MV_CHECK_HANDLE(h);
   MV_REQUIRE(b && logits, "mv_full_logits: null argument");

@@ -86,6 +86,9 @@ struct ItmArgs {
   float* dw; float* db;              // fp32 grads (atomic)
 };
 int itm_head_fwd_bwd(const ItmArgs& a, int f32, cudaStream_t s);
+// out[b] = softmax(logits[b, :2])[1]: the image-report match probability used as the retrieval similarity
+// (Downstream_task/Retrieval/full_dset_retrieval.py:499-509)
+int itm_match_prob(const float* logits, float* out, int B, cudaStream_t s);
 
 // ---- optimizer: HF-3.x AdamW, correct_bias=True (models/train_origin.py:60,129-131)
 struct AdamArgs {

@@ -155,7 +155,25 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, float step
   }
 }
 
+// Retrieval score of a pair = softmax(itm_logits)[1] (Downstream_task/Retrieval/full_dset_retrieval.py:506-507), fp32
+__global__ void __launch_bounds__(256) itm_match_prob_kernel(const float* __restrict__ logits, float* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float z0 = logits[2 * b], z1 = logits[2 * b + 1];
+  const float mx = fmaxf(z0, z1);
+  const float e0 = expf(z0 - mx), e1 = expf(z1 - mx);
+  out[b] = e1 / (e0 + e1);
+}
+
 }  // namespace
+
+int itm_match_prob(const float* logits, float* out, int B, cudaStream_t s) {
+  if (B <= 0) return 0;
+  MV_REQUIRE(logits && out, "itm_match_prob: null argument");
+  itm_match_prob_kernel<<<(B + 255) / 256, 256, 0, s>>>(logits, out, B);
+  MV_LAUNCH_CHECK();
+  return 0;
+}
 
 int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s) {
   if (a.n <= 0) return 0;

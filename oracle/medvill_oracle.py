@@ -541,3 +541,78 @@ def attention_reference(q, k, v, mode, t_len, A, scale=None):
     ext = extended_mask(masks)
     probs = torch.softmax((q @ k.transpose(-1, -2)) * scale + ext, dim=-1)
     return probs @ v
+
+
+# =====================================================================================================
+# Label-conditioned retrieval scoring (BASELINE.json configs[4])
+# =====================================================================================================
+def retrieval_params(cfg, seed=0, bn_seed=7, itm_gain=60.0):
+    """synth_params with (a) non-trivial BatchNorm running statistics — retrieval runs model.eval()
+    (full_dset_retrieval.py:462), so BN reads them — and (b) the ITM weight scaled up so that match probabilities spread
+    over (0, 1) instead of clustering at 0.5 (a random-init head is otherwise not discriminative for a ranking test)."""
+    params = synth_params(cfg, seed=seed)
+    g = torch.Generator().manual_seed(bn_seed)
+    for k in sorted(params):
+        if k.endswith("running_mean"):
+            params[k] = 0.1 * torch.randn(params[k].shape, generator=g)
+        elif k.endswith("running_var"):
+            params[k] = 0.5 + torch.rand(params[k].shape, generator=g)
+    params["itm.linear.weight"] = params["itm.linear.weight"] * itm_gain
+    return params
+
+
+def retrieval_pair(encoded_sentence, cfg):
+    """CXR_Retrieval_Dataset.data_processing (Downstream_task/Retrieval/full_dset_retrieval.py:199-218):
+    ids + [SEP], zero padding to seq_len + 1, 1-D attention mask over [CLS]+regions+[SEP] and the real text."""
+    ids = list(encoded_sentence)[:cfg.seq_len] + [SEP]
+    t_len = len(ids)
+    n_pad = cfg.seq_len - t_len + 1
+    return dict(cls_tok=np.asarray([CLS], dtype=np.int64), input_ids=np.asarray(ids + [PAD] * n_pad, dtype=np.int64),
+                attn_masks=np.asarray([1] * (cfg.num_image_embeds + 2) + [1] * t_len + [PAD] * n_pad, dtype=np.int64),
+                segment=np.ones(cfg.seq_len + 1, dtype=np.int64), sep_tok=np.asarray([SEP], dtype=np.int64), t_len=t_len)
+
+
+def retrieval_logits(params, batch, cfg, feats=None):
+    """CXRBertForRetrieval.forward (Downstream_task/Retrieval/retrieval.py:29-32): itm(pooled [CLS]) -> [B, 2]."""
+    x = joint_embeddings(params, batch, cfg, feats=feats)
+    ext = extended_mask(batch["attn_masks"])
+    for l in range(cfg.layers):
+        x = encoder_layer(params, l, x, ext, cfg)
+    pooled = torch.tanh(x[:, 0] @ params["enc.pooler.dense.weight"].t() + params["enc.pooler.dense.bias"])
+    return pooled @ params["itm.linear.weight"].t() + params["itm.linear.bias"]
+
+
+def retrieval_scores(params, batch, cfg, feats=None):
+    """test() of full_dset_retrieval.py:499-509: nn.Softmax(dim=1)(logits)[:, 1] — P(image and report match)."""
+    return torch.softmax(retrieval_logits(params, batch, cfg, feats=feats), dim=1)[:, 1]
+
+
+def retrieval_rank_metrics(sims, labels, idx_lst, group, direction="i2t"):
+    """compute_ranks / compute_recall_precision / compute_mrr / evaluate (full_dset_retrieval.py:250-339) restated with
+    explicit Python loops: per group of `group` candidates, order by descending similarity (np.argsort(sim)[::-1], so
+    ties break as numpy's default sort breaks them), rank = position of the first aligned candidate (group size if none)."""
+    sims = np.asarray(sims, dtype=np.float32).reshape(-1, group)
+    labels = np.asarray(labels).reshape(-1, group)
+    idx = np.asarray(idx_lst).reshape(-1, group)
+    ranks, aligned = [], []
+    per_k = {1: ([], []), 5: ([], []), 10: ([], [])}
+    for g in range(sims.shape[0]):
+        order = np.argsort(sims[g])[::-1]
+        rank, at = group, order[-1]
+        for pos, cand in enumerate(order):
+            if labels[g][cand] == 1:
+                rank, at = pos, cand
+                break
+        ranks.append(rank)
+        aligned.append([idx[g][at], rank])
+        ordered = [labels[g][c] for c in order]
+        for k, (rec, prec) in per_k.items():
+            top = np.array(ordered[:k]).sum()
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rec.append(top / np.array(ordered).sum())
+            prec.append(top / k)
+    hits = {"R@%d" % k: sum(r < k for r in ranks) / len(ranks) for k in (1, 5, 10)}
+    recall = {"R@%d" % k: round(np.mean(np.array(per_k[k][0])), 3) for k in (1, 5, 10)}
+    precision = {"R@%d" % k: round(np.mean(np.array(per_k[k][1])), 3) for k in (1, 5, 10)}
+    mrr = np.mean(np.reciprocal(np.array(ranks, dtype=float) + 1))
+    return dict(ranks=ranks, aligned=aligned, hits=hits, recall=recall, precision=precision, mrr=mrr, direction=direction)
