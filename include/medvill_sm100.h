@@ -11,6 +11,8 @@
  *                                   BertPreTrainingHeads :205-248, ImageTextMatching :164-173,
  *                                   losses models/train_origin.py:62-63,118-126, metrics :133-146
  *   mv_adamw_step                   transformers AdamW.step (upstream)  models/train_origin.py:60,129-131
+ *   mv_bert_adam_step               BertAdam.step (fine-tune)           Downstream_task/report_generation_and_vqa/sc/
+ *                                                                       pytorch_pretrained_bert/optimization.py:112-182
  *   mv_comm_* / bucketed all-reduce nn.DataParallel gradient reduction  models/train_origin.py:53-55
  *   mv_attn_mask_dump / classify    CXRDataset mask construction        data/dataset_origin.py:138-176
  *                                   get_extended_attn_mask              models/cxrbert_origin.py:75-85
@@ -31,7 +33,9 @@ extern "C" {
 #define MV_ABI_VERSION 1
 
 enum { MV_PREC_BF16 = 0, MV_PREC_FP32 = 1 };          /* activation / GEMM-operand precision policy */
-enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3 };   /* attention-mask modes */
+enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3,      /* attention-mask modes */
+       MV_MODE_S2S_FT = 4, MV_MODE_BAR_FT = 5 };   /* fine-tune variants: causal block ends at the real text end, padded
+                                                      rows see the prefix only (.../sc/data_loader.py:394-408)          */
 enum {                                                 /* GEMM epilogues (mv_gemm) */
   MV_EPI_NONE = 0, MV_EPI_BIAS = 1, MV_EPI_BIAS_GELU = 2, MV_EPI_BIAS_RESID = 3, MV_EPI_BIAS_TANH = 4,
   MV_EPI_RESID = 5, MV_EPI_DGELU = 6
@@ -83,6 +87,14 @@ typedef struct mv_batch {
   float inv_batch_global;      /* 1 / GLOBAL batch size                                                             */
   uint64_t dropout_seed;       /* per-step seed of the counter-based dropout RNG                                    */
   int32_t train;               /* 1: dropout active (if dropout_p > 0) and backward state is kept                   */
+  /* embedding-layout switches; all 0 = the pre-training model (models/cxrbert_origin.py:112-125).  The report-generation
+   * fine-tune model (Downstream_task/report_generation_and_vqa/sc/pytorch_pretrained_bert/model.py:864-900,223-260)
+   * differs in exactly these three places: */
+  int32_t sep_position;        /* position id of the prefix [SEP]: 0, or A-1 (= N+1) in the fine-tune model        */
+  int32_t prefix_type;         /* token type of [CLS]/regions/[SEP]: 0, or 4 with new_segment_ids                   */
+  int32_t pad_lookup_grad;     /* 1: keep the embedding-lookup gradient of [PAD] (vendored nn.Embedding: no padding_idx) */
+  const float* lab_weights;    /* [n_lab] optional per-row loss weights (fine-tune masked_weights, model.py:998-1005;  */
+                               /* a position masked twice is one row of weight 2); NULL = 1                            */
 } mv_batch;
 
 typedef struct mv_step_stats {
@@ -123,6 +135,13 @@ int mv_backward(mv_handle* h, const mv_batch* b, int32_t allreduce, void* stream
 int mv_zero_grads(mv_handle* h, void* stream);
 int mv_adamw_step(mv_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                   float grad_scale, void* stream);                       /* waits for pending all-reduces; zeroes g */
+/* BertAdam.step of the report-generation fine-tune (Downstream_task/report_generation_and_vqa/sc/pytorch_pretrained_bert/
+ * optimization.py:112-182; parameter groups finetune.py:383-395): per-parameter clip_grad_norm_(p, max_grad_norm), Adam
+ * moments without bias correction, update += weight_decay * p for non-bias / non-LayerNorm tensors, p -= lr * update with
+ * `lr` already scheduled by the caller (warmup_linear, optimization.py:45-48).  Pooler and ITM head are skipped (no
+ * gradient on that path).  Zeroes the gradients it consumed and refreshes the bf16 shadow. */
+int mv_bert_adam_step(mv_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                      void* stream);
 int mv_read_stats(mv_handle* h, mv_step_stats* host_out, void* stream);  /* D2H + stream sync                       */
 int mv_read_stats_async(mv_handle* h, mv_step_stats* pinned_out, void* stream);  /* D2H enqueue only (pinned dst):   */
                                                                          /* lets the trainer log the loss lazily    */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmedvill_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 MV_PREC_BF16, MV_PREC_FP32 = 0, 1
-MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS = 0, 1, 2, 3
+MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS, MODE_S2S_FT, MODE_BAR_FT = 0, 1, 2, 3, 4, 5
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_BIAS_TANH, EPI_RESID, EPI_DGELU = range(7)
 
 
@@ -40,7 +40,9 @@ class mv_batch(C.Structure):
                 ("segment", C.c_void_p), ("is_aligned", C.c_void_p), ("region_idx", C.c_void_p), ("mode", C.c_void_p),
                 ("t_len", C.c_void_p), ("feats", C.c_void_p), ("n_lab", C.c_int32), ("lab_rows", C.c_void_p),
                 ("lab_labels", C.c_void_p), ("inv_n_lab_global", C.c_float), ("inv_batch_global", C.c_float),
-                ("dropout_seed", C.c_uint64), ("train", C.c_int32)]
+                ("dropout_seed", C.c_uint64), ("train", C.c_int32),
+                ("sep_position", C.c_int32), ("prefix_type", C.c_int32), ("pad_lookup_grad", C.c_int32),
+                ("lab_weights", C.c_void_p)]
 
 
 class mv_step_stats(C.Structure):
@@ -73,6 +75,7 @@ SYMBOLS = {
     "mv_backward": (_I, [_P, C.POINTER(mv_batch), _I, _P]),
     "mv_zero_grads": (_I, [_P, _P]),
     "mv_adamw_step": (_I, [_P, _F, _F, _F, _F, _F, _I, _F, _P]),
+    "mv_bert_adam_step": (_I, [_P, _F, _F, _F, _F, _F, _F, _P]),
     "mv_read_stats": (_I, [_P, C.POINTER(mv_step_stats), _P]),
     "mv_read_stats_async": (_I, [_P, _P, _P]),
     "mv_itm_logits": (_I, [_P, _P, _I, _P]),

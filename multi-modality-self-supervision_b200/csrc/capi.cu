@@ -115,6 +115,15 @@ int mv_adamw_step(mv_handle* h, float lr, float beta1, float beta2, float eps, f
   return adamw_step(a, S(stream));
 }
 
+// BertAdam.step of the report-generation fine-tune (optimization.py:112-182): `lr` is the already scheduled rate
+// (lr * warmup_linear(step / t_total, warmup), host side).  Waits for pending all-reduces; zeroes the updated gradients.
+int mv_bert_adam_step(mv_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                      void* stream) {
+  MV_CHECK_HANDLE(h);
+  if (engine_comm_sync(&h->eng, S(stream))) return -2;
+  return h->eng.bert_adam(lr, beta1, beta2, eps, weight_decay, max_grad_norm, S(stream));
+}
+
 int mv_read_stats(mv_handle* h, mv_step_stats* host_out, void* stream) {
   MV_CHECK_HANDLE(h);
   MV_REQUIRE(host_out, "mv_read_stats: null output");

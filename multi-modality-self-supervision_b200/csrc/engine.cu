@@ -299,6 +299,9 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
   ea.gamma = params + lay.emb_ln_g; ea.beta = params + lay.emb_ln_b; ea.eps = cfg.ln_eps;
   ea.proj = proj; ea.emb_sum = emb_sum; ea.out = x[0];
   ea.drop_on = drop; ea.drop_site = SITE_EMB; ea.drop = dc;
+  MV_REQUIRE(b.sep_position >= 0 && b.sep_position < cfg.max_pos && b.prefix_type >= 0 && b.prefix_type < cfg.type_vocab,
+             "mv_batch: sep_position %d / prefix_type %d out of range", b.sep_position, b.prefix_type);
+  ea.sep_pos = b.sep_position; ea.prefix_type = b.prefix_type;
   MV_TRY(embed_ln_fwd(ea, f32, s));
 
   // --- encoder ---
@@ -343,6 +346,7 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     ca.n = n; ca.V = cfg.vocab; ca.ldv = Vpad; ca.logits = logits; ca.labels = reinterpret_cast<const int64_t*>(b.lab_labels);
     ca.dlogits = b.train ? dlogits : nullptr; ca.gscale = b.inv_n_lab_global;
     ca.loss_sum = &stats->mlm_loss_sum; ca.correct = &stats->mlm_correct; ca.row_lse = row_lse; ca.row_argmax = row_argmax;
+    ca.row_weight = b.lab_weights;
     MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
   }
   return 0;
@@ -439,12 +443,59 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
   eb.cls_tok = reinterpret_cast<const int64_t*>(b.cls_tok); eb.sep_tok = reinterpret_cast<const int64_t*>(b.sep_tok);
   eb.input_ids = reinterpret_cast<const int64_t*>(b.input_ids); eb.segment = reinterpret_cast<const int64_t*>(b.segment);
   eb.region_idx = reinterpret_cast<const int64_t*>(b.region_idx);
-  eb.dsum = Q; eb.d_word = grads + lay.word; eb.d_pos = grads + lay.pos; eb.d_type = grads + lay.type; eb.d_proj = dproj; eb.pad_id = 0;
+  eb.dsum = Q; eb.d_word = grads + lay.word; eb.d_pos = grads + lay.pos; eb.d_type = grads + lay.type; eb.d_proj = dproj; eb.pad_id = b.pad_lookup_grad ? -1 : 0;
+  eb.sep_pos = b.sep_position; eb.prefix_type = b.prefix_type;
   MV_TRY(embed_bwd_scatter(eb, f32, s));
   MV_TRY(colsum_add(dproj, H, B * N, H, grads + lay.img_b, f32, s));
   MV_TRY(linear_wgrad(dproj, H, feats_g, B * N, H, cfg.img_hidden, lay.img_w, s));
   MV_TRY(bucket_done(buckets.size() - 1, allreduce, s));
   return 0;
+}
+
+// Parameter tensors the report-generation fine-tune updates (finetune.py:383-395): everything with a gradient, i.e. all
+// but the pooler and the ITM head (BertAdam skips p.grad is None, optimization.py:128-129); q/k/v are separate
+// Parameters in the reference, so each gets its own clipping norm.  decay = name has no 'bias' / 'LayerNorm' part.
+int Engine::bert_adam(float lr, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm, cudaStream_t s) {
+  MV_REQUIRE(params && grads && adam_m && adam_v, "mv_bert_adam_step: arenas (incl. Adam moments) not bound");
+  if (!adam_chunks) {
+    struct T { int64_t off, n; int decay; };
+    std::vector<T> ts;
+    const int64_t H = cfg.hidden, I = cfg.inter, V = cfg.vocab;
+    ts.push_back({lay.word, V * H, 1}); ts.push_back({lay.pos, static_cast<int64_t>(cfg.max_pos) * H, 1});
+    ts.push_back({lay.type, static_cast<int64_t>(cfg.type_vocab) * H, 1});
+    ts.push_back({lay.emb_ln_g, H, 0}); ts.push_back({lay.emb_ln_b, H, 0});
+    ts.push_back({lay.img_w, H * cfg.img_hidden, 1}); ts.push_back({lay.img_b, H, 0});
+    for (int l = 0; l < cfg.layers; ++l) {
+      const int64_t b = lay.layer0 + l * lay.layer_stride;
+      for (int j = 0; j < 3; ++j) ts.push_back({b + lay.l_wqkv + j * H * H, H * H, 1});
+      for (int j = 0; j < 3; ++j) ts.push_back({b + lay.l_bqkv + j * H, H, 0});
+      ts.push_back({b + lay.l_wo, H * H, 1}); ts.push_back({b + lay.l_bo, H, 0});
+      ts.push_back({b + lay.l_ln1_g, H, 0}); ts.push_back({b + lay.l_ln1_b, H, 0});
+      ts.push_back({b + lay.l_w1, I * H, 1}); ts.push_back({b + lay.l_b1, I, 0});
+      ts.push_back({b + lay.l_w2, H * I, 1}); ts.push_back({b + lay.l_b2, H, 0});
+      ts.push_back({b + lay.l_ln2_g, H, 0}); ts.push_back({b + lay.l_ln2_b, H, 0});
+    }
+    ts.push_back({lay.mlm_bias, V, 0}); ts.push_back({lay.mlm_tw, H * H, 1}); ts.push_back({lay.mlm_tb, H, 0});
+    ts.push_back({lay.mlm_ln_g, H, 0}); ts.push_back({lay.mlm_ln_b, H, 0});
+    std::vector<AdamChunk> ch;
+    const int64_t kChunk = 32768;
+    for (size_t t = 0; t < ts.size(); ++t)
+      for (int64_t o = 0; o < ts[t].n; o += kChunk)
+        ch.push_back({static_cast<long>(ts[t].off + o), static_cast<int>(ts[t].n - o < kChunk ? ts[t].n - o : kChunk), static_cast<int>(t), ts[t].decay});
+    void* p = nullptr;
+    MV_TRY(alloc(&p, ch.size() * sizeof(AdamChunk)));
+    adam_chunks = static_cast<AdamChunk*>(p);
+    MV_TRY(alloc(&p, ts.size() * sizeof(float)));
+    adam_sumsq = static_cast<float*>(p);
+    MV_CUDA_CHECK(cudaMemcpy(adam_chunks, ch.data(), ch.size() * sizeof(AdamChunk), cudaMemcpyHostToDevice));
+    n_adam_chunks = static_cast<int>(ch.size());
+    n_adam_tensors = static_cast<int>(ts.size());
+  }
+  BertAdamArgs a;
+  a.p = params; a.g = grads; a.m = adam_m; a.v = adam_v; a.shadow = shadow;
+  a.chunks = adam_chunks; a.n_chunks = n_adam_chunks; a.sumsq = adam_sumsq; a.n_tensors = n_adam_tensors;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_grad_norm = max_grad_norm;
+  return bert_adam_step(a, s);
 }
 
 // prediction_scores for EVERY position (reference semantics, models/cxrbert_origin.py:147): [B*L, ld] fp32

@@ -63,6 +63,10 @@ struct Engine {
   int prof_begin(int tag, double flops, cudaStream_t s);
   int prof_end(cudaStream_t s);
 
+  // BertAdam state (built on first use): chunk table + per-tensor norm scratch, device
+  AdamChunk* adam_chunks = nullptr; float* adam_sumsq = nullptr; int n_adam_chunks = 0, n_adam_tensors = 0;
+  int bert_adam(float lr, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm, cudaStream_t s);
+
   int init(const mv_config& c);
   void destroy();
   int ensure_mlm(int n);

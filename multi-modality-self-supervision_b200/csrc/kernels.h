@@ -21,6 +21,9 @@ struct EmbedArgs {
   void* emb_sum;                     // [B*L, H] pre-LayerNorm sum (saved for backward)
   void* out;                         // [B*L, H] LN + dropout output = encoder input
   int drop_on; uint32_t drop_site; DropoutCfg drop;
+  int sep_pos = 0;                   // position id of the prefix [SEP]: 0 (pre-training, cxrbert_origin.py:119) or A-1
+                                     // (fine-tune model, .../pytorch_pretrained_bert/model.py:886-892)
+  int prefix_type = 0;               // token type of [CLS] / regions / [SEP]: 0, or 4 with new_segment_ids (data_loader.py:344)
 };
 int embed_ln_fwd(const EmbedArgs& a, int f32, cudaStream_t s);
 
@@ -32,6 +35,8 @@ struct EmbedBwdArgs {
   float* d_word; float* d_pos; float* d_type;   // fp32 gradient tables (atomically accumulated)
   void* d_proj;                      // [B*N, H] gradient of the projected image rows (activation dtype)
   int pad_id;                        // upstream nn.Embedding(padding_idx=0): lookup gradient of [PAD] is dropped
+                                     // (-1: keep it — the vendored fine-tune BertEmbeddings has no padding_idx, model.py:228)
+  int sep_pos = 0, prefix_type = 0;  // as EmbedArgs
 };
 int embed_bwd_scatter(const EmbedBwdArgs& a, int f32, cudaStream_t s);
 
@@ -71,6 +76,7 @@ struct CeArgs {
   float* loss_sum;                   // += sum_i (lse_i - logit_i[label_i])
   int* correct;                      // += #(argmax == label)
   float* row_lse; int* row_argmax;   // optional per-row outputs (parity aids)
+  const float* row_weight = nullptr; // optional [n] per-row loss weights (fine-tune masked_weights / multiplicities)
 };
 int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s);
 
@@ -99,6 +105,17 @@ struct AdamArgs {
   int zero_grad;                     // write zeros back to g (fuses optimizer.zero_grad())
 };
 int adamw_step(const AdamArgs& a, cudaStream_t s);
+
+// ---- fine-tune optimizer: BertAdam (.../sc/pytorch_pretrained_bert/optimization.py:112-182): per-tensor gradient-norm
+// clipping, Adam moments without bias correction, decoupled weight decay on non-bias / non-LayerNorm tensors
+struct AdamChunk { long off; int n; int tensor; int decay; };   // a slice of ONE parameter tensor inside the arena
+struct BertAdamArgs {
+  float* p; float* g; float* m; float* v; bf16* shadow;
+  const AdamChunk* chunks; int n_chunks;       // device
+  float* sumsq; int n_tensors;                 // device scratch: squared gradient norm per tensor
+  float lr, beta1, beta2, eps, weight_decay, max_grad_norm;
+};
+int bert_adam_step(const BertAdamArgs& a, cudaStream_t s);
 
 // ---- BatchNorm2d of the frozen ResNet trunk, channels-last [rows, C]: batch statistics + affine (+ residual) (+ ReLU)
 int bn_num_parts(long rows, int C);

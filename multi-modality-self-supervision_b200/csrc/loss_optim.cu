@@ -56,17 +56,19 @@ __global__ void __launch_bounds__(256) mlm_ce_kernel(const CeArgs a) {
   const float total = s_bcast[1];
   const float inv = 1.0f / total;
   const int label = static_cast<int>(a.labels[row]);
+  const float rw = a.row_weight ? a.row_weight[row] : 1.f;       // fine-tune masked_weights (model.py:998-1005)
   if (a.dlogits) {
     T* d = static_cast<T*>(a.dlogits) + static_cast<long>(row) * a.ldv;
+    const float gs = a.gscale * rw;
     for (int c = tid; c < a.ldv; c += 256) {
       float g = 0.f;
-      if (c < a.V) g = (__expf(z[c] - mx) * inv - (c == label ? 1.f : 0.f)) * a.gscale;
+      if (c < a.V) g = (__expf(z[c] - mx) * inv - (c == label ? 1.f : 0.f)) * gs;
       d[c] = from_f32<T>(g);
     }
   }
   if (tid == 0) {
     const float lse = mx + logf(total);
-    atomicAdd(a.loss_sum, lse - z[label]);
+    atomicAdd(a.loss_sum, (lse - z[label]) * rw);
     if (s_arg == label) atomicAdd(a.correct, 1);
     if (a.row_lse) a.row_lse[row] = lse;
     if (a.row_argmax) a.row_argmax[row] = s_arg;
@@ -155,6 +157,48 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamArgs a, float step
   }
 }
 
+// ---- BertAdam (fine-tune optimizer, Downstream_task/report_generation_and_vqa/sc/pytorch_pretrained_bert/optimization.py:112-182)
+// The arena is cut into chunks that never straddle a parameter tensor; pass 1 accumulates each tensor's squared gradient
+// norm, pass 2 applies clip_grad_norm_(p, max_norm) PER TENSOR (:146-147), Adam moments WITHOUT bias correction (:151-153,
+// :178-181), decoupled weight decay added to the update (:162-163) and the scheduled learning rate (:165-172).
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ g, const AdamChunk* __restrict__ chunks,
+                                                         float* __restrict__ sumsq) {
+  const AdamChunk c = chunks[blockIdx.x];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < c.n; i += 256) { const float x = g[c.off + i]; acc += x * x; }
+  acc = warp_sum(acc);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(sumsq + c.tensor, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) bert_adam_kernel(const BertAdamArgs a) {
+  const AdamChunk c = a.chunks[blockIdx.x];
+  float coef = 1.f;
+  if (a.max_grad_norm > 0.f) {
+    coef = a.max_grad_norm / (sqrtf(a.sumsq[c.tensor]) + 1e-6f);      // torch.nn.utils.clip_grad_norm_
+    coef = fminf(coef, 1.f);
+  }
+  const float wd = c.decay ? a.weight_decay : 0.f;
+  for (int i = threadIdx.x; i < c.n; i += 256) {
+    const long j = c.off + i;
+    const float g = a.g[j] * coef;
+    const float m = a.m[j] * a.beta1 + (1.f - a.beta1) * g;
+    const float v = a.v[j] * a.beta2 + (1.f - a.beta2) * g * g;
+    float p = a.p[j];
+    const float update = m / (sqrtf(v) + a.eps) + wd * p;
+    p -= a.lr * update;
+    a.p[j] = p; a.m[j] = m; a.v[j] = v;
+    a.g[j] = 0.f;
+    if (a.shadow) a.shadow[j] = __float2bfloat16_rn(p);
+  }
+}
+
 // Retrieval score of a pair = softmax(itm_logits)[1] (Downstream_task/Retrieval/full_dset_retrieval.py:506-507), fp32
 __global__ void __launch_bounds__(256) itm_match_prob_kernel(const float* __restrict__ logits, float* __restrict__ out, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,6 +210,16 @@ __global__ void __launch_bounds__(256) itm_match_prob_kernel(const float* __rest
 }
 
 }  // namespace
+
+int bert_adam_step(const BertAdamArgs& a, cudaStream_t s) {
+  MV_REQUIRE(a.p && a.g && a.m && a.v && a.chunks && a.sumsq && a.n_chunks > 0 && a.n_tensors > 0, "bert_adam: null argument");
+  MV_CUDA_CHECK(cudaMemsetAsync(a.sumsq, 0, sizeof(float) * a.n_tensors, s));
+  grad_sumsq_kernel<<<a.n_chunks, 256, 0, s>>>(a.g, a.chunks, a.sumsq);
+  MV_LAUNCH_CHECK();
+  bert_adam_kernel<<<a.n_chunks, 256, 0, s>>>(a);
+  MV_LAUNCH_CHECK();
+  return 0;
+}
 
 int itm_match_prob(const float* logits, float* out, int B, cudaStream_t s) {
   if (B <= 0) return 0;

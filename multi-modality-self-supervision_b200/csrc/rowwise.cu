@@ -78,12 +78,16 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const EmbedArgs a) {
   const T* prow = nullptr;
   int pos_id = 0, type_id = 0;
   if (s == 0) {
-    wrow = a.word + a.cls_tok[b] * H;                                         // [CLS]: position 0, type 0
+    wrow = a.word + a.cls_tok[b] * H;                                         // [CLS]: position 0, prefix type
+    type_id = a.prefix_type;
   } else if (s <= a.N) {
     prow = static_cast<const T*>(a.proj) + (static_cast<long>(b) * a.N + (s - 1)) * H;
     pos_id = static_cast<int>(a.region_idx[s - 1]);                           // grid index as position id
+    type_id = a.prefix_type;
   } else if (s == a.N + 1) {
-    wrow = a.word + a.sep_tok[b] * H;                                         // [SEP]: position restarts at 0
+    wrow = a.word + a.sep_tok[b] * H;                                         // [SEP]: position restarts at 0 (pre-training)
+    pos_id = a.sep_pos;                                                       // or continues at A-1 (fine-tune model)
+    type_id = a.prefix_type;
   } else {
     const int i = s - a.A;
     wrow = a.word + a.input_ids[static_cast<long>(b) * a.T + i] * H;
@@ -251,9 +255,9 @@ __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const EmbedBwdAr
   long word_id = -1;
   int pos_id = 0, type_id = 0;
   T* proj_row = nullptr;
-  if (s == 0) word_id = a.cls_tok[b];
-  else if (s <= a.N) { proj_row = static_cast<T*>(a.d_proj) + (static_cast<long>(b) * a.N + (s - 1)) * H; pos_id = static_cast<int>(a.region_idx[s - 1]); }
-  else if (s == a.N + 1) word_id = a.sep_tok[b];
+  if (s == 0) { word_id = a.cls_tok[b]; type_id = a.prefix_type; }
+  else if (s <= a.N) { proj_row = static_cast<T*>(a.d_proj) + (static_cast<long>(b) * a.N + (s - 1)) * H; pos_id = static_cast<int>(a.region_idx[s - 1]); type_id = a.prefix_type; }
+  else if (s == a.N + 1) { word_id = a.sep_tok[b]; pos_id = a.sep_pos; type_id = a.prefix_type; }
   else {
     const int i = s - a.A;
     word_id = a.input_ids[static_cast<long>(b) * a.T + i];
@@ -382,16 +386,18 @@ __global__ void __launch_bounds__(256) mask_classify_kernel(const int64_t* mask,
     if (bad) atomicAdd(mismatches, bad);
   } else {
     const int64_t* m = mask + static_cast<long>(b) * L * L;
-    __shared__ int s_cnt_first;
-    if (threadIdx.x == 0) s_cnt_first = 0;
+    __shared__ int s_cnt_first, s_cnt_diag;
+    if (threadIdx.x == 0) { s_cnt_first = 0; s_cnt_diag = 0; }
     __syncthreads();
-    int c = 0, c0 = 0;
+    int c = 0, c0 = 0, cd = 0;
     for (int k = threadIdx.x; k < L; k += blockDim.x) {
       c += m[static_cast<long>(L - 1) * L + k] != 0;   // last text row
       c0 += m[static_cast<long>(A) * L + k] != 0;      // first text row
+      if (k >= A) cd += m[static_cast<long>(k) * L + k] != 0;   // text rows that see themselves
     }
     atomicAdd(&s_cnt, c);
     atomicAdd(&s_cnt_first, c0);
+    atomicAdd(&s_cnt_diag, cd);
     __syncthreads();
     if (threadIdx.x == 0) {
       const bool txt_sees_img = m[static_cast<long>(A) * L + 0] != 0;
@@ -403,8 +409,15 @@ __global__ void __launch_bounds__(256) mask_classify_kernel(const int64_t* mask,
       else if (!img_sees_txt) md = MODE_S2S;
       else if (!rows_identical) md = MODE_BAR;
       else md = MODE_BIDIR;
+      int tl = md == MODE_BIDIR ? s_cnt - A : L - A;
+      // fine-tune variants (data_loader.py:394-408): padded text rows see the prefix only and not themselves, so the
+      // diagonal counts the real text rows; without pads they coincide with the pre-training masks
+      if ((md == MODE_S2S || md == MODE_BAR) && s_cnt_diag < L - A && s_cnt == A) {
+        md = md == MODE_S2S ? MODE_S2S_FT : MODE_BAR_FT;
+        tl = s_cnt_diag;
+      }
       s_mode = md;
-      s_tlen = md == MODE_BIDIR ? s_cnt - A : L - A;
+      s_tlen = tl;
     }
     __syncthreads();
     const int md = s_mode, tl = s_tlen;

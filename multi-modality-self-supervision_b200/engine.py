@@ -113,7 +113,8 @@ class Batch:
     """One micro-batch resident on the device, plus the mv_batch struct pointing into it."""
 
     def __init__(self, engine, cls_tok, input_ids, segment, sep_tok, mode, t_len, region_idx, feats, txt_labels=None,
-                 is_aligned=None, lab_rows=None, lab_labels=None, n_lab_global=None, batch_global=None, seed=0, train=True):
+                 is_aligned=None, lab_rows=None, lab_labels=None, n_lab_global=None, batch_global=None, seed=0, train=True,
+                 sep_position=0, prefix_type=0, pad_lookup_grad=False, lab_weights=None):
         d = engine.dims
         dev = engine.device
         i64 = lambda t: None if t is None else torch.as_tensor(t).to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
@@ -144,6 +145,9 @@ class Batch:
                 lab_rows, lab_labels = torch.from_numpy(rows), torch.from_numpy(flat[rows])
         self.lab_rows, self.lab_labels = i64(lab_rows), i64(lab_labels)
         self.n_lab = 0 if self.lab_rows is None else int(self.lab_rows.numel())
+        self.lab_weights = None if lab_weights is None else torch.as_tensor(lab_weights).to(device=dev, dtype=torch.float32).contiguous()
+        if self.lab_weights is not None and self.lab_weights.numel() != self.n_lab:
+            raise MedvillError("lab_weights must hold one weight per labelled row")
         n_glob = self.n_lab if n_lab_global is None else n_lab_global
         b_glob = self.B if batch_global is None else batch_global
         self.c = _lib.mv_batch(
@@ -152,7 +156,25 @@ class Batch:
             mode=ptr(self.mode), t_len=ptr(self.t_len), feats=ptr(self.feats), n_lab=self.n_lab,
             lab_rows=ptr(self.lab_rows) if self.n_lab else None, lab_labels=ptr(self.lab_labels) if self.n_lab else None,
             inv_n_lab_global=1.0 / max(1, n_glob), inv_batch_global=1.0 / max(1, b_glob), dropout_seed=int(seed) & (2 ** 64 - 1),
-            train=1 if train else 0)
+            train=1 if train else 0, sep_position=int(sep_position), prefix_type=int(prefix_type),
+            pad_lookup_grad=1 if pad_lookup_grad else 0, lab_weights=ptr(self.lab_weights))
+
+
+_LIVE_ENGINES = []      # weak references; lets optimizers locate the engine that owns a parameter view
+
+
+def find_engine(tensor):
+    """The live engine whose parameter arena contains `tensor` (an nn.Parameter view), or None."""
+    ptr_ = tensor.data_ptr()
+    for ref in list(_LIVE_ENGINES):
+        eng = ref()
+        if eng is None or not getattr(eng, "_h", None) or not eng._h.value:
+            _LIVE_ENGINES.remove(ref)
+            continue
+        lo = eng.params.data_ptr()
+        if lo <= ptr_ < lo + eng.params.numel() * 4:
+            return eng
+    return None
 
 
 class PretrainEngine:
@@ -182,6 +204,9 @@ class PretrainEngine:
               "mv_bind_arenas")
         self.step_count = 0
         self.world, self.rank = 1, 0
+        import weakref
+
+        _LIVE_ENGINES.append(weakref.ref(self))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -233,6 +258,12 @@ class PretrainEngine:
         self.step_count += 1
         check(lib().mv_adamw_step(self._h, lr, betas[0], betas[1], eps, weight_decay, self.step_count, grad_scale,
                                   stream_ptr(self.device)), "mv_adamw_step")
+
+    def bert_adam_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01, max_grad_norm=1.0):
+        """BertAdam.step (fine-tune; .../sc/pytorch_pretrained_bert/optimization.py:112-182); `lr` is the scheduled rate."""
+        self.step_count += 1
+        check(lib().mv_bert_adam_step(self._h, lr, betas[0], betas[1], eps, weight_decay, max_grad_norm, stream_ptr(self.device)),
+              "mv_bert_adam_step")
 
     def read_stats(self):
         st = _lib.mv_step_stats()

@@ -25,6 +25,10 @@ MODE_BIDIR = 0      # full bidirectional / attn_1d   : k < A + t_len
 MODE_S2S = 1        # Seq2Seq                        : k < A or (q >= A and A <= k <= q)
 MODE_BAR = 2        # Bidirectional Auto-Regressive  : q < A or k < A or k <= q
 MODE_NONCROSS = 3   # Non-cross ("disturbing_mask")  : (q < A) == (k < A)
+# report-generation fine-tune variants (Downstream_task/report_generation_and_vqa/sc/data_loader.py:394-408): the causal
+# block stops at the real text end and padded rows see the prefix only
+MODE_S2S_FT = 4     # k < A or (A <= q < A + t_len and k <= q)
+MODE_BAR_FT = 5     # q < A or k < A or (q < A + t_len and k <= q)
 
 PAD, UNK, CLS, SEP, MASK = 0, 100, 101, 102, 103
 
@@ -82,6 +86,10 @@ def mask_allowed(mode, q, k, A, t_len):
         return (q < A) | (k < A) | (k <= q)
     if mode == MODE_NONCROSS:
         return (q < A) == (k < A)
+    if mode == MODE_S2S_FT:
+        return ((k < A) | ((q >= A) & (q < A + t_len) & (k <= q))) & (q >= 0)
+    if mode == MODE_BAR_FT:
+        return (q < A) | (k < A) | ((q < A + t_len) & (k <= q))
     raise ValueError("unknown mask mode %r" % (mode,))
 
 
@@ -616,3 +624,211 @@ def retrieval_rank_metrics(sims, labels, idx_lst, group, direction="i2t"):
     precision = {"R@%d" % k: round(np.mean(np.array(per_k[k][1])), 3) for k in (1, 5, 10)}
     mrr = np.mean(np.reciprocal(np.array(ranks, dtype=float) + 1))
     return dict(ranks=ranks, aligned=aligned, hits=hits, recall=recall, precision=precision, mrr=mrr, direction=direction)
+
+
+# =====================================================================================================
+# Report-generation fine-tune step (BASELINE.json configs[4]).  Reference files are under
+# Downstream_task/report_generation_and_vqa/sc/ : data_loader.py, pytorch_pretrained_bert/{model.py, optimization.py}, finetune.py
+# =====================================================================================================
+def finetune_cfg(**kw):
+    """BERT-base fine-tune shapes: all 256 grid regions (pixel_full_sampling, model.py:36-54), max_len_b = 253 -> L = 512
+    (finetune.py:68-76), LayerNorm eps 1e-5 everywhere (model.py:238,327,367)."""
+    base = dict(num_image_embeds=256, seq_len=253, ln_eps=1e-5)
+    base.update(kw)
+    return Cfg(**base)
+
+
+TINY_FT = dict(TINY, num_image_embeds=16, ln_eps=1e-5)       # 128x128 image -> 4x4 grid, every region used
+
+
+def truncate_tokens_pair(tokens_a, tokens_b, max_len, rng, max_len_b=0, always_truncate_tail=False):
+    """data_loader.py:24-59 with trunc_seg='b' (finetune.py:158): drop from the report until both fit; each removal
+    draws rand() to pick head or tail unless always_truncate_tail."""
+    while len(tokens_a) + len(tokens_b) > max_len:
+        trunc = tokens_b          # max_len_a = 0, so either the max_len_b rule (:33-35) or trunc_seg == 'b' (:36-43) picks B
+        if (not always_truncate_tail) and rng.random() < 0.5:
+            del trunc[0]
+        else:
+            trunc.pop()
+
+
+def preprocess4seq2seq(tokens_b, rng, cfg, mode="s2s", bar=False, max_pred=10, mask_prob=0.15, new_segment_ids=False,
+                       always_truncate_tail=False):
+    """Preprocess4Seq2seq.__call__ for tasks == 'report_generation' (data_loader.py:330-452) on token IDS.
+    `rng` is a random.Random; the reference uses the module-level generator with the same call order:
+    truncation draws, shuffle(cand_pos), one random() for the 50 % forced [SEP] mask.  Returns numpy int64 arrays."""
+    N = cfg.num_image_embeds
+    A = N + 2
+    max_len = cfg.L
+    tokens_a = [UNK] * N                                                    # :333
+    tokens_b = list(tokens_b)
+    truncate_tokens_pair(tokens_a, tokens_b, N + cfg.seq_len, rng, max_len_b=cfg.seq_len,
+                         always_truncate_tail=always_truncate_tail)          # :336-338
+    tokens = [CLS] + tokens_a + [SEP] + tokens_b + [SEP]                    # :340
+    if new_segment_ids and mode == "s2s":                                   # :342-348
+        segment_ids = [4] * A + [5] * (len(tokens_b) + 1)
+    else:
+        segment_ids = [0] * A + [1] * (len(tokens_b) + 1)
+    n_pred = min(max_pred, max(1, int(round(len(tokens_b) * mask_prob))))   # :352-353
+    cand_pos = [i for i, tk in enumerate(tokens) if i >= A and tk != CLS]   # :360-364
+    rng.shuffle(cand_pos)                                                   # :367
+    if rng.random() > 0.5:                                                  # :368-372  force-mask the final [SEP]
+        masked_pos = cand_pos[:n_pred - 1]
+        masked_pos.append(len(tokens) - 1)
+    else:
+        masked_pos = cand_pos[:n_pred]
+    masked_ids = [tokens[p] for p in masked_pos]                            # :374
+    for p in masked_pos:
+        tokens[p] = MASK                                                    # :376-377
+    masked_weights = [1] * len(masked_ids)                                  # :383
+    n_pad = max_len - len(tokens)                                           # :390-392
+    input_ids = tokens + [PAD] * n_pad
+    segment_ids = segment_ids + [0] * n_pad
+    t_len = len(tokens_b) + 1
+    if bar:                                                                 # :398-402
+        md = MODE_BAR_FT
+    elif mode == "s2s":                                                     # :405-408
+        md = MODE_S2S_FT
+    else:                                                                   # :410-412 ('bi': 1-D mask expanded)
+        md = MODE_BIDIR
+    # step-by-step construction (kept independent of the closed form, asserted equal below)
+    mask = np.zeros((max_len, max_len), dtype=np.int64)
+    st, end = A, A + t_len
+    tril = np.tril(np.ones((max_len, max_len), dtype=np.int64))
+    if bar:
+        mask[:, :A] = 1
+        mask[:A, :] = 1
+        mask[st:end, st:end] = tril[:end - st, :end - st]
+    elif mode == "s2s":
+        mask[:, :A] = 1
+        mask[st:end, st:end] = tril[:end - st, :end - st]
+    else:
+        mask[:] = np.asarray([1] * len(tokens) + [0] * n_pad, dtype=np.int64)[None, :]
+    assert np.array_equal(mask, attention_mask(md, A, max_len, t_len))
+    n_real = len(masked_ids)                                                # :415-419 (pad to max_pred; n_pred may be < len)
+    if max_pred > n_pred:
+        pad = max_pred - n_pred
+        masked_ids = masked_ids + [0] * pad
+        masked_pos = masked_pos + [0] * pad
+        masked_weights = masked_weights + [0] * pad
+    i64 = lambda v: np.asarray(v, dtype=np.int64)
+    return dict(input_ids=i64(input_ids), segment_ids=i64(segment_ids), input_mask=mask, masked_ids=i64(masked_ids),
+                masked_pos=i64(masked_pos), masked_weights=i64(masked_weights), mode=md, t_len=t_len, n_real=n_real)
+
+
+def finetune_batch(cfg, B, seed, mode="s2s", bar=False, new_segment_ids=False, min_len=1):
+    """Seeded synthetic fine-tune batch: report ids U[999, vocab), length U{min_len..seq_len+6} (some get truncated)."""
+    import random
+
+    rng = random.Random(seed)
+    nrng = np.random.RandomState(seed)
+    lo = min(999, cfg.vocab // 2)
+    samples = []
+    for _ in range(B):
+        t = int(nrng.randint(min_len, cfg.seq_len + 7))
+        samples.append(preprocess4seq2seq(nrng.randint(lo, cfg.vocab, size=t).tolist(), rng, cfg, mode=mode, bar=bar,
+                                          new_segment_ids=new_segment_ids))
+    g = torch.Generator().manual_seed(seed)
+    st = lambda k: np.stack([s[k] for s in samples])
+    return dict(input_ids=st("input_ids"), segment_ids=st("segment_ids"), input_mask=st("input_mask"), masked_ids=st("masked_ids"),
+                masked_pos=st("masked_pos"), masked_weights=st("masked_weights"),
+                mode=np.asarray([s["mode"] for s in samples], dtype=np.uint8), t_len=np.asarray([s["t_len"] for s in samples], dtype=np.int32),
+                image=torch.randn(B, 3, cfg.img_size, cfg.img_size, generator=g))
+
+
+def finetune_embeddings(params, batch, cfg, feats=None):
+    """BertForPreTrainingLossMask.forward up to the encoder input (model.py:970-975; ImageBertEmbeddings :864-900;
+    vendored BertEmbeddings :223-260).  Differences from pre-training: every grid region is used (vis_pe = arange),
+    the prefix [SEP] keeps position A-1, prefix token types come from segment_ids, no padding_idx on the word table."""
+    H, N = cfg.hidden, cfg.num_image_embeds
+    A = N + 2
+    W = params["enc.txt_embeddings.word_embeddings.weight"]
+    P = params["enc.txt_embeddings.position_embeddings.weight"]
+    Ty = params["enc.txt_embeddings.token_type_embeddings.weight"]
+    lw, lb = params["enc.txt_embeddings.LayerNorm.weight"], params["enc.txt_embeddings.LayerNorm.bias"]
+    ids, seg = torch.as_tensor(batch["input_ids"]), torch.as_tensor(batch["segment_ids"])
+    if feats is None:
+        fmap = resnet50_trunk(params, batch["image"])                          # model.py:49 (train-mode BN: model.train())
+        feats = torch.flatten(fmap, start_dim=2).transpose(1, 2).contiguous()    # :50-51
+    img = feats @ params["enc.img_embeddings.img_embeddings.weight"].t() + params["enc.img_embeddings.img_embeddings.bias"]
+    tok = torch.cat([W[ids[:, :1]], img, W[ids[:, A - 1:A]]], dim=1)           # :879-886
+    pos = torch.cat([P[:1], P[torch.arange(N)], P[N + 1:A]], dim=0)[None]      # :888-892
+    img_out = tf_layer_norm(tok + pos + Ty[seg[:, :A]], lw, lb, cfg.ln_eps)    # :894-898
+    T = ids.shape[1] - A
+    txt_out = tf_layer_norm(W[ids[:, A:]] + P[:T][None] + Ty[seg[:, A:]], lw, lb, cfg.ln_eps)   # :240-258
+    return torch.cat([img_out, txt_out], 1)
+
+
+def finetune_loss(params, batch, cfg, feats=None, keep=None):
+    """masked-LM loss of the fine-tune step (model.py:968-1054, drop_worst_ratio = 0 — finetune.py:179 default):
+    heads on the <= max_pred gathered rows, CE(reduction='none') * weights, sum / (sum(weights) + 1e-5)."""
+    x = finetune_embeddings(params, batch, cfg, feats=feats)
+    ext = extended_mask(batch["input_mask"])
+    for l in range(cfg.layers):
+        x = encoder_layer(params, l, x, ext, cfg)
+    pos = torch.as_tensor(batch["masked_pos"])
+    rows = torch.gather(x, 1, pos[:, :, None].expand(-1, -1, x.shape[-1]))     # :992-993, 1040
+    t = rows @ params["mlm.predictions.transform.dense.weight"].t() + params["mlm.predictions.transform.dense.bias"]
+    t = tf_layer_norm(gelu(t), params["mlm.predictions.transform.LayerNorm.weight"],
+                      params["mlm.predictions.transform.LayerNorm.bias"], cfg.head_ln_eps)
+    logits = t @ params["enc.txt_embeddings.word_embeddings.weight"].t() + params["mlm.predictions.bias"]
+    ce = F.cross_entropy(logits.transpose(1, 2).float(), torch.as_tensor(batch["masked_ids"]), reduction="none")   # :1047-1048
+    w = torch.as_tensor(batch["masked_weights"]).to(ce.dtype)
+    per_sample = (ce * w).sum(-1)                                              # :1004-1005
+    kept, idx = torch.topk(per_sample, per_sample.shape[0], largest=False)     # :1007 (ratio 0: every sample kept)
+    denom = w.sum(-1)[idx].sum() + 1e-5                                        # :1009
+    if keep is not None:
+        keep["seq"], keep["logits"], keep["ce"] = x, logits, ce
+    return (kept / denom).sum()                                                # :1010
+
+
+FT_NO_GRAD = ("enc.pooler.dense.weight", "enc.pooler.dense.bias", "itm.linear.weight", "itm.linear.bias")
+
+
+def finetune_trainable_names(cfg):
+    """parameters that receive a gradient in the fine-tune step: the pooled output feeds nothing (model.py:1041-1042
+    discards seq_relationship), so the pooler has grad None and BertAdam skips it; there is no ITM head."""
+    return [n for n in trainable_names(cfg) if n not in FT_NO_GRAD]
+
+
+def finetune_loss_and_grads(params, batch, cfg, feats=None, keep=None):
+    names = finetune_trainable_names(cfg)
+    leaf = dict(params)
+    for n in names:
+        leaf[n] = params[n].detach().clone().requires_grad_(True)
+    loss = finetune_loss(leaf, batch, cfg, feats=feats, keep=keep)
+    loss.backward()
+    grads = {n: (leaf[n].grad if leaf[n].grad is not None else torch.zeros_like(leaf[n])) for n in names}
+    return dict(loss=loss.item(), grads=grads)
+
+
+def warmup_linear(x, warmup=0.002):
+    """optimization.py:45-48"""
+    if x < warmup:
+        return x / warmup
+    return max((x - 1.0) / (warmup - 1.0), 0)
+
+
+def bert_adam_decays(name):
+    """finetune.py:383-389: no weight decay for names containing 'bias', 'LayerNorm.bias', 'LayerNorm.weight'"""
+    return not any(nd in name for nd in ("bias", "LayerNorm.bias", "LayerNorm.weight"))
+
+
+def bert_adam_step(params, grads, state, lr, step, t_total=-1, warmup=-1, b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01,
+                   max_grad_norm=1.0):
+    """BertAdam.step (optimization.py:112-182): per-parameter clip_grad_norm_, no bias correction, decoupled decay
+    added to the update, warmup_linear schedule evaluated at the parameter's own step counter (`step`, 0-based)."""
+    lr_sched = lr * warmup_linear(step / t_total, warmup) if t_total != -1 else lr
+    out = {}
+    for n, g in grads.items():
+        st = state.setdefault(n, dict(m=torch.zeros_like(params[n]), v=torch.zeros_like(params[n])))
+        if max_grad_norm > 0:
+            coef = max_grad_norm / (float(torch.linalg.vector_norm(g.float(), 2)) + 1e-6)
+            g = g * min(coef, 1.0)
+        st["m"].mul_(b1).add_(g, alpha=1 - b1)
+        st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+        update = st["m"] / (st["v"].sqrt() + e)
+        if weight_decay > 0.0 and bert_adam_decays(n):
+            update = update + weight_decay * params[n]
+        out[n] = params[n] - lr_sched * update
+    return out
