@@ -55,6 +55,10 @@ def test_score_matrix_matches_reference_fixture(precision, tol):
             want = torch.flatten(orc.resnet50_trunk(params, images, bn_train=False), start_dim=2).transpose(1, 2).contiguous()
         assert float((feats.float().cpu() - want).norm() / want.norm()) < 5e-2
         feats = want.to("cuda:0", torch.bfloat16)
+        # retrieval_params scales the ITM weight x60 to spread the scores: bf16 rounding of the 128-wide pooled vector
+        # (2^-9 relative) is amplified by the same factor, ~0.04 on logits of magnitude 1.3.  BERT-base (768-wide pooled,
+        # test_bert_base_pairs_match_oracle) holds the plain 1e-2.
+        tol = 4e-2
     sims = scorer.score_matrix(feats, torch.from_numpy(g["input_ids"]), torch.from_numpy(g["t_len"]), region_idx=g["region_idx"])
     got = sims.cpu().numpy()
     assert got.shape == g["scores"].shape
