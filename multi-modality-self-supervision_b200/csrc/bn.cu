@@ -46,74 +46,98 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
   n = nt;
 }
 
-// 256 threads; thread t owns channels [8*(t % cpr), +8) and rows (t / cpr) + k * rpi of the CTA's row slab, where
-// cpr = C/8 threads per row and rpi = 256 / cpr rows per iteration (C >= 2048 handled by gridDim.y channel blocks).
+// Statistics pass.  grid = (row parts, 64-channel blocks).  256 threads = 32 row lanes x 8 chunk threads: a warp reads four
+// 128-byte row segments per iteration (full sectors), a CTA walks its row slab 32 rows at a time.  Every thread keeps
+// fp32 sum / sum-of-squares of 8 channels, converts to (n, mean, M2) and the 32 row lanes are merged with Chan updates
+// through shared memory.  Partials: [channel block][part][64 channels][3] — per layer at most 148*4*64*3 floats, so the
+// finalize pass reads a few hundred KB instead of the nparts*C*3 table the first version wrote (14.5 MB at C = 2048).
+constexpr int kBnCh = 64;        // channels per CTA
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long rows, int C, long rows_per_cta,
-                                                       float* __restrict__ partial /* [gridDim.x][C][3] */) {
-  __shared__ float red[256][3 * 8 + 1];
-  const int cpr = min(C >> 3, 256);
-  const int rpi = 256 / cpr;
-  const int cch = (threadIdx.x % cpr) + blockIdx.y * 256;   // 8-channel chunk index
-  const int roff = threadIdx.x / cpr;
+                                                       float* __restrict__ partial) {
+  __shared__ float red[32][kBnCh][3];      // 24 KB
+  const int ct = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * kBnCh + ct * 8;
   const long r0 = static_cast<long>(blockIdx.x) * rows_per_cta;
   const long r1 = min(rows, r0 + rows_per_cta);
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float cnt = 0.f;
-  if (roff < rpi && cch * 8 < C) {
-    for (long r = r0 + roff; r < r1; r += rpi) {
-      float v[8];
-      ld8<T>(x + r * C + cch * 8, v);
+  if (c0 < C) {
+    long r = r0 + rl;
+    for (; r + 96 < r1; r += 128) {         // four independent 16-byte loads in flight per thread
+      float v[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] += v[j] * v[j]; }
+      for (int u = 0; u < 4; ++u) ld8<T>(x + (r + 32 * u) * C + c0, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += v[u][j]; q[j] = fmaf(v[u][j], v[u][j], q[j]); }
+      cnt += 4.f;
+    }
+    for (; r < r1; r += 32) {
+      float v[8];
+      ld8<T>(x + r * C + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
       cnt += 1.f;
     }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float mean = cnt > 0.f ? s[j] / cnt : 0.f;
-    red[threadIdx.x][3 * j] = cnt;
-    red[threadIdx.x][3 * j + 1] = mean;
-    red[threadIdx.x][3 * j + 2] = cnt > 0.f ? fmaxf(q[j] - s[j] * mean, 0.f) : 0.f;
+    red[rl][ct * 8 + j][0] = cnt;
+    red[rl][ct * 8 + j][1] = mean;
+    red[rl][ct * 8 + j][2] = cnt > 0.f ? fmaxf(q[j] - s[j] * mean, 0.f) : 0.f;
   }
   __syncthreads();
-  // threads [0, cpr) merge the rpi row-lanes of their channel chunk
-  if (threadIdx.x < cpr && cch * 8 < C) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float n = 0.f, mean = 0.f, m2 = 0.f;
-      for (int k = 0; k < rpi; ++k) {
-        const float* e = &red[threadIdx.x + k * cpr][3 * j];
-        chan_merge(n, mean, m2, e[0], e[1], e[2]);
-      }
-      float* o = partial + (static_cast<long>(blockIdx.x) * C + cch * 8 + j) * 3;
-      o[0] = n; o[1] = mean; o[2] = m2;
-    }
-  }
-}
-
-// one WARP per channel: lanes merge strided subsets of the per-CTA partials, then a shuffle tree of Chan updates;
-// lane 0 produces scale/shift and updates the running statistics
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float* running_mean, float* running_var, float momentum, float eps,
-                                                          int update_running, float* __restrict__ scale_shift /* [2][C] */) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= C) return;
+  // 4 threads per channel merge 8 row lanes each, then a 2-step shuffle merge
+  const int ch = threadIdx.x >> 2, sub = threadIdx.x & 3;
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int p = lane; p < nparts; p += 32) {
-    const float* e = partial + (static_cast<long>(p) * C + c) * 3;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* e = red[sub * 8 + k][ch];
     chan_merge(n, mean, m2, e[0], e[1], e[2]);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float nb = __shfl_xor_sync(0xffffffffu, n, o);
-    const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
-    const float qb = __shfl_xor_sync(0xffffffffu, m2, o);
+  for (int o = 1; o < 4; o <<= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o), qb = __shfl_xor_sync(0xffffffffu, m2, o);
     chan_merge(n, mean, m2, nb, mb, qb);
   }
-  if (lane != 0) return;
+  if (sub == 0 && blockIdx.y * kBnCh + ch < C) {
+    float* o = partial + ((static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * kBnCh + ch) * 3;
+    o[0] = n; o[1] = mean; o[2] = m2;
+  }
+}
+
+// One CTA per 64-channel block, 1024 threads = 64 channels x 16 part lanes: coalesced reads of the partial table, Chan
+// merges in registers, a 16-way merge through shared memory; thread (channel, 0) produces scale / shift and updates the
+// running statistics (momentum, unbiased variance: PyTorch semantics).
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float* running_mean, float* running_var, float momentum, float eps,
+                                                           int update_running, float* __restrict__ scale_shift /* [2][C] */) {
+  __shared__ float red[16][kBnCh][3];
+  const int ch = threadIdx.x & (kBnCh - 1), pl = threadIdx.x >> 6;
+  const int c = blockIdx.x * kBnCh + ch;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  const float* base = partial + static_cast<long>(blockIdx.x) * nparts * kBnCh * 3;
+  for (int p = pl; p < nparts; p += 16 * 8) {        // 8 partials (24 loads) in flight per thread, then 8 serial merges
+    float e[8][3];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int pp = p + 16 * u;
+      const float* src = base + (static_cast<long>(pp < nparts ? pp : p) * kBnCh + ch) * 3;
+      e[u][0] = pp < nparts ? src[0] : 0.f; e[u][1] = src[1]; e[u][2] = src[2];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) chan_merge(n, mean, m2, e[u][0], e[u][1], e[u][2]);
+  }
+  red[pl][ch][0] = n; red[pl][ch][1] = mean; red[pl][ch][2] = m2;
+  __syncthreads();
+  if (pl != 0 || c >= C) return;
+  n = 0.f; mean = 0.f; m2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) chan_merge(n, mean, m2, red[k][ch][0], red[k][ch][1], red[k][ch][2]);
   const float var = m2 / n;                      // biased: what normalisation uses
   const float invstd = rsqrtf(var + eps);
   const float sc = gamma[c] * invstd;
@@ -162,16 +186,35 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
 
 }  // namespace
 
-// workspace: [nparts * C * 3] partials followed by [2 * C] scale/shift; nparts = bn_num_parts(rows)
+// workspace: [channel blocks][nparts][64][3] partials followed by [2 * C] scale/shift; nparts = bn_num_parts(rows, C)
 int bn_num_parts(long rows, int C) {
   const int sms = device_sm_count();
-  const int cpr = (C >> 3) < 256 ? (C >> 3) : 256;
-  const int rpi = 256 / cpr;
-  long parts = sms * 4 / ((C + 2047) / 2048);
-  const long max_parts = (rows + rpi * 8 - 1) / (rpi * 8);     // at least 8 rows per thread
+  const int cblocks = (C + kBnCh - 1) / kBnCh;
+  long parts = (static_cast<long>(sms) * 4 + cblocks - 1) / cblocks;       // ~4 CTAs per SM over the whole grid
+  const long max_parts = (rows + 32 * 8 - 1) / (32 * 8);                    // at least 8 rows per thread
   if (parts > max_parts) parts = max_parts;
   if (parts < 1) parts = 1;
   return static_cast<int>(parts);
+}
+static long bn_partial_floats(long rows, int C) {
+  return static_cast<long>((C + kBnCh - 1) / kBnCh) * bn_num_parts(rows, C) * kBnCh * 3;
+}
+long bn_workspace_floats(long rows, int C) { return bn_partial_floats(rows, C) + 2L * C; }
+
+static int bn_launch_stats(const void* x, long rows, int C, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, float momentum, float eps, float* workspace, float* scale_shift, int f32,
+                           cudaStream_t s) {
+  const int nparts = bn_num_parts(rows, C);
+  const int cblocks = (C + kBnCh - 1) / kBnCh;
+  const long rows_per_cta = (rows + nparts - 1) / nparts;
+  dim3 grid(nparts, cblocks);
+  if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
+  else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
+  MV_LAUNCH_CHECK();
+  bn_finalize_kernel<<<cblocks, 1024, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
+                                              scale_shift);
+  MV_LAUNCH_CHECK();
+  return 0;
 }
 
 int bn_forward(const void* x, const void* resid, void* y, long rows, int C, const float* gamma, const float* beta,
@@ -179,19 +222,10 @@ int bn_forward(const void* x, const void* resid, void* y, long rows, int C, cons
                long ws_floats, int f32, cudaStream_t s) {
   MV_REQUIRE(x && y && gamma && beta && running_mean && running_var && workspace, "bn_forward: null argument");
   MV_REQUIRE(C % 8 == 0 && C >= 8 && rows > 0, "bn_forward: C must be a multiple of 8 (got %d)", C);
-  MV_REQUIRE(C <= 2048 || C % 2048 == 0, "bn_forward: C > 2048 must be a multiple of 2048");
-  const int nparts = bn_num_parts(rows, C);
-  MV_REQUIRE(ws_floats >= static_cast<long>(nparts) * C * 3 + 2 * C, "bn_forward: workspace too small");
-  float* scale_shift = workspace + static_cast<long>(nparts) * C * 3;
+  MV_REQUIRE(ws_floats >= bn_workspace_floats(rows, C), "bn_forward: workspace too small");
+  float* scale_shift = workspace + bn_partial_floats(rows, C);
   if (training) {
-    const long rows_per_cta = (rows + nparts - 1) / nparts;
-    dim3 grid(nparts, (C + 2047) / 2048);
-    if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
-    else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
-    MV_LAUNCH_CHECK();
-    bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
-                                                      scale_shift);
-    MV_LAUNCH_CHECK();
+    if (bn_launch_stats(x, rows, C, gamma, beta, running_mean, running_var, momentum, eps, workspace, scale_shift, f32, s)) return -2;
   } else {
     bn_eval_scale_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, gamma, beta, running_mean, running_var, eps, scale_shift);
     MV_LAUNCH_CHECK();
@@ -274,18 +308,10 @@ int bn_relu_maxpool(const void* x, void* y, int B, int H, int W, int C, const fl
   MV_REQUIRE(x && y && gamma && beta && running_mean && running_var && workspace, "bn_relu_maxpool: null argument");
   MV_REQUIRE(C % 8 == 0 && C <= 2048 && H % 2 == 0 && W % 2 == 0, "bn_relu_maxpool: need C %% 8 == 0, even H and W");
   const long rows = static_cast<long>(B) * H * W;
-  const int nparts = bn_num_parts(rows, C);
-  MV_REQUIRE(ws_floats >= static_cast<long>(nparts) * C * 3 + 2 * C, "bn_relu_maxpool: workspace too small");
-  float* scale_shift = workspace + static_cast<long>(nparts) * C * 3;
+  MV_REQUIRE(ws_floats >= bn_workspace_floats(rows, C), "bn_relu_maxpool: workspace too small");
+  float* scale_shift = workspace + bn_partial_floats(rows, C);
   if (training) {
-    const long rows_per_cta = (rows + nparts - 1) / nparts;
-    dim3 grid(nparts, 1);
-    if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
-    else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
-    MV_LAUNCH_CHECK();
-    bn_finalize_kernel<<<(C * 32 + 255) / 256, 256, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
-                                                          scale_shift);
-    MV_LAUNCH_CHECK();
+    if (bn_launch_stats(x, rows, C, gamma, beta, running_mean, running_var, momentum, eps, workspace, scale_shift, f32, s)) return -2;
   } else {
     bn_eval_scale_kernel<<<(C + 127) / 128, 128, 0, s>>>(C, gamma, beta, running_mean, running_var, eps, scale_shift);
     MV_LAUNCH_CHECK();

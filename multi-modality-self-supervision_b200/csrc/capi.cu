@@ -301,7 +301,7 @@ int mv_mlm_ce(const float* logits, int64_t ld, const int64_t* labels, int32_t n,
   return mlm_ce_fwd_bwd(a, precision == MV_PREC_FP32, S(stream));
 }
 
-int64_t mv_bn_workspace_floats(int64_t rows, int32_t C) { return static_cast<int64_t>(bn_num_parts(rows, C)) * C * 3 + 2 * C; }
+int64_t mv_bn_workspace_floats(int64_t rows, int32_t C) { return bn_workspace_floats(rows, C); }
 
 int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32_t C, const float* gamma, const float* beta,
                   float* running_mean, float* running_var, float momentum, float eps, int32_t training, int32_t relu,

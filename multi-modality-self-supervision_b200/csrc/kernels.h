@@ -119,6 +119,7 @@ int bert_adam_step(const BertAdamArgs& a, cudaStream_t s);
 
 // ---- BatchNorm2d of the frozen ResNet trunk, channels-last [rows, C]: batch statistics + affine (+ residual) (+ ReLU)
 int bn_num_parts(long rows, int C);
+long bn_workspace_floats(long rows, int C);
 int bn_forward(const void* x, const void* resid, void* y, long rows, int C, const float* gamma, const float* beta,
                float* running_mean, float* running_var, float momentum, float eps, int training, int relu, float* workspace,
                long ws_floats, int f32, cudaStream_t s);
@@ -145,7 +146,14 @@ struct AttnArgs {
   float* dq_acc;                     // [B*L, H] fp32 scratch (tcgen05 path; zeroed by the launcher)
   float* delta;                      // [B, nh, L] scratch: rowsum(dO * O)
   int drop_on; uint32_t drop_site; DropoutCfg drop;
+  // tcgen05 path: precomputed keep bits [B, nh, L, bits_w] (attn_dropout_bits); null = the launcher generates them into a
+  // process-wide scratch first.  bits_w is filled by the launcher.
+  const uint32_t* drop_bits; int bits_w;
 };
+// keep-bit words of one dropout site for a [B, nh, L, L] probability tensor, and the generator: site = site0 + i * stride
+long attn_bits_words(int B, int nh, int L);
+int attn_dropout_bits(uint32_t* bits, int n_sites, uint32_t site0, uint32_t site_stride, int B, int nh, int L,
+                      const DropoutCfg& drop, cudaStream_t s);
 int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s);
 int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s);
 int attention_fwd_simt(const AttnArgs& a, cudaStream_t s);

@@ -161,63 +161,129 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T*
 // accumulated in WARP-PRIVATE shared-memory rows (each lane owns its columns, so no synchronisation), which keeps the
 // register budget low enough for two CTAs per SM; at the end the 8 rows are summed and one fp32 atomicAdd per column
 // per CTA goes to the gradient arena.  Algorithmic traffic: read dy, x; write dx (+ dx_drop).
-template <typename T>
+// A row costs ONE butterfly reduction: with x' = x - x0 (x0 = the row's first element, a cheap shift that keeps the
+// single-pass variance well conditioned) the four sums  sum x', sum x'^2, sum dy*g, sum dy*g*x'  give mean, rstd and both
+// projection terms  s1 = mean(dy*g),  s2 = mean(dy*g*xhat) = rstd * (sum dy*g*x' - mean' * sum dy*g) / H,
+// so the dependency chain per row is load -> one 4-wide reduction -> store (it was four serial reductions).  The bf16
+// instantiation also prefetches the next row's operands (raw 16-byte vectors) under the current row's arithmetic.
+template <typename T, int NC>
+struct RawRow;
+template <int NC>
+struct RawRow<bf16, NC> { uint4 x[NC], d[NC]; };
+template <int NC>
+struct RawRow<float, NC> { float4 x[NC][2], d[NC][2]; };
+
+template <int NC>
+__device__ __forceinline__ void raw_load(RawRow<bf16, NC>& r, const bf16* x, const bf16* dy, long row, int H, int nch, int lane) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      r.x[c] = *reinterpret_cast<const uint4*>(x + row * H + ch * 8);
+      r.d[c] = *reinterpret_cast<const uint4*>(dy + row * H + ch * 8);
+    }
+  }
+}
+template <int NC>
+__device__ __forceinline__ void raw_load(RawRow<float, NC>& r, const float* x, const float* dy, long row, int H, int nch, int lane) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      r.x[c][0] = *reinterpret_cast<const float4*>(x + row * H + ch * 8);
+      r.x[c][1] = *reinterpret_cast<const float4*>(x + row * H + ch * 8 + 4);
+      r.d[c][0] = *reinterpret_cast<const float4*>(dy + row * H + ch * 8);
+      r.d[c][1] = *reinterpret_cast<const float4*>(dy + row * H + ch * 8 + 4);
+    }
+  }
+}
+__device__ __forceinline__ void raw_unpack(const uint4& u, float (&v)[8]) {
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ void raw_unpack(const float4 (&u)[2], float (&v)[8]) {
+  v[0] = u[0].x; v[1] = u[0].y; v[2] = u[0].z; v[3] = u[0].w; v[4] = u[1].x; v[5] = u[1].y; v[6] = u[1].z; v[7] = u[1].w;
+}
+
+template <typename T, int NC>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                         const float* __restrict__ gamma, T* __restrict__ dx,
                                                         T* __restrict__ dx_drop, float* dgamma, float* dbeta, float* dbias,
                                                         int rows, int H, float eps, int in_drop, int out_drop, uint32_t site,
                                                         DropoutCfg drop) {
   extern __shared__ float red[];  // [8 warps][3][H]
+  constexpr bool kPrefetch = sizeof(T) == 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = H >> 3;
+  const float inv_h = 1.f / static_cast<float>(H);
   float* my = red + static_cast<size_t>(warp) * 3 * H;
   for (int i = lane; i < 3 * H; i += 32) my[i] = 0.f;
   __syncwarp();
-  for (long row = static_cast<long>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<long>(gridDim.x) * 8) {
-    float xv[kMaxChunks][8], dv[kMaxChunks][8];
+  const long stride = static_cast<long>(gridDim.x) * 8;
+  long row = static_cast<long>(blockIdx.x) * 8 + warp;
+  RawRow<T, NC> cur;
+  if (kPrefetch && row < rows) raw_load(cur, x, dy, row, H, nch, lane);
+  for (; row < rows; row += stride) {
+    if (!kPrefetch) raw_load(cur, x, dy, row, H, nch, lane);
+    float xv[NC][8], dv[NC][8];
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
-        load8<T>(x + row * H + ch * 8, xv[c]);
-        load8<T>(dy + row * H + ch * 8, dv[c]);
+        raw_unpack(cur.x[c], xv[c]);
+        raw_unpack(cur.d[c], dv[c]);
         if (in_drop) apply_dropout8(dv[c], drop, site, row, H, ch * 8);
       }
     }
-    float mean, rstd;
-    row_stats(xv, nch, lane, H, eps, mean, rstd);
-    float s1 = 0.f, s2 = 0.f;
+    if (kPrefetch && row + stride < rows) raw_load(cur, x, dy, row + stride, H, nch, lane);
+    const float x0 = __shfl_sync(0xffffffffu, xv[0][0], 0);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
-        float g[8], ag[8], ab[8];
+        float g[8];
+        load8<float>(gamma + ch * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xs = xv[c][j] - x0;
+          const float dg = dv[c][j] * g[j];
+          a0 += xs;
+          a1 = fmaf(xs, xs, a1);
+          a2 += dg;
+          a3 = fmaf(dg, xs, a3);
+          xv[c][j] = xs;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    const float mean = a0 * inv_h;                                   // of the shifted row
+    const float rstd = rsqrtf(fmaxf(a1 * inv_h - mean * mean, 0.f) + eps);
+    const float s1 = a2 * inv_h;
+    const float s2 = rstd * (a3 - mean * a2) * inv_h;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nch) {
+        float g[8], ag[8], ab[8], o[8];
         load8<float>(gamma + ch * 8, g);
         load8<float>(my + ch * 8, ag);
         load8<float>(my + H + ch * 8, ab);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (xv[c][j] - mean) * rstd;
-          ag[j] += dv[c][j] * xh;
+          ag[j] = fmaf(dv[c][j], xh, ag[j]);
           ab[j] += dv[c][j];
-          dv[c][j] *= g[j];              // dv <- dy * gamma
-          s1 += dv[c][j];
-          s2 += dv[c][j] * xh;
-          xv[c][j] = xh;
+          o[j] = rstd * (dv[c][j] * g[j] - s1 - xh * s2);
         }
         store8<float>(my + ch * 8, ag);
         store8<float>(my + H + ch * 8, ab);
-      }
-    }
-    s1 = warp_sum(s1) / H;
-    s2 = warp_sum(s2) / H;
-#pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
-      const int ch = lane + 32 * c;
-      if (ch < nch) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[c][j] - s1 - xv[c][j] * s2);
         store8<T>(dx + row * H + ch * 8, o);
         if (out_drop) {
           apply_dropout8(o, drop, site, row, H, ch * 8);
@@ -481,13 +547,22 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx
   const size_t smem = static_cast<size_t>(8) * 3 * H * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
-    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<bf16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<float, kMaxChunks>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<bf16, kMaxChunks>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
     attr = true;
   }
-  MV_DISPATCH_T(f32, (ln_bwd_kernel<T><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
-                                                               static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
-                                                               dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
+  // H <= 768 (BERT-base): three 8-element chunks per lane, which keeps the whole row + the prefetched next row in registers
+  if (H <= 768) {
+    MV_DISPATCH_T(f32, (ln_bwd_kernel<T, 3><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
+                                                                    static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
+                                                                    dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
+  } else {
+    MV_DISPATCH_T(f32, (ln_bwd_kernel<T, kMaxChunks><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
+                                                                             static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
+                                                                             dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
+  }
   MV_LAUNCH_CHECK();
   return 0;
 }
