@@ -257,11 +257,29 @@ def run_ours(args):
     gemm_tf = pfl[0] / (pms[0] * 1e-3) / 1e12 if pms[0] > 0 else 0.0
     step_ms = ms / args.steps
     enc_tf = ENC_FLOPS_PER_SAMPLE * B / (step_ms * 1e-3) / 1e12
+    # north_star scope "encoder GEMMs + attention": dense encoder FLOPs over the time of ALL tcgen05 GEMM launches (the
+    # encoder's, plus the small image-projection / pooler / MLM-head ones, i.e. a slight under-estimate) + attention
+    enc_ms = (pms[0] + pms[1] + pms[2]) / 2
+    enc_scope_tf = ENC_FLOPS_PER_SAMPLE * B / (enc_ms * 1e-3) / 1e12 if enc_ms > 0 else 0.0
+    # DRAM traffic of the same kernel family, per launch like `achieved`: measured offline with ncu (one pass over a
+    # profiled step, dram__bytes_read.sum + dram__bytes_write.sum per launch; tools/summarize_launches.py --json)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_step_traffic.json")) as f:
+            tr = json.load(f)["gemm_tc05"]
+        traffic = tr["dram_bytes"] / tr["launches"]
+        traffic_src = "profiles/r01_step_traffic.json: %.1f GB over %d launches of one step (ncu)" % (tr["dram_bytes"] / 1e9, tr["launches"])
+    except Exception:
+        pass
+    n_gemm = max(1, pcn[0] // 2)
     roofline = {"bound": "tensor", "kernel": "gemm_tc05_kernel (all %d launches of a step)" % (pcn[0] // 2), "achieved": gemm_tf,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch (DRAM)",
+                "traffic_source": traffic_src, "algorithmic_flops_per_launch": pfl[0] / 2 / n_gemm, "peak_source": peak_src,
                 "gemm_ms_per_step": pms[0] / 2, "attn_fwd_ms_per_step": pms[1] / 2, "attn_bwd_ms_per_step": pms[2] / 2,
                 "attn_fwd_tflops_dense": pfl[1] / (pms[1] * 1e-3) / 1e12 if pms[1] > 0 else None,
                 "attn_bwd_tflops_dense": pfl[2] / (pms[2] * 1e-3) / 1e12 if pms[2] > 0 else None,
+                "encoder_gemm_plus_attention_ms": enc_ms, "encoder_gemm_plus_attention_tflops_dense": enc_scope_tf,
+                "encoder_gemm_plus_attention_frac_of_peak": enc_scope_tf / peak_tf,
                 "encoder_dense_tflops_over_whole_step": enc_tf, "encoder_frac_of_peak_over_whole_step": enc_tf / peak_tf}
 
     def teardown():

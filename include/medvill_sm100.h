@@ -93,6 +93,9 @@ typedef struct mv_batch {
   int32_t sep_position;        /* position id of the prefix [SEP]: 0, or A-1 (= N+1) in the fine-tune model        */
   int32_t prefix_type;         /* token type of [CLS]/regions/[SEP]: 0, or 4 with new_segment_ids                   */
   int32_t pad_lookup_grad;     /* 1: keep the embedding-lookup gradient of [PAD] (vendored nn.Embedding: no padding_idx) */
+  const float* global_counts;  /* optional DEVICE [2] = {#labelled tokens, batch size} of the GLOBAL batch, e.g. all-reduced     */
+                               /* in-stream by mv_comm_allreduce_f32; when set it replaces inv_n_lab_global / inv_batch_global */
+                               /* so that a multi-rank step needs no host round trip for the loss normalisers             */
   const float* lab_weights;    /* [n_lab] optional per-row loss weights (fine-tune masked_weights, model.py:998-1005;  */
                                /* a position masked twice is one row of weight 2); NULL = 1                            */
 } mv_batch;

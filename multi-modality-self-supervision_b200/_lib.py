@@ -42,7 +42,7 @@ class mv_batch(C.Structure):
                 ("lab_labels", C.c_void_p), ("inv_n_lab_global", C.c_float), ("inv_batch_global", C.c_float),
                 ("dropout_seed", C.c_uint64), ("train", C.c_int32),
                 ("sep_position", C.c_int32), ("prefix_type", C.c_int32), ("pad_lookup_grad", C.c_int32),
-                ("lab_weights", C.c_void_p)]
+                ("global_counts", C.c_void_p), ("lab_weights", C.c_void_p)]
 
 
 class mv_step_stats(C.Structure):

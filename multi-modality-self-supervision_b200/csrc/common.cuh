@@ -15,6 +15,8 @@ namespace mv {
 void set_error(const char* fmt, ...);
 const char* last_error();
 int device_sm_count();
+void set_reserved_sms(int n); // persistent GEMM grids use device_sm_count() - n SMs (n SMs stay free for NCCL CTAs)
+int gemm_sm_budget();
 void count_launch();          // every kernel launch of this library bumps one process-wide counter
 long launch_count();
 

@@ -15,6 +15,8 @@
 #include "engine.h"
 
 #include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mv {
@@ -106,9 +108,28 @@ int nccl_unique_id(uint8_t out[128]) {
   return 0;
 }
 
+// CTAs NCCL may use for the gradient all-reduces, and the SMs the persistent GEMMs leave free for them while buckets are
+// in flight.  Without this the all-reduce kernel's CTAs queue behind a 148-CTA persistent GEMM, take over some SMs when
+// it exits, and the NEXT GEMM's statically assigned tiles on those SMs wait for the whole collective (GEMM time per step
+// 13.6 -> 15.6 ms at 8 GPUs, profiles/r01_bench_n8.json).  447 MB of fp32 gradients per step need ~2 ms of NVLink time
+// spread over a 25 ms backward, so a few CTAs are plenty.
+static int comm_ctas() {
+  static int n = -1;
+  if (n < 0) {
+    const char* e = getenv("MEDVILL_COMM_CTAS");
+    n = e ? atoi(e) : 8;
+    if (n < 1) n = 1;
+    if (n > 32) n = 32;
+  }
+  return n;
+}
+
 int engine_comm_init(Engine* e, const uint8_t id[128], int rank, int world) {
   NcclApi* n = load_nccl();
   if (!n) return -3;
+  char buf[16];
+  snprintf(buf, sizeof(buf), "%d", comm_ctas());
+  setenv("NCCL_MAX_CTAS", buf, 0);          // read by ncclCommInitRank below; an explicit user setting wins
   NcclUid uid;
   memcpy(uid.b, id, 128);
   void* comm = nullptr;
@@ -129,6 +150,7 @@ int engine_allreduce(Engine* e, float* buf, int64_t count, cudaStream_t s) {
 }
 
 int engine_comm_sync(Engine* e, cudaStream_t s) {
+  set_reserved_sms(0);
   if (e->comm_pending) {
     MV_CUDA_CHECK(cudaEventRecord(e->ev_done, e->comm_stream));
     MV_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_done, 0));
@@ -337,6 +359,7 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
   ItmArgs ia;
   ia.B = B; ia.H = H; ia.pooled = pooled; ia.w = params + lay.itm_w; ia.b = params + lay.itm_b;
   ia.labels = reinterpret_cast<const int64_t*>(b.is_aligned); ia.gscale = b.inv_batch_global; ia.logits = itm_logits;
+  ia.count_dev = b.global_counts ? b.global_counts + 1 : nullptr;
   ia.loss_sum = &stats->itm_loss_sum; ia.correct = &stats->itm_correct;
   ia.d_pre = (b.train && b.is_aligned) ? d_pre : nullptr; ia.dw = grads + lay.itm_w; ia.db = grads + lay.itm_b;
   MV_TRY(itm_head_fwd_bwd(ia, f32, s));
@@ -352,6 +375,7 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     CeArgs ca;
     ca.n = n; ca.V = cfg.vocab; ca.ldv = Vpad; ca.logits = logits; ca.labels = reinterpret_cast<const int64_t*>(b.lab_labels);
     ca.dlogits = b.train ? dlogits : nullptr; ca.gscale = b.inv_n_lab_global;
+    ca.count_dev = b.global_counts;
     ca.loss_sum = &stats->mlm_loss_sum; ca.correct = &stats->mlm_correct; ca.row_lse = row_lse; ca.row_argmax = row_argmax;
     ca.row_weight = b.lab_weights;
     MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
@@ -367,6 +391,7 @@ int Engine::bucket_done(size_t idx, int allreduce, cudaStream_t s) {
   MV_CUDA_CHECK(cudaStreamWaitEvent(comm_stream, ev_ready, 0));
   MV_TRY(engine_allreduce(this, grads + bk.offset, bk.count, comm_stream));
   comm_pending = true;
+  set_reserved_sms(comm_ctas());            // GEMMs launched from now on leave room for the collective's CTAs
   return 0;
 }
 

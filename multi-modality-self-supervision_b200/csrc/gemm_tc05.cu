@@ -460,7 +460,7 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   p.n_tiles = (d.N + BN - 1) / BN;
   p.stages = pick_stages(stage_bytes<BN, TWO>());
   // split-K only for fp32 reduce-add outputs (weight gradients): fill ~2 waves of SMs (or SM pairs)
-  const int slots = TWO ? device_sm_count() / 2 : device_sm_count();
+  const int slots = TWO ? gemm_sm_budget() / 2 : gemm_sm_budget();
   const int tiles = p.m_tiles * p.n_tiles;
   int splits = 1;
   if (d.accumulate) {
@@ -578,7 +578,7 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   bool pair = d.M > BM;                       // a single 128-row tile gains nothing from a partner SM
   if (pair_env() >= 0) pair = pair_env() != 0;
   if (d.pair >= 0) pair = d.pair != 0;
-  const int sms = device_sm_count();
+  const int sms = gemm_sm_budget();
   const int m_tiles = pair ? (d.M + 2 * BM - 1) / (2 * BM) : p.m_tiles;
   int bn = d.bn;
   if (bn == 0) bn = pick_bn(m_tiles, d.N, pair ? sms / 2 : sms, d.accumulate != 0, pair, d.b_mn != 0);

@@ -73,6 +73,7 @@ struct CeArgs {
   const int64_t* labels;           // [n]
   void* dlogits;                     // [n, ldv] activation dtype: (softmax - onehot) * gscale, pad columns zeroed
   float gscale;                      // 1 / (#labelled tokens in the GLOBAL batch)
+  const float* count_dev = nullptr;  // optional device scalar holding that count (all-reduced in-stream): gscale = 1 / *count_dev
   float* loss_sum;                   // += sum_i (lse_i - logit_i[label_i])
   int* correct;                      // += #(argmax == label)
   float* row_lse; int* row_argmax;   // optional per-row outputs (parity aids)
@@ -86,6 +87,7 @@ struct ItmArgs {
   const float* w; const float* b;    // [2, H], [2]
   const int64_t* labels;           // [B]
   float gscale;                      // 1 / (GLOBAL batch)
+  const float* count_dev = nullptr;  // optional device scalar holding the global batch size: gscale = 1 / *count_dev
   float* logits;                     // [B, 2] fp32 out
   float* loss_sum; int* correct;
   void* d_pre;                       // [B, H] activation dtype: grad w.r.t. pooler pre-activation; null = forward only

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) mlm_ce_kernel(const CeArgs a) {
   const float rw = a.row_weight ? a.row_weight[row] : 1.f;       // fine-tune masked_weights (model.py:998-1005)
   if (a.dlogits) {
     T* d = static_cast<T*>(a.dlogits) + static_cast<long>(row) * a.ldv;
-    const float gs = a.gscale * rw;
+    const float gs = (a.count_dev ? 1.f / *a.count_dev : a.gscale) * rw;
     for (int c = tid; c < a.ldv; c += 256) {
       float g = 0.f;
       if (c < a.V) g = (__expf(z[c] - mx) * inv - (c == label ? 1.f : 0.f)) * gs;
@@ -107,8 +107,9 @@ __global__ void __launch_bounds__(256) itm_kernel(const ItmArgs a) {
     atomicAdd(a.loss_sum, lse - (y == 0 ? z0 : z1));
     const int pred = z1 > z0 ? 1 : 0;  // argmax returns the first maximal index on ties
     if (pred == y) atomicAdd(a.correct, 1);
-    const float d0 = (e0 / (e0 + e1) - (y == 0 ? 1.f : 0.f)) * a.gscale;
-    const float d1 = (e1 / (e0 + e1) - (y == 1 ? 1.f : 0.f)) * a.gscale;
+    const float gsc = a.count_dev ? 1.f / *a.count_dev : a.gscale;
+    const float d0 = (e0 / (e0 + e1) - (y == 0 ? 1.f : 0.f)) * gsc;
+    const float d1 = (e1 / (e0 + e1) - (y == 1 ? 1.f : 0.f)) * gsc;
     s_dl[0] = d0;
     s_dl[1] = d1;
     if (a.d_pre) { atomicAdd(a.db, d0); atomicAdd(a.db + 1, d1); }

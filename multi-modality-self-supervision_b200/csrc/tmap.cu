@@ -83,6 +83,15 @@ static std::atomic<long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+// SMs the persistent GEMMs leave free (for NCCL's all-reduce CTAs while gradient buckets are in flight, engine.cu)
+static int g_reserved_sms = 0;
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
+int gemm_sm_budget() {
+  int n = device_sm_count() - g_reserved_sms;
+  if (n < 2) n = 2;
+  return n & ~1;            // CTA pairs
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

@@ -356,10 +356,13 @@ class CXRBERT(nn.Module):
         lab = torch.as_tensor(txt_labels)
         n_lab = int((lab != -100).sum())
         n_lab_g, b_g = float(n_lab), float(B)
+        counts = None
         if eng.world > 1:
-            cnt = torch.tensor([n_lab_g, b_g], dtype=torch.float32, device=eng.device)
-            eng.allreduce_f32(cnt)
-            n_lab_g, b_g = (float(x) for x in cnt.tolist())
+            # global loss normalisers stay on the device: all-reduced in-stream and read by the CE kernels through
+            # mv_batch.global_counts, so the host never waits for the GPU here (a .tolist() drained the whole queue
+            # once per step)
+            counts = torch.tensor([n_lab_g, b_g], dtype=torch.float32).pin_memory().to(eng.device, non_blocking=True)
+            eng.allreduce_f32(counts)
         if mode is None:
             mode, t_len = self.classify_mask(torch.as_tensor(attn_masks), eng)
         cap = eng.max_batch
@@ -369,7 +372,8 @@ class CXRBERT(nn.Module):
             sl = slice(s, e)
             _, batch = self._encode(cls_tok[sl], input_ids[sl], None, segment[sl], None if image is None else image[sl], sep_tok[sl],
                                     train=True, mode=mode[sl], t_len=t_len[sl], txt_labels=lab[sl], is_aligned=is_aligned[sl],
-                                    feats=None if feats is None else feats[sl], n_lab_global=n_lab_g, batch_global=b_g)
+                                    feats=None if feats is None else feats[sl], n_lab_global=n_lab_g, batch_global=b_g,
+                                    global_counts=counts)
             eng.backward(batch, allreduce=(eng.world > 1 and ci == len(chunks) - 1))
         if optimizer_step:
             eng.adamw_step(lr=float(self.args.lr if lr is None else lr))
