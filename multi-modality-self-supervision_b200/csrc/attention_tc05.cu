@@ -37,53 +37,8 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t sel) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
-  return d;
-}
-// 4 keep bits (bit i = element i kept) -> one word whose byte i has its MSB set iff element i is kept.  prmt's
-// sign-replicating selectors then give the AND masks directly: 0x9988 / 0xbbaa for the bf16 pairs (0,1) / (2,3),
-// 0x8888 .. 0xbbbb for the four fp32 elements.
-__device__ __forceinline__ uint32_t keep4_to_msb_bytes(uint32_t bits, int shift) {
-  return (((bits >> shift) & 0xFu) * 0x10204080u) & 0x80808080u;
-}
-
-// Attention-probability dropout keep bits, generated ONCE per step and read by forward and backward: word
-// [((b * nh + h) * L + q) * W + c] holds the keep bits of keys [32c, 32c + 32) of probability row (b, h, q), bit i = key
-// 32c + i kept.  Same Philox stream as dropout_keep16 / attn_keep (the SIMT twin evaluates it per element), so the masks
-// are unchanged — only where they are computed: a dedicated pass runs the 7-round Philox at full occupancy (~0.15 ms for
-// all 12 layers at B = 64) instead of twice inside the latency-bound softmax loops, where it was 35 % of the forward
-// kernel's issued instructions (profiles/r01_ncu_attn_fwd_summary.txt).
-__global__ void __launch_bounds__(256) attn_dropout_bits_kernel(uint32_t* __restrict__ bits, long words_per_site, int n_sites,
-                                                                uint32_t site0, uint32_t site_stride, int B, int nh, int L, int W,
-                                                                DropoutCfg drop) {
-  const long total = words_per_site * n_sites;
-  const int groups_per_row = (L + 15) >> 4;
-  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int site_i = static_cast<int>(i / words_per_site);
-    const long w = i - static_cast<long>(site_i) * words_per_site;
-    const int c = static_cast<int>(w % W);
-    const long row = w / W;                               // (b * nh + h) * L + q
-    uint32_t out = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int k16 = 2 * c + half;
-      if (k16 < groups_per_row) {
-        const uint4 keep = dropout_keep16(drop, site0 + site_stride * site_i, static_cast<uint64_t>(row) * groups_per_row + k16);
-        const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) out |= ((((kw[j] & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (16 * half + 4 * j);
-      }
-    }
-    bits[i] = out;
-  }
-}
-
-// Forward.  256 threads: two threads per query row (warp w reads TMEM lane quarter w & 3 and owns the column half
-// w >> 2 of S and of O), two CTAs per SM.  Online softmax with a reference exponent that lags one key tile behind the
-// running maximum (exact after the final normalisation; only the first tile needs a true max pass).
-// same, from 16 already-packed bf16x2 words
+// P row `r`: 32 consecutive columns starting at c32*32, from 16 already-packed bf16x2 words, into the swizzled
+// [128 x 128] tile (two 64-column halves)
 __device__ __forceinline__ void store_pk32(uint8_t* sP, int r, int c32, const uint32_t (&pk)[16]) {
   uint8_t* half = sP + (c32 >> 1) * TILE_BYTES;
 #pragma unroll
@@ -91,6 +46,9 @@ __device__ __forceinline__ void store_pk32(uint8_t* sP, int r, int c32, const ui
     *reinterpret_cast<uint4*>(half + sw128_off(r, (c32 & 1) * 4 + j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
 }
 
+// Forward.  256 threads: two threads per query row (warp w reads TMEM lane quarter w & 3 and owns the column half
+// w >> 2 of S and of O), two CTAs per SM.  Online softmax with a reference exponent that lags one key tile behind the
+// running maximum (exact after the final normalisation); the reference is seeded from the first 16 keys.
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -152,15 +110,11 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
   for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
   float ref = 0.f, l_loc = 0.f;
   uint32_t it = 0;
-  // this row's keep-bit words (a.drop_bits: [B, nh, L, W] words, W = 4 * key tiles)
-  const uint32_t* bits_row = a.drop_on ? a.drop_bits + ((static_cast<long>(b) * a.nh + h) * L + min(q, L - 1)) * a.bits_w : nullptr;
 
   for (; j < n_kv; ++it) {
     const int jn = next_active(j);
     const uint32_t ph = it & 1u;
     const int k_lo = j * TK;
-    uint2 kbits = make_uint2(0xffffffffu, 0xffffffffu);   // keep bits of keys [k_lo + ch * 64, +64): in flight under the S wait
-    if (a.drop_on) kbits = __ldg(reinterpret_cast<const uint2*>(bits_row + ((k_lo + ch * 64) >> 5)));
     if (warp == 0) {      // warp-uniform (descriptors stay in uniform registers); one elected lane issues
       if (it == 0) mbar_wait(&sh->bar_q, 0);
       mbar_wait(&sh->bar_k, ph);
@@ -233,12 +187,15 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
       for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(p[2 * i], p[2 * i + 1]);
       if (a.drop_on) {
         // dropped probabilities are zeroed with one AND per bf16 pair; the 1/(1-p) keep-scale is applied once to O
-        const uint32_t wb = c == 0 ? kbits.x : kbits.y;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint32_t m = keep4_to_msb_bytes(wb, 4 * g);
-          pk[2 * g] &= prmt(m, 0x9988u);
-          pk[2 * g + 1] &= prmt(m, 0xbbaau);
+        for (int g = 0; g < 2; ++g) {
+          const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (kc0 + c * 32 + 16 * g) >> 4));
+          const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            pk[8 * g + 2 * w] &= __byte_perm(kw[w], 0, 0x1100);
+            pk[8 * g + 2 * w + 1] &= __byte_perm(kw[w], 0, 0x3322);
+          }
         }
       }
       store_pk32(sP, r, ch * 2 + c, pk);
@@ -450,6 +407,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     tc_fence_after();
     issue_s_dp(0);
   }
+
   for (; i < n_q; ++it) {
     const int in = next_active(i);
     const uint32_t ph = it & 1u, buf = it & 1u;
@@ -462,9 +420,6 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mask_row_interval(mode, q_ok ? q : 0, A, tl, L, m_lo, m_hi);
     const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L) &&
                       (q_lo + TQ <= L);
-    uint32_t kbits = 0xffffffffu;                         // keep bits of keys [k_lo + cq * 32, +32) of this row
-    if (a.drop_on)
-      kbits = __ldg(a.drop_bits + ((static_cast<long>(b) * a.nh + h) * L + (q_ok ? q : 0)) * a.bits_w + ((k_lo >> 5) + cq));
     mbar_wait(&sh->bar_s, ph);
     tc_fence_after();
 #pragma unroll 1
@@ -481,25 +436,29 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       if (full || (q_ok && rel_lo <= 0 && rel_hi >= 16)) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) p[e] = ex2(fmaf(__uint_as_float(sv[e]), scale2, -lse2));
-      } else {                       // partial or empty (span = 0): one code path
-        const uint32_t span = (q_ok && rel_hi > rel_lo) ? static_cast<uint32_t>(rel_hi - rel_lo) : 0u;
+      } else if (!q_ok || rel_hi <= 0 || rel_lo >= 16) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) p[e] = 0.f;
+      } else {
+        const uint32_t span = static_cast<uint32_t>(rel_hi - rel_lo);
 #pragma unroll
         for (int e = 0; e < 16; ++e)
           p[e] = (static_cast<uint32_t>(e - rel_lo) < span) ? ex2(fmaf(__uint_as_float(sv[e]), scale2, -lse2)) : 0.f;
       }
       uint32_t pk[8], dk[8];
       if (a.drop_on) {
+        const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + col) >> 4));
+        const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const uint32_t m = keep4_to_msb_bytes(kbits, 16 * c + 4 * w);      // elements 4w .. 4w+3 of this 16-chunk
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int e = 4 * w + 2 * hh;
-            // dP masked per element (all-ones / zero words), then dS = p * (dP * keep_scale - delta)
-            const float t0 = __uint_as_float(dv[e] & prmt(m, hh ? 0xaaaau : 0x8888u));
-            const float t1 = __uint_as_float(dv[e + 1] & prmt(m, hh ? 0xbbbbu : 0x9999u));
+            // dP masked by the keep bytes (all-ones / zero per element), then dS = p * (dP * keep_scale - delta)
+            const float t0 = __uint_as_float(dv[e] & __byte_perm(kw[w], 0, hh ? 0x2222 : 0x0000));
+            const float t1 = __uint_as_float(dv[e + 1] & __byte_perm(kw[w], 0, hh ? 0x3333 : 0x1111));
             dk[e >> 1] = pack_bf16x2(p[e] * fmaf(t0, a.drop.scale, -delta), p[e + 1] * fmaf(t1, a.drop.scale, -delta));
-            pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]) & prmt(m, hh ? 0xbbaau : 0x9988u);
+            pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]) & __byte_perm(kw[w], 0, hh ? 0x3322 : 0x1100);
           }
         }
       } else {
@@ -616,46 +575,8 @@ constexpr uint32_t kBwdSmem = 1024 + 6 * TILE_BYTES + 3 * P_BYTES + sizeof(BwdSm
 
 }  // namespace
 
-int attn_bits_words_per_row(int L) { return 4 * ((L + TK - 1) / TK); }
-long attn_bits_words(int B, int nh, int L) { return static_cast<long>(B) * nh * L * attn_bits_words_per_row(L); }
-
-int attn_dropout_bits(uint32_t* bits, int n_sites, uint32_t site0, uint32_t site_stride, int B, int nh, int L,
-                      const DropoutCfg& drop, cudaStream_t s) {
-  MV_REQUIRE(bits && n_sites > 0 && B > 0 && nh > 0 && L > 0, "attn_dropout_bits: bad arguments");
-  const long per_site = attn_bits_words(B, nh, L);
-  long blocks = (per_site * n_sites + 255) / 256;
-  const long cap = static_cast<long>(device_sm_count()) * 16;
-  if (blocks > cap) blocks = cap;
-  attn_dropout_bits_kernel<<<static_cast<int>(blocks), 256, 0, s>>>(bits, per_site, n_sites, site0, site_stride, B, nh, L,
-                                                                   attn_bits_words_per_row(L), drop);
-  MV_LAUNCH_CHECK();
-  return 0;
-}
-
-namespace {
-// Per-op entry points (mv_attention_fwd / _bwd without an engine) keep one lazily grown keep-bit scratch per process.
-int scratch_bits(const AttnArgs& a, cudaStream_t s, const uint32_t** out) {
-  static uint32_t* buf = nullptr;
-  static long cap = 0;
-  const long need = attn_bits_words(a.B, a.nh, a.L);
-  if (need > cap) {
-    MV_CUDA_CHECK(cudaDeviceSynchronize());
-    if (buf) cudaFree(buf);
-    buf = nullptr; cap = 0;
-    MV_CUDA_CHECK(cudaMalloc(&buf, need * sizeof(uint32_t)));
-    cap = need;
-  }
-  if (attn_dropout_bits(buf, 1, a.drop_site, 0, a.B, a.nh, a.L, a.drop, s)) return -2;
-  *out = buf;
-  return 0;
-}
-}  // namespace
-
-int attention_fwd_tc05(const AttnArgs& a_in, cudaStream_t s) {
-  AttnArgs a = a_in;
+int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s) {
   MV_REQUIRE(a.qkv && a.ctx && a.lse && a.mode && a.t_len, "attention_fwd: null argument");
-  if (a.drop_on && !a.drop_bits && scratch_bits(a, s, &a.drop_bits)) return -2;
-  a.bits_w = attn_bits_words_per_row(a.L);
   const int H = a.nh * D;
   CUtensorMap tm;
   int rc = tmap_encode_2d(&tm, TMAP_BF16, a.qkv, 3 * H, static_cast<uint64_t>(a.B) * a.L, static_cast<uint64_t>(3 * H) * 2, D, TQ);
@@ -671,11 +592,8 @@ int attention_fwd_tc05(const AttnArgs& a_in, cudaStream_t s) {
   return 0;
 }
 
-int attention_bwd_tc05(const AttnArgs& a_in, cudaStream_t s) {
-  AttnArgs a = a_in;
+int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
   MV_REQUIRE(a.qkv && a.ctx && a.lse && a.dctx && a.dqkv && a.dq_acc && a.delta, "attention_bwd: null argument");
-  if (a.drop_on && !a.drop_bits && scratch_bits(a, s, &a.drop_bits)) return -2;
-  a.bits_w = attn_bits_words_per_row(a.L);
   const int H = a.nh * D;
   const long rows = static_cast<long>(a.B) * a.L;
   CUtensorMap tmQKV, tmDO;

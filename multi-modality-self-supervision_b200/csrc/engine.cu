@@ -215,9 +215,7 @@ int Engine::init(const mv_config& c) {
       alloc(&dxc, M * H * es) || alloc(&dh1, M * I * es) || alloc(&dqkv, M * 3 * H * es) || alloc(&dctx, M * H * es) ||
       alloc(&dproj, B * N * H * es) || alloc(reinterpret_cast<void**>(&dq_acc), M * H * sizeof(float)) ||
       alloc(reinterpret_cast<void**>(&delta), B * nh * L * sizeof(float)) || alloc(reinterpret_cast<void**>(&zero_idx), 16) ||
-      alloc(reinterpret_cast<void**>(&stats), sizeof(mv_step_stats)) ||
-      ((c.dropout_p > 0.f && !f32) &&
-       alloc(reinterpret_cast<void**>(&attn_bits), static_cast<size_t>(c.layers) * attn_bits_words(c.max_batch, nh, L) * sizeof(uint32_t))))
+      alloc(reinterpret_cast<void**>(&stats), sizeof(mv_step_stats)))
     return -2;
   MV_CUDA_CHECK(cudaMemset(zero_idx, 0, 16));
   MV_CUDA_CHECK(cudaMemset(stats, 0, sizeof(mv_step_stats)));
@@ -328,10 +326,6 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
   ea.sep_pos = b.sep_position; ea.prefix_type = b.prefix_type;
   MV_TRY(embed_ln_fwd(ea, f32, s));
 
-  // --- attention-probability dropout: keep bits of all layers in one pass, reused by backward ---
-  const long bits_per_layer = attn_bits_words(B, nh, L);
-  if (drop && !f32) MV_TRY(attn_dropout_bits(attn_bits, cfg.layers, site_att(0), 4, B, nh, L, dc, s));
-
   // --- encoder ---
   for (int l = 0; l < cfg.layers; ++l) {
     const int64_t base = lay.layer0 + l * lay.layer_stride;
@@ -341,7 +335,6 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     memset(&aa, 0, sizeof(aa));
     aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
     aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
-    aa.drop_bits = (drop && !f32) ? attn_bits + l * bits_per_layer : nullptr;
     MV_TRY(prof_begin(1, 4.0 * B * nh * static_cast<double>(L) * L * 64, s));
     MV_TRY(f32 ? attention_fwd_simt(aa, s) : attention_fwd_tc05(aa, s));
     MV_TRY(prof_end(s));
@@ -458,7 +451,6 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
     aa.dctx = dctx; aa.dqkv = dqkv; aa.dq_acc = dq_acc; aa.delta = delta;
     aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
-    aa.drop_bits = (drop && !f32) ? attn_bits + l * attn_bits_words(B, nh, L) : nullptr;   // generated by forward()
     MV_TRY(prof_begin(2, 10.0 * B * nh * static_cast<double>(L) * L * 64, s));
     MV_TRY(f32 ? attention_bwd_simt(aa, s) : attention_bwd_tc05(aa, s));
     MV_TRY(prof_end(s));

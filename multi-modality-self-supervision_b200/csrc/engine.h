@@ -41,7 +41,6 @@ struct Engine {
   float* itm_logits = nullptr;
   void *dxa = nullptr, *dxb = nullptr, *dxc = nullptr, *dh1 = nullptr, *dqkv = nullptr, *dctx = nullptr, *dproj = nullptr;
   float *dq_acc = nullptr, *delta = nullptr;
-  uint32_t* attn_bits = nullptr;   // [layers][B, nh, L, W] attention-dropout keep bits of the current step (bf16 path, p > 0)
   int64_t* zero_idx = nullptr;     // [1] = {0}: gather/scatter of the [CLS] rows
   mv_step_stats* stats = nullptr;    // device
   mv_step_stats* stats_host = nullptr;  // pinned

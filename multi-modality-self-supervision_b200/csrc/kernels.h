@@ -148,14 +148,7 @@ struct AttnArgs {
   float* dq_acc;                     // [B*L, H] fp32 scratch (tcgen05 path; zeroed by the launcher)
   float* delta;                      // [B, nh, L] scratch: rowsum(dO * O)
   int drop_on; uint32_t drop_site; DropoutCfg drop;
-  // tcgen05 path: precomputed keep bits [B, nh, L, bits_w] (attn_dropout_bits); null = the launcher generates them into a
-  // process-wide scratch first.  bits_w is filled by the launcher.
-  const uint32_t* drop_bits; int bits_w;
 };
-// keep-bit words of one dropout site for a [B, nh, L, L] probability tensor, and the generator: site = site0 + i * stride
-long attn_bits_words(int B, int nh, int L);
-int attn_dropout_bits(uint32_t* bits, int n_sites, uint32_t site0, uint32_t site_stride, int B, int nh, int L,
-                      const DropoutCfg& drop, cudaStream_t s);
 int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s);
 int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s);
 int attention_fwd_simt(const AttnArgs& a, cudaStream_t s);
