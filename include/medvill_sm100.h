@@ -196,6 +196,12 @@ int mv_bn_forward(const void* x, const void* resid, void* y, int64_t rows, int32
  * get_transforms (data/helper.py:20-27), so a step ships uint8 pixels over PCIe.  mean3/std3 are HOST pointers. */
 int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, int32_t cpad, const float* mean3, const float* std3,
                     int32_t precision, void* stream);        /* dst is [B,H,W,cpad], channels >= 3 zero-filled        */
+/* The same transform in 2x2 space-to-depth form, dst [B, H/2 + 3, W/2 + 3, 16] channels-last (zero border: 2 blocks in
+ * front, 1 behind; channel = c*4 + dy*2 + dx as torch pixel_unshuffle, 12..15 zero): the ResNet stem's 7x7/2 convolution
+ * (torchvision resnet50 child 0 inside ImageEncoder_cnn, models/image.py:50-56) is then a 4x4 stride-1 convolution over 16
+ * channels with re-indexed weights — same arithmetic, a shape cuDNN runs on tensor cores.  H and W must be even. */
+int mv_normalize_u8_s2d(const uint8_t* src, void* dst, int32_t B, int32_t H, int32_t W, const float* mean3, const float* std3,
+                        int32_t precision, void* stream);
 /* ResNet stem tail in one pass: BatchNorm + ReLU + MaxPool2d(3,2,1), channels-last [B,H,W,C] -> [B,H/2,W/2,C]
  * (torchvision resnet50 children 1-3 inside ImageEncoder_cnn, models/image.py:50-56). Workspace as mv_bn_forward. */
 int mv_bn_relu_maxpool(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, const float* gamma, const float* beta,

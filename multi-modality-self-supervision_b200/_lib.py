@@ -100,6 +100,7 @@ SYMBOLS = {
     "mv_bn_workspace_floats": (_L, [_L, _I]),
     "mv_bn_forward": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _F, _F, _I, _I, _P, _L, _I, _P]),
     "mv_normalize_u8": (_I, [_P, _P, _L, _L, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _P]),
+    "mv_normalize_u8_s2d": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _P]),
     "mv_bn_relu_maxpool": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _F, _F, _I, _P, _L, _I, _P]),
     "mv_adamw": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _I, _P]),
 }

@@ -265,6 +265,44 @@ __global__ void __launch_bounds__(256) normalize_u8_kernel(const unsigned char* 
   }
 }
 
+// Space-to-depth form of the same transform, for the ResNet stem: the 7x7 / stride-2 / pad-3 convolution over 3 channels is
+// run as a 4x4 / stride-1 convolution over 2x2 pixel blocks (12 channels, zero-padded to 16) — a shape cuDNN's tensor-core
+// implicit GEMM handles well, where the 3-channel strided form runs at 0.39 TB/s (profiles/r01_launches_step_b64_summary.txt).
+//   dst: [B, H/2 + 3, W/2 + 3, 16] channels-last, block (by, bx) at row by + 2, column bx + 2 (two zero rows / columns in
+//        front, one behind: output pixel oy reads input rows 2oy - 4 .. 2oy + 3, i.e. blocks oy - 2 .. oy + 1);
+//        channel = c * 4 + dy * 2 + dx (torch.nn.functional.pixel_unshuffle order), channels 12 .. 15 are zero.
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_u8_s2d_kernel(const unsigned char* __restrict__ src, T* __restrict__ dst, int B, int H,
+                                                               int W, float m0, float m1, float m2, float s0, float s1, float s2) {
+  const int Hb = H >> 1, Wb = W >> 1, Hp = Hb + 3, Wp = Wb + 3;
+  const long total = static_cast<long>(B) * Hp * Wp;
+  const float mean[3] = {m0, m1, m2}, istd[3] = {s0, s1, s2};
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int px = static_cast<int>(i % Wp), py = static_cast<int>((i / Wp) % Hp), b = static_cast<int>(i / (static_cast<long>(Wp) * Hp));
+    const int by = py - 2, bx = px - 2;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;
+    if (by >= 0 && by < Hb && bx >= 0 && bx < Wb) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const unsigned char* pl = src + (static_cast<long>(b) * 3 + c) * H * W + static_cast<long>(2 * by) * W + 2 * bx;
+        const uchar2 r0 = *reinterpret_cast<const uchar2*>(pl), r1 = *reinterpret_cast<const uchar2*>(pl + W);
+        v[c * 4 + 0] = (static_cast<float>(r0.x) * (1.f / 255.f) - mean[c]) * istd[c];
+        v[c * 4 + 1] = (static_cast<float>(r0.y) * (1.f / 255.f) - mean[c]) * istd[c];
+        v[c * 4 + 2] = (static_cast<float>(r1.x) * (1.f / 255.f) - mean[c]) * istd[c];
+        v[c * 4 + 3] = (static_cast<float>(r1.y) * (1.f / 255.f) - mean[c]) * istd[c];
+      }
+    }
+    T* d = dst + i * 16;
+    float lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { lo[k] = v[k]; hi[k] = v[8 + k]; }
+    st8<T>(d, lo);
+    st8<T>(d + 8, hi);
+  }
+}
+
 // Stem tail fused in one pass: y = maxpool3x3/s2/p1( relu( x * scale + shift ) ) on channels-last [B, H, W, C] ->
 // [B, H/2, W/2, C].  Replaces BatchNorm-apply + ReLU + nn.MaxPool2d (models/image.py:50-56, torchvision stem).
 template <typename T>
@@ -322,6 +360,20 @@ int bn_relu_maxpool(const void* x, void* y, int B, int H, int W, int C, const fl
   if (blocks > cap) blocks = cap;
   if (f32) bn_relu_maxpool_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y), B, H, W, C, scale_shift);
   else bn_relu_maxpool_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), B, H, W, C, scale_shift);
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+
+int normalize_u8_s2d(const unsigned char* src, void* dst, int B, int H, int W, const float mean[3], const float stdv[3], int f32,
+                     cudaStream_t s) {
+  MV_REQUIRE(src && dst && B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "normalize_u8_s2d: need even H and W");
+  const long total = static_cast<long>(B) * (H / 2 + 3) * (W / 2 + 3);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (f32) normalize_u8_s2d_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<float*>(dst), B, H, W, mean[0], mean[1], mean[2],
+                                                                                  1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]);
+  else normalize_u8_s2d_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(src, static_cast<bf16*>(dst), B, H, W, mean[0], mean[1], mean[2],
+                                                                              1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]);
   MV_LAUNCH_CHECK();
   return 0;
 }

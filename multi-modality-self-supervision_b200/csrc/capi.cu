@@ -316,6 +316,12 @@ int mv_normalize_u8(const uint8_t* src, void* dst, int64_t B, int64_t hw, int32_
   return normalize_u8(src, dst, B, hw, cpad, mean3, std3, precision == MV_PREC_FP32, S(stream));
 }
 
+int mv_normalize_u8_s2d(const uint8_t* src, void* dst, int32_t B, int32_t H, int32_t W, const float* mean3, const float* std3,
+                        int32_t precision, void* stream) {
+  MV_REQUIRE(mean3 && std3, "mv_normalize_u8_s2d: null mean/std");
+  return normalize_u8_s2d(src, dst, B, H, W, mean3, std3, precision == MV_PREC_FP32, S(stream));
+}
+
 int mv_bn_relu_maxpool(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, int32_t training, float* workspace,
                        int64_t ws_floats, int32_t precision, void* stream) {

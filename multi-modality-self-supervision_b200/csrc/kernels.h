@@ -129,6 +129,10 @@ int bn_forward(const void* x, const void* resid, void* y, long rows, int C, cons
 // uint8 [B,3,H,W] -> normalised channels-last activation [B,H,W,3] (data/helper.py:20-27 ToTensor + Normalize)
 int normalize_u8(const unsigned char* src, void* dst, long B, long hw, int cpad, const float mean[3], const float stdv[3],
                  int f32, cudaStream_t s);
+// same transform, written as 2x2 space-to-depth blocks [B, H/2 + 3, W/2 + 3, 16] (zero border 2 front / 1 back, channel =
+// c*4 + dy*2 + dx, 12..15 zero): the input of the stem convolution in its 4x4 / stride-1 form (models/image.py)
+int normalize_u8_s2d(const unsigned char* src, void* dst, int B, int H, int W, const float mean[3], const float stdv[3], int f32,
+                     cudaStream_t s);
 // stem tail: BatchNorm (train/eval) + ReLU + MaxPool2d(3, 2, 1) in one apply pass, channels-last [B,H,W,C] -> [B,H/2,W/2,C]
 int bn_relu_maxpool(const void* x, void* y, int B, int H, int W, int C, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float momentum, float eps, int training, float* workspace, long ws_floats, int f32,

@@ -82,6 +82,36 @@ def test_uint8_images_are_normalised_on_the_device():
             assert float(out[:, 3:].abs().max()) == 0.0      # zero pad channels feed zero-padded stem weights
 
 
+def test_stem_space_to_depth_equals_the_strided_convolution():
+    """The stem runs as a 4x4 / stride-1 convolution over 2x2 pixel blocks (mv_normalize_u8_s2d + re-indexed weights):
+    same result as ToTensor + Normalize + Conv2d(3, 64, 7, stride 2, padding 3) of torchvision's ResNet-50 stem
+    (models/image.py:50-56), from uint8 pixels and from float images, incl. the zero border and the zero pad channels"""
+    import torch.nn.functional as F
+
+    import medvill_b200  # noqa: F401
+    from medvill_b200.models.image import TrunkExecutor
+
+    g = torch.Generator().manual_seed(3)
+    x8 = torch.randint(0, 256, (2, 3, 64, 96), dtype=torch.uint8, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.05
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    xf = (x8.float() / 255.0 - mean) / std
+    ref = F.conv2d(xf, w, None, 2, 3)
+    ex = TrunkExecutor.__new__(TrunkExecutor)
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        ex.act_dtype = dt
+        w2 = TrunkExecutor._stem_s2d_weight(w.to(dt)).cuda()
+        for src in (x8.cuda(), xf.cuda()):
+            blk = ex._stem_s2d_input(src)
+            assert blk.shape == (2, 16, 64 // 2 + 3, 96 // 2 + 3) and blk.is_contiguous(memory_format=torch.channels_last)
+            assert float(blk[:, 12:].abs().max()) == 0.0 and float(blk[:, :, :2].abs().max()) == 0.0 and float(blk[:, :, -1].abs().max()) == 0.0
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                out = F.conv2d(blk, w2, None, 1, 0)
+            assert out.shape == ref.shape
+            assert (out.float().cpu() - ref).abs().max() <= tol * ref.abs().max()
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
 def test_stem_tail_bn_relu_maxpool_vs_torch(dtype, tol):
     from medvill_b200 import _lib
