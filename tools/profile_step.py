@@ -24,7 +24,7 @@ margs = types.SimpleNamespace(img_hidden_sz=2048, embedding_size=768, hidden_siz
                               num_image_embeds=180, img_size=512, seq_len=253, lr=1e-5, precision="bf16", max_micro_batch=a.batch, seed=123)
 torch.manual_seed(0)
 model = CXRBERT(BertConfig.from_pretrained("bert-base-uncased"), margs).to(dev).train()
-b = synthetic_batch(a.batch, seed=123)
+b = synthetic_batch(a.batch, seed=123, image_dtype=torch.uint8)      # uint8 pixels on the wire, as bench.py
 d = {k: (v if k == "txt_labels" else v.to(dev)) for k, v in b.items()}
 step = lambda: model.pretrain_step(d["cls_tok"], d["input_ids"], d["txt_labels"], None, d["image"], d["segment"], d["is_aligned"],
                                    d["sep_tok"], mode=d["mode"], t_len=d["t_len"])
