@@ -12,6 +12,18 @@
 #include "tc05.cuh"
 #include "tmap.h"
 
+// Phase timeline (debug build `make tests/attn_timeline`, -DMV_ATTN_TIMELINE): two probe threads of one mid-grid CTA
+// record clock64() at the marks; compiled out otherwise.
+#ifdef MV_ATTN_TIMELINE
+#define TL_DECL(slot, cond)                                                                  \
+  unsigned long long* tl_p = (a.timeline && (cond)) ? a.timeline + (slot) * 64 : nullptr; \
+  int tl_n = 0
+#define TL_MARK() do { if (tl_p && tl_n < 64) tl_p[tl_n++] = clock64(); } while (0)
+#else
+#define TL_DECL(slot, cond) do { } while (0)
+#define TL_MARK() do { } while (0)
+#endif
+
 namespace mv {
 using namespace tc05;
 
@@ -296,7 +308,7 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 }
 
 struct BwdSmem {
-  uint64_t bar_kv, bar_q[2], bar_s, bar_o;
+  uint64_t bar_kv, bar_q[2], bar_s, bar_o, bar_pd, bar_stage;
   uint32_t tmem_base;
 };
 
@@ -308,11 +320,23 @@ __device__ __forceinline__ void store_pk16(uint8_t* sP, int r, int col, const ui
   *reinterpret_cast<uint4*>(half + sw128_off(r, j0 + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
-// Backward.  One CTA (512 threads: four per query row, each owning 32 of the 128 key columns) per (key tile, head,
-// sample); loops over the query tiles that can see this key tile, Q / dO double-buffered, the next tile's S / dP
-// products issued right behind the current tile's dV / dK / dQ products.
+// Backward.  One CTA per (key tile, head, sample) loops over the query tiles that can see this key tile.
+// 544 threads = 16 math warps (four threads per query row, each owning 32 of the 128 key columns) + 1 issuer warp (TMA
+// loads, tcgen05.mma, dQ TMA reduce-add).  The phases that used to run back to back inside the CTA — wait for S / dP,
+// softmax-backward math, the dV / dK / dQ products, dQ staging (~7 000 cycles per query tile, of which ~2 600 are math:
+// profiles/r01_attn_timeline.txt) — are software pipelined across query tiles:
+//   * P / dS staging is double buffered, so the products of tile i (which read it) run under the math of tile i+1;
+//   * S / dP of tile i+1 are issued BEFORE the products of tile i, so they are ready when the math warps come around;
+//   * dQ of tile i is drained from TMEM at the end of tile i+1's math and staged in the (by then dead) P buffer of
+//     tile i; the issuer sends it off as one fp32 TMA reduce-add per 32-column half.
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448)
-__global__ void __launch_bounds__(512, 1)
+// mbarriers (completion k belongs to the k-th ACTIVE query tile of this CTA, parity k & 1):
+//   bar_s      S / dP of tile k complete (tcgen05.commit)            math warps wait
+//   bar_pd     P / dS of tile k stored and dQ of tile k-1 staged     512 arrivals, issuer waits (one extra for the tail)
+//   bar_o      dV / dK / dQ products of tile k complete              math warps wait before draining dQ(k); issuer before
+//                                                                    re-using the Q / dO buffer
+//   bar_stage  the reduce-add of dQ(k) has read its staging          issuer arrives, math warps wait before tile k+2's stores
+__global__ void __launch_bounds__(544, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                      const __grid_constant__ CUtensorMap tmDQ, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -322,27 +346,25 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint8_t* sV = smem + TILE_BYTES;
   uint8_t* sQ = smem + 2 * TILE_BYTES;     // [2]
   uint8_t* sdO = smem + 4 * TILE_BYTES;    // [2]
-  uint8_t* sP = smem + 6 * TILE_BYTES;
-  uint8_t* sdS = sP + P_BYTES;
-  uint8_t* sDQ = sdS + P_BYTES;            // [2 halves of 32 fp32 columns][128 rows x 128 B]: dQ tile staged for TMA reduce-add
-  BwdSmem* sh = reinterpret_cast<BwdSmem*>(sDQ + P_BYTES);
+  uint8_t* sPD = smem + 6 * TILE_BYTES;    // [2] x { P 32 KB | dS 32 KB }; the P half doubles as the fp32 dQ staging of the same tile
+  BwdSmem* sh = reinterpret_cast<BwdSmem*>(sPD + 4 * P_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int lq = warp & 3, cq = warp >> 2;          // TMEM lane quarter, column quarter
-  const int r = lq * 32 + lane;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int L = a.L, H = a.nh * D, A = a.A;
   const int mode = a.mode[b], tl = a.t_len[b];
   const int k_lo = kt * TK, k_hi = min(k_lo + TK - 1, L - 1);
   const int n_q = (L + TQ - 1) / TQ;
   const int row0 = b * L;
+  TL_DECL(tid == 512 ? 2 : 3, kt == 1 && h == 3 && b == a.B / 2 && (tid == 512 || tid == 96));
+  TL_MARK();
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQ);
     mbar_init(&sh->bar_kv, 1); mbar_init(&sh->bar_q[0], 1); mbar_init(&sh->bar_q[1], 1);
-    mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1);
+    mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1); mbar_init(&sh->bar_pd, 512); mbar_init(&sh->bar_stage, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&sh->tmem_base, 512); tmem_relinquish(); }
@@ -350,67 +372,154 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  const uint32_t t_lane = tmem + (static_cast<uint32_t>(lq * 32) << 16);
 
   auto active = [&](int i) { return tile_any_allowed(mode, i * TQ, min(i * TQ + TQ - 1, L - 1), k_lo, k_hi, A, tl); };
   auto next_active = [&](int i) { ++i; while (i < n_q && !active(i)) ++i; return i; };
   int i = next_active(-1);
-
-  auto load_q = [&](int qi, int buf) {
-    mbar_expect_tx(&sh->bar_q[buf], 2 * TILE_BYTES);
-    tma_load_2d(&tmQKV, &sh->bar_q[buf], sQ + buf * TILE_BYTES, h * D, row0 + qi * TQ);
-    tma_load_2d(&tmDO, &sh->bar_q[buf], sdO + buf * TILE_BYTES, h * D, row0 + qi * TQ);
-  };
-  if (tid == 0 && i < n_q) {
-    mbar_expect_tx(&sh->bar_kv, 2 * TILE_BYTES);
-    tma_load_2d(&tmQKV, &sh->bar_kv, sK, H + h * D, row0 + k_lo);
-    tma_load_2d(&tmQKV, &sh->bar_kv, sV, 2 * H + h * D, row0 + k_lo);
-    load_q(i, 0);
-  }
+  const bool any = i < n_q;
 
   constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);     // S, dP : K-major x K-major
   constexpr uint32_t idesc_t = make_idesc_bf16(TK, D, 1, 1);      // dV, dK: P^T / dS^T (MN-major) x dO / Q (MN-major)
   constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D, 0, 1);      // dQ    : dS (K-major) x K (MN-major)
-  const float scale2 = 0.125f * kLog2e;
-  const bool any = i < n_q;
-  const int kc0 = k_lo + cq * 32;        // first key column of this thread's quarter
-  uint32_t it = 0;
 
-  auto issue_s_dp = [&](uint32_t buf) {
-    // called by all of warp 0 (uniform); one elected lane issues
-    const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO + buf * TILE_BYTES);
-    if (elect_one()) {
+  if (warp == 16) {
+    // ------------------------------ issuer warp: TMA, tcgen05.mma, dQ reduce-add (one elected lane) ------------------------------
+    auto load_q = [&](int qi, int buf) {
+      mbar_expect_tx(&sh->bar_q[buf], 2 * TILE_BYTES);
+      tma_load_2d(&tmQKV, &sh->bar_q[buf], sQ + buf * TILE_BYTES, h * D, row0 + qi * TQ);
+      tma_load_2d(&tmDO, &sh->bar_q[buf], sdO + buf * TILE_BYTES, h * D, row0 + qi * TQ);
+    };
+    auto issue_s_dp = [&](uint32_t buf) {
+      const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO + buf * TILE_BYTES);
+      if (elect_one()) {
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
-      for (int k = 0; k < D / 16; ++k)
-        umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
-      umma_commit(&sh->bar_s);
+        for (int k = 0; k < D / 16; ++k)
+          umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(&sh->bar_s);
+      }
+      __syncwarp();
+    };
+    int in = any ? next_active(i) : n_q;
+    if (any) {
+      if (lane == 0) {
+        mbar_expect_tx(&sh->bar_kv, 2 * TILE_BYTES);
+        tma_load_2d(&tmQKV, &sh->bar_kv, sK, H + h * D, row0 + k_lo);
+        tma_load_2d(&tmQKV, &sh->bar_kv, sV, 2 * H + h * D, row0 + k_lo);
+        load_q(i, 0);
+        if (in < n_q) load_q(in, 1);
+      }
+      __syncwarp();
+      mbar_wait(&sh->bar_kv, 0);
+      mbar_wait(&sh->bar_q[0], 0);
+      tc_fence_after();
+      issue_s_dp(0);
     }
-    __syncwarp();
-  };
+    int prev = -1;
+    uint32_t it = 0;
+    for (; i < n_q; ++it) {
+      const uint32_t buf = it & 1u;
+      const int inn = in < n_q ? next_active(in) : n_q;
+      TL_MARK();
+      mbar_wait(&sh->bar_pd, it & 1u);            // P / dS of this tile stored; dQ of the previous tile staged
+      tc_fence_after();
+      TL_MARK();
+      if (it > 0 && lane == 0) {                  // previous tile's dQ: one fp32 reduce-add per 32-column half
+        uint8_t* stg = sPD + (buf ^ 1u) * 2 * P_BYTES;
+        tma_reduce_add_2d(&tmDQ, stg, h * D, row0 + prev * TQ);
+        tma_reduce_add_2d(&tmDQ, stg + TILE_BYTES, h * D + 32, row0 + prev * TQ);
+        tma_commit_group();
+      }
+      __syncwarp();
+      if (in < n_q) {                             // next tile's S / dP first: ready when the math warps come around
+        mbar_wait(&sh->bar_q[buf ^ 1u], ((it + 1) >> 1) & 1u);
+        tc_fence_after();
+        issue_s_dp(buf ^ 1u);
+      }
+      {
+        const uint32_t pa = smem_u32(sPD + buf * 2 * P_BYTES), sa = pa + P_BYTES, qa = smem_u32(sQ + buf * TILE_BYTES),
+                       ka = smem_u32(sK), da = smem_u32(sdO + buf * TILE_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < TQ / 16; ++kk)  // dV[k,d] += sum_q P[q,k] dO[q,d]
+            umma_bf16(tmem + 256, make_smem_desc_sw128(pa + kk * 2048, TILE_BYTES, 1024),
+                      make_smem_desc_sw128(da + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < TQ / 16; ++kk)  // dK[k,d] += sum_q dS[q,k] Q[q,d]
+            umma_bf16(tmem + 320, make_smem_desc_sw128(sa + kk * 2048, TILE_BYTES, 1024),
+                      make_smem_desc_sw128(qa + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < TK / 16; ++kk)  // dQ[q,d] = sum_k dS[q,k] K[k,d]
+            umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+          umma_commit(&sh->bar_o);
+        }
+        __syncwarp();
+      }
+      if (it > 0) {                               // the reduce-add has read its staging: tile it+1 may overwrite that buffer
+        if (lane == 0) { tma_wait_group_read<0>(); mbar_arrive(&sh->bar_stage); }
+        __syncwarp();
+      }
+      TL_MARK();
+      if (inn < n_q) {                            // Q / dO two tiles ahead: this buffer is free once the products are complete
+        mbar_wait(&sh->bar_o, it & 1u);
+        if (lane == 0) load_q(inn, static_cast<int>(buf));
+        __syncwarp();
+      }
+      prev = i;
+      i = in;
+      in = inn;
+    }
+    if (any) {                                    // tail: the last tile's dQ
+      mbar_wait(&sh->bar_pd, it & 1u);
+      if (lane == 0) {
+        uint8_t* stg = sPD + ((it - 1) & 1u) * 2 * P_BYTES;
+        tma_reduce_add_2d(&tmDQ, stg, h * D, row0 + prev * TQ);
+        tma_reduce_add_2d(&tmDQ, stg + TILE_BYTES, h * D + 32, row0 + prev * TQ);
+        tma_commit_group();
+        tma_wait_group<0>();
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
+
+  // ------------------------------------------------ math warps (512 threads) ------------------------------------------------
+  const int lq = warp & 3, cq = warp >> 2;          // TMEM lane quarter, column quarter
+  const int r = lq * 32 + lane;
+  const uint32_t t_lane = tmem + (static_cast<uint32_t>(lq * 32) << 16);
+  const float scale2 = 0.125f * kLog2e;
   auto row_stats = [&](int qi, float& lse2_o, float& delta_o) {
     const int qq = qi * TQ + r;
     const long st = (static_cast<long>(b) * a.nh + h) * L + (qq < L ? qq : 0);
     lse2_o = qq < L ? a.lse[st] * kLog2e : 0.f;
     delta_o = qq < L ? a.delta[st] : 0.f;
   };
+  auto drain_dq = [&](uint32_t buf) {
+    // dQ tile (x 1/8) -> swizzled fp32 staging in the dead P buffer `buf`.  Rows past the sequence end hold exact zeros.
+    uint32_t v[16];
+    tmem_ld16(t_lane + 384 + cq * 16, v);
+    tmem_ld_wait();
+    uint8_t* half = sPD + buf * 2 * P_BYTES + (cq >> 1) * TILE_BYTES;
+#pragma unroll
+    for (int e = 0; e < 16; e += 4)
+      *reinterpret_cast<float4*>(half + sw128_off(r, (cq & 1) * 4 + (e >> 2))) =
+          make_float4(0.125f * __uint_as_float(v[e]), 0.125f * __uint_as_float(v[e + 1]), 0.125f * __uint_as_float(v[e + 2]),
+                      0.125f * __uint_as_float(v[e + 3]));
+  };
   float lse2 = 0.f, delta = 0.f;
   if (any) row_stats(i, lse2, delta);
-  if (warp == 0 && any) {
-    const int i1 = next_active(i);
-    if (lane == 0 && i1 < n_q) load_q(i1, 1);
-    __syncwarp();
-    mbar_wait(&sh->bar_kv, 0);
-    mbar_wait(&sh->bar_q[0], 0);
-    tc_fence_after();
-    issue_s_dp(0);
-  }
+  uint32_t it = 0;
 
   for (; i < n_q; ++it) {
     const int in = next_active(i);
-    const uint32_t ph = it & 1u, buf = it & 1u;
+    const uint32_t buf = it & 1u;
+    uint8_t* sP = sPD + buf * 2 * P_BYTES;
+    uint8_t* sdS = sP + P_BYTES;
     const int q_lo = i * TQ;
     const int q = q_lo + r;
     const bool q_ok = q < L;
@@ -420,8 +529,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mask_row_interval(mode, q_ok ? q : 0, A, tl, L, m_lo, m_hi);
     const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L) &&
                       (q_lo + TQ <= L);
-    mbar_wait(&sh->bar_s, ph);
+    TL_MARK();
+    mbar_wait(&sh->bar_s, it & 1u);
     tc_fence_after();
+    TL_MARK();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int col = cq * 32 + c * 16;                  // column inside the 128-wide tile
@@ -468,70 +579,34 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]);
         }
       }
+      // this staging buffer last held tile it-2: its products were waited for when dQ(it-2) was drained; the
+      // reduce-add of that dQ (staged in the P half) must have read it too
+      if (c == 0 && it >= 2) mbar_wait(&sh->bar_stage, (it - 2) & 1u);
       store_pk16(sP, r, col, pk);
       store_pk16(sdS, r, col, dk);
     }
-    if (tid == 0) tma_wait_group_read<0>();   // the previous tile's dQ reduce has finished reading its staging buffer
-    tc_fence_before();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp == 0) {      // warp-uniform; one elected lane issues the 24 MMAs
+    TL_MARK();
+    if (it > 0) {      // previous tile's products are complete (they ran under this tile's math): drain its dQ
+      mbar_wait(&sh->bar_o, (it - 1) & 1u);
       tc_fence_after();
-      const uint32_t pa = smem_u32(sP), sa = smem_u32(sdS), qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK),
-                     da = smem_u32(sdO + buf * TILE_BYTES);
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < TQ / 16; ++kk)  // dV[k,d] += sum_q P[q,k] dO[q,d]
-          umma_bf16(tmem + 256, make_smem_desc_sw128(pa + kk * 2048, TILE_BYTES, 1024),
-                    make_smem_desc_sw128(da + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
-#pragma unroll
-        for (int kk = 0; kk < TQ / 16; ++kk)  // dK[k,d] += sum_q dS[q,k] Q[q,d]
-          umma_bf16(tmem + 320, make_smem_desc_sw128(sa + kk * 2048, TILE_BYTES, 1024),
-                    make_smem_desc_sw128(qa + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
-#pragma unroll
-        for (int kk = 0; kk < TK / 16; ++kk)  // dQ[q,d] = sum_k dS[q,k] K[k,d]
-          umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
-        umma_commit(&sh->bar_o);
-      }
-      __syncwarp();
-      if (in < n_q) {                       // S / dP columns were released by the barrier above: start the next tile now
-        mbar_wait(&sh->bar_q[buf ^ 1u], ((it + 1) >> 1) & 1u);
-        tc_fence_after();
-        issue_s_dp(buf ^ 1u);
-      }
-    }
-    mbar_wait(&sh->bar_o, ph);
-    tc_fence_after();
-    if (tid == 0 && in < n_q) {             // Q / dO buffer `buf` is free (this tile's products are complete)
-      const int in2 = next_active(in);
-      if (in2 < n_q) load_q(in2, buf);
-    }
-    {
-      // dQ tile (x 1/8) -> swizzled fp32 staging -> ONE TMA reduce-add per 32-column half into the fp32 dQ accumulator
-      // (per-thread red.global ops were the bottleneck of this kernel).  Rows past the sequence end hold exact zeros.
-      uint32_t v[16];
-      tmem_ld16(t_lane + 384 + cq * 16, v);
-      tmem_ld_wait();
-      uint8_t* half = sDQ + (cq >> 1) * TILE_BYTES;
-#pragma unroll
-      for (int e = 0; e < 16; e += 4)
-        *reinterpret_cast<float4*>(half + sw128_off(r, (cq & 1) * 4 + (e >> 2))) =
-            make_float4(0.125f * __uint_as_float(v[e]), 0.125f * __uint_as_float(v[e + 1]), 0.125f * __uint_as_float(v[e + 2]),
-                        0.125f * __uint_as_float(v[e + 3]));
+      TL_MARK();
+      drain_dq(buf ^ 1u);
     }
     tc_fence_before();
     fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tma_reduce_add_2d(&tmDQ, sDQ, h * D, row0 + q_lo);
-      tma_reduce_add_2d(&tmDQ, sDQ + TILE_BYTES, h * D + 32, row0 + q_lo);
-      tma_commit_group();
-    }
-    tc_fence_before();
+    mbar_arrive(&sh->bar_pd);
+    TL_MARK();
     i = in;
     lse2 = lse2_n;
     delta = delta_n;
+  }
+  if (any) {           // tail: the last tile's dQ, then dV / dK
+    mbar_wait(&sh->bar_o, (it - 1) & 1u);
+    tc_fence_after();
+    drain_dq((it - 1) & 1u);
+    tc_fence_before();
+    fence_proxy_async_smem();
+    mbar_arrive(&sh->bar_pd);
   }
 
   // epilogue: dV, dK rows of this key tile.  tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only
@@ -564,14 +639,15 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
     }
   }
-  if (tid == 0) tma_wait_group<0>();
+  TL_MARK();
   tc_fence_before();
   __syncthreads();
+  TL_MARK();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 constexpr uint32_t kFwdSmem = 1024 + 3 * TILE_BYTES + P_BYTES + sizeof(FwdSmem) + 64;
-constexpr uint32_t kBwdSmem = 1024 + 6 * TILE_BYTES + 3 * P_BYTES + sizeof(BwdSmem) + 64;
+constexpr uint32_t kBwdSmem = 1024 + 6 * TILE_BYTES + 4 * P_BYTES + sizeof(BwdSmem) + 64;
 
 }  // namespace
 
@@ -615,7 +691,7 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
                                                                              static_cast<int>(rows), a.L, a.nh);
   MV_LAUNCH_CHECK();
   dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
-  attn_bwd_tc05_kernel<<<grid, 512, kBwdSmem, s>>>(tmQKV, tmDO, tmDQ, a);
+  attn_bwd_tc05_kernel<<<grid, 544, kBwdSmem, s>>>(tmQKV, tmDO, tmDQ, a);
   MV_LAUNCH_CHECK();
   attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
   MV_LAUNCH_CHECK();

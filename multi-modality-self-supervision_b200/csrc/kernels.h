@@ -152,6 +152,9 @@ struct AttnArgs {
   float* dq_acc;                     // [B*L, H] fp32 scratch (tcgen05 path; zeroed by the launcher)
   float* delta;                      // [B, nh, L] scratch: rowsum(dO * O)
   int drop_on; uint32_t drop_site; DropoutCfg drop;
+#ifdef MV_ATTN_TIMELINE
+  unsigned long long* timeline;      // [4][64] clock64() marks of one probe CTA (tests/attn_timeline build only)
+#endif
 };
 int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s);
 int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s);

@@ -225,8 +225,54 @@ static void perf(int drop) {
          f / iters, fl / (f / iters) / 1e9, b / iters, 2.5 * fl / (b / iters) / 1e9);
 }
 
+#ifdef MV_ATTN_TIMELINE
+// phase timeline of one mid-grid CTA under full load (bench shape): clock64() marks, printed as cycle deltas
+static void timeline(int drop) {
+  const int B = 64, nh = 12, L = 436, A = 182, H = nh * 64;
+  const size_t rows = (size_t)B * L;
+  std::vector<float> qkv(rows * 3 * H), dctx(rows * H);
+  for (auto& v : qkv) v = frand() * 2.f;
+  for (auto& v : dctx) v = frand();
+  std::vector<unsigned char> mode(B, MODE_BAR);
+  std::vector<int> tlen(B, 150);
+  bf16* d_qkv = dupload_bf16(qkv);
+  bf16* d_dctx = dupload_bf16(dctx);
+  unsigned char* d_mode = dupload(mode);
+  int* d_tlen = dupload(tlen);
+  void *d_ctx, *d_dqkv;
+  float *lse, *delta, *dq_acc;
+  unsigned long long* d_tl;
+  cudaMalloc(&d_ctx, rows * H * 2); cudaMalloc(&d_dqkv, rows * 3 * H * 2);
+  cudaMalloc(&lse, (size_t)B * nh * L * 4); cudaMalloc(&delta, (size_t)B * nh * L * 4); cudaMalloc(&dq_acc, rows * H * 4);
+  cudaMalloc(&d_tl, 256 * 8);
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.L = L; a.nh = nh; a.A = A; a.mode = d_mode; a.t_len = d_tlen; a.qkv = d_qkv; a.ctx = d_ctx; a.lse = lse;
+  a.dctx = d_dctx; a.dqkv = d_dqkv; a.dq_acc = dq_acc; a.delta = delta; a.drop_on = drop; a.drop_site = 3; a.drop = make_dropout(0.1f, 7);
+  attention_fwd_tc05(a, 0); attention_bwd_tc05(a, 0);
+  cudaMemset(d_tl, 0, 256 * 8);
+  a.timeline = d_tl;
+  attention_fwd_tc05(a, 0); attention_bwd_tc05(a, 0);
+  cudaDeviceSynchronize();
+  std::vector<unsigned long long> t(256);
+  cudaMemcpy(t.data(), d_tl, 256 * 8, cudaMemcpyDeviceToHost);
+  const char* names[4] = {"fwd slot 0", "fwd slot 1", "bwd issuer (tid 512)", "bwd math (tid 96)"};
+  for (int s = 0; s < 4; ++s) {
+    int n = 0;
+    while (n < 64 && t[s * 64 + n]) ++n;
+    if (!n) continue;
+    printf("  %s: cycle deltas between marks:", names[s]);
+    for (int i = 1; i < n; ++i) printf(" %llu", t[s * 64 + i] - t[s * 64 + i - 1]);
+    printf("  | total %llu cycles over %d marks\n", t[s * 64 + n - 1] - t[s * 64], n);
+  }
+}
+#endif
+
 int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "--perf")) { perf(argc > 2 ? atoi(argv[2]) : 1); return 0; }
+#ifdef MV_ATTN_TIMELINE
+  if (argc > 1 && !strcmp(argv[1], "--timeline")) { timeline(argc > 2 ? atoi(argv[2]) : 1); return 0; }
+#endif
   int fails = 0;
   printf("== fused masked attention ==\n");
   fails += run(4, 2, 436, 182, {MODE_BAR, MODE_S2S, MODE_NONCROSS, MODE_BIDIR}, {254, 254, 254, 57}, "L=436 all modes");
