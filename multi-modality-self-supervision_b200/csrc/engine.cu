@@ -469,7 +469,7 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
   eb.input_ids = reinterpret_cast<const int64_t*>(b.input_ids); eb.segment = reinterpret_cast<const int64_t*>(b.segment);
   eb.region_idx = reinterpret_cast<const int64_t*>(b.region_idx);
   eb.dsum = Q; eb.d_word = grads + lay.word; eb.d_pos = grads + lay.pos; eb.d_type = grads + lay.type; eb.d_proj = dproj; eb.pad_id = b.pad_lookup_grad ? -1 : 0;
-  eb.sep_pos = b.sep_position; eb.prefix_type = b.prefix_type;
+  eb.sep_pos = b.sep_position; eb.prefix_type = b.prefix_type; eb.TV = cfg.type_vocab;
   MV_TRY(embed_bwd_scatter(eb, f32, s));
   MV_TRY(colsum_add(dproj, H, B * N, H, grads + lay.img_b, f32, s));
   MV_TRY(linear_wgrad(dproj, H, feats_g, B * N, H, cfg.img_hidden, lay.img_w, s));

@@ -37,6 +37,7 @@ struct EmbedBwdArgs {
   int pad_id;                        // upstream nn.Embedding(padding_idx=0): lookup gradient of [PAD] is dropped
                                      // (-1: keep it — the vendored fine-tune BertEmbeddings has no padding_idx, model.py:228)
   int sep_pos = 0, prefix_type = 0;  // as EmbedArgs
+  int TV = 2;                        // token-type vocabulary size (rows of d_type), <= 8
 };
 int embed_bwd_scatter(const EmbedBwdArgs& a, int f32, cudaStream_t s);
 
