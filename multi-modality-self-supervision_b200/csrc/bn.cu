@@ -109,35 +109,49 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   }
 }
 
-// One CTA per 64-channel block, 1024 threads = 64 channels x 16 part lanes: coalesced reads of the partial table, Chan
-// merges in registers, a 16-way merge through shared memory; thread (channel, 0) produces scale / shift and updates the
-// running statistics (momentum, unbiased variance: PyTorch semantics).
+// One CTA per 64-channel block, 1024 threads = 64 channels x 16 part lanes, coalesced reads of the (L2-resident) partial
+// table.  The partials are combined in two division-free passes instead of a chain of Chan updates (whose two divisions
+// per merge made this kernel ~12 us on its single SM):  mean = sum n_i mean_i / N,  M2 = sum (M2_i + n_i (mean_i - mean)^2).
+// Thread (channel, 0) produces scale / shift and updates the running statistics (momentum, unbiased variance: PyTorch).
 __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            float* running_mean, float* running_var, float momentum, float eps,
                                                            int update_running, float* __restrict__ scale_shift /* [2][C] */) {
-  __shared__ float red[16][kBnCh][3];
+  __shared__ float red[16][kBnCh][2];
+  __shared__ float s_mean[kBnCh], s_n[kBnCh];
   const int ch = threadIdx.x & (kBnCh - 1), pl = threadIdx.x >> 6;
   const int c = blockIdx.x * kBnCh + ch;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
   const float* base = partial + static_cast<long>(blockIdx.x) * nparts * kBnCh * 3;
-  for (int p = pl; p < nparts; p += 16 * 8) {        // 8 partials (24 loads) in flight per thread, then 8 serial merges
-    float e[8][3];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int pp = p + 16 * u;
-      const float* src = base + (static_cast<long>(pp < nparts ? pp : p) * kBnCh + ch) * 3;
-      e[u][0] = pp < nparts ? src[0] : 0.f; e[u][1] = src[1]; e[u][2] = src[2];
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) chan_merge(n, mean, m2, e[u][0], e[u][1], e[u][2]);
+  float n = 0.f, sm = 0.f;
+  for (int p = pl; p < nparts; p += 16) {
+    const float* e = base + (static_cast<long>(p) * kBnCh + ch) * 3;
+    n += e[0];
+    sm = fmaf(e[0], e[1], sm);
   }
-  red[pl][ch][0] = n; red[pl][ch][1] = mean; red[pl][ch][2] = m2;
+  red[pl][ch][0] = n; red[pl][ch][1] = sm;
+  __syncthreads();
+  if (pl == 0) {
+    float N = 0.f, S = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { N += red[k][ch][0]; S += red[k][ch][1]; }
+    s_n[ch] = N;
+    s_mean[ch] = N > 0.f ? S / N : 0.f;
+  }
+  __syncthreads();
+  const float mean = s_mean[ch];
+  float m2 = 0.f;
+  for (int p = pl; p < nparts; p += 16) {
+    const float* e = base + (static_cast<long>(p) * kBnCh + ch) * 3;
+    const float d = e[1] - mean;
+    m2 += fmaf(e[0] * d, d, e[2]);
+  }
+  red[pl][ch][0] = m2;
   __syncthreads();
   if (pl != 0 || c >= C) return;
-  n = 0.f; mean = 0.f; m2 = 0.f;
+  m2 = 0.f;
 #pragma unroll
-  for (int k = 0; k < 16; ++k) chan_merge(n, mean, m2, red[k][ch][0], red[k][ch][1], red[k][ch][2]);
+  for (int k = 0; k < 16; ++k) m2 += red[k][ch][0];
+  n = s_n[ch];
   const float var = m2 / n;                      // biased: what normalisation uses
   const float invstd = rsqrtf(var + eps);
   const float sc = gamma[c] * invstd;
