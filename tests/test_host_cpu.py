@@ -90,3 +90,17 @@ def test_two_rank_global_normalisation_equals_single_process_batch():
     smp = np.concatenate([res[0][5], res[1][5]])
     single = tok.mean() + smp.mean()                                    # one process, batch of 8: CE means
     assert abs(res[0][3] - single) < 1e-5 and abs(res[1][3] - single) < 1e-5
+
+
+def test_mask_predicates_exhaustive_host_build():
+    """csrc/tests/mask_test (host-only build of mask.cuh): per-row intervals and the tile-skipping predicates of all six mask
+    modes (four pre-training, two fine-tune) against brute force over every (A, t_len) of small layouts"""
+    import subprocess
+
+    from medvill_b200 import _lib
+
+    exe = os.path.join(_lib.CSRC, "tests", "mask_test")
+    out = subprocess.run(["make", "-C", _lib.CSRC, "tests/mask_test"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "MASK TEST PASSED" in run.stdout, run.stdout[-2000:]
