@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MV_ABI_VERSION 1
+#define MV_ABI_VERSION 2   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries */
 
 enum { MV_PREC_BF16 = 0, MV_PREC_FP32 = 1 };          /* activation / GEMM-operand precision policy */
 enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3,      /* attention-mask modes */

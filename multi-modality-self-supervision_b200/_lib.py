@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmedvill_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
+ABI_VERSION = 2          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
 MV_PREC_BF16, MV_PREC_FP32 = 0, 1
 MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS, MODE_S2S_FT, MODE_BAR_FT = 0, 1, 2, 3, 4, 5
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_BIAS_TANH, EPI_RESID, EPI_DGELU = range(7)
@@ -131,7 +132,7 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if l.mv_abi_version() != 1:
+        if l.mv_abi_version() != ABI_VERSION:
             raise MedvillError("libmedvill_sm100.so ABI version mismatch")
         _lib = l
     return _lib

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libmedvill_sm100.so lacks %s" % s
     assert set(syms) == set(_lib.SYMBOLS), set(syms) ^ set(_lib.SYMBOLS)      # ctypes table mirrors the header
-    assert _lib.lib().mv_abi_version() == 1
+    assert _lib.lib().mv_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_layout_matches_reference_parameter_count():
@@ -74,3 +74,29 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert b"no CPU fallback" in _lib.lib().mv_last_error()
     with pytest.raises(m.MedvillError):
         m.PretrainEngine(m.EngineDims(), "cuda:0")
+
+
+def test_ctypes_struct_layouts_match_the_c_header(tmp_path):
+    """sizeof / offsetof of every struct in include/medvill_sm100.h, as gcc lays them out, equal the ctypes mirrors in
+    _lib.py (a silent mismatch here would shift every pointer of an mv_batch)"""
+    import ctypes as C
+    import subprocess
+
+    structs = {"mv_config": _lib.mv_config, "mv_layout": _lib.mv_layout, "mv_batch": _lib.mv_batch,
+               "mv_step_stats": _lib.mv_step_stats, "mv_gemm_desc": _lib.mv_gemm_desc}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "medvill_sm100.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('  printf("%s %%zu\\n", sizeof(%s));' % (name, name))
+        for field, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field, name, field))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-I", inc, "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == C.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got["%s.%s" % (name, field)]) == getattr(cls, field).offset, "%s.%s" % (name, field)
