@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from ..config import AutoConfig, BertConfig
+from ..data.prefetch import DevicePrefetcher
 from .cxrbert_origin import CXRBERT
 
 try:  # logging only; the reference requires wandb, here it is optional
@@ -84,7 +85,9 @@ class CXRBERT_Trainer():
         return cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok, mode, t_len
 
     def _iterate(self, loader, epoch, train):
-        it = enumerate(loader)
+        # host -> device staging of step i+1 overlaps step i (two persistent device buffer sets); txt_labels stay on the
+        # host: selecting the labelled rows is host integer work (replaces the blocking .to(device) calls of :95-104)
+        it = enumerate(DevicePrefetcher(loader, self.device, host_indices=(2, 8)))
         if tqdm is not None and self.rank == 0:
             it = tqdm.tqdm(it, desc=f'EP_:{epoch}', total=len(loader), bar_format='{l_bar}{r_bar}')
         losses, mlm_losses, itm_losses = [], [], []
