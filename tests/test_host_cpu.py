@@ -104,3 +104,27 @@ def test_mask_predicates_exhaustive_host_build():
     assert out.returncode == 0, out.stderr[-2000:]
     run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0 and "MASK TEST PASSED" in run.stdout, run.stdout[-2000:]
+
+
+def test_main_origin_parser_keeps_the_reference_command_line():
+    """every flag of the reference's main_origin.py:80-139 (fixture: oracle/make_golden_cli.py) exists with the same default;
+    `choices` are equal or a superset (the hard-coded checkpoint paths / model names of the reference are not enforced);
+    --output_path defaults to None here because the reference creates `output/<now>` at import time"""
+    import json
+
+    from medvill_b200.main_origin import build_parser
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    ref = json.load(open(os.path.join(here, "golden", "main_origin_flags.json")))
+    ours = {a.option_strings[0]: a for a in build_parser()._actions if a.option_strings and a.option_strings[0] != "-h"}
+    assert len(ref) == 42
+    for flag, spec in ref.items():
+        assert flag in ours, flag
+        act = ours[flag]
+        if flag != "--output_path":
+            assert act.default == spec.get("default"), (flag, act.default, spec.get("default"))
+        if "choices" in spec and act.choices is not None:
+            assert set(spec["choices"]) <= set(act.choices), flag
+        if spec.get("type") in ("int", "float", "str"):
+            assert act.type is {"int": int, "float": float, "str": str}[spec["type"]], flag
+    assert set(ours) - set(ref) == {"--precision", "--compact_masks", "--max_micro_batch"}
