@@ -15,6 +15,7 @@
 #include "engine.h"
 
 #include <dlfcn.h>
+#include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -75,6 +76,7 @@ struct NcclApi {
   void* lib = nullptr;
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, NcclUid, int) = nullptr;
+  int (*CommInitRankConfig)(void**, int, NcclUid, int, void*) = nullptr;   // optional (NCCL >= 2.14)
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -89,6 +91,7 @@ static NcclApi* load_nccl() {
   if (!lib) { set_error("cannot dlopen libnccl.so.2: %s", dlerror()); return nullptr; }
   api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
   api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(lib, "ncclCommInitRankConfig"));
   api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
   api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
   api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
@@ -108,33 +111,58 @@ int nccl_unique_id(uint8_t out[128]) {
   return 0;
 }
 
-// CTAs NCCL may use for the gradient all-reduces, and the SMs the persistent GEMMs leave free for them while buckets are
-// in flight.  Without this the all-reduce kernel's CTAs queue behind a 148-CTA persistent GEMM, take over some SMs when
-// it exits, and the NEXT GEMM's statically assigned tiles on those SMs wait for the whole collective (GEMM time per step
-// 13.6 -> 15.6 ms at 8 GPUs, profiles/r01_bench_n8.json).  447 MB of fp32 gradients per step need ~2 ms of NVLink time
-// spread over a 25 ms backward, so a few CTAs are plenty.
-static int comm_ctas() {
+// SMs the persistent GEMMs leave free for NCCL's CTAs while gradient buckets are in flight.  Without this the all-reduce
+// kernel's CTAs queue behind a 148-CTA persistent GEMM, take over some SMs when it exits, and the NEXT GEMM's statically
+// assigned tiles on those SMs wait for the whole collective (GEMM time per step 13.6 -> 15.6 ms at 8 GPUs; 14.8 ms with
+// the reservation, profiles/r01_bench_n8.json).  447 MB of fp32 gradients per step need ~2 ms of NVLink time spread over
+// a 25 ms backward, so a few CTAs are plenty.  MEDVILL_COMM_CTAS=n sets the reservation AND caps this communicator at n
+// CTAs through ncclConfig_t.maxCTAs; unset, the reservation is 8 and NCCL keeps its own channel count (the measured
+// configuration -- an NCCL_MAX_CTAS exported by the launcher is honoured by NCCL itself either way).
+static int comm_ctas(bool* explicit_cap = nullptr) {
   static int n = -1;
+  static bool from_env = false;
   if (n < 0) {
     const char* e = getenv("MEDVILL_COMM_CTAS");
-    n = e ? atoi(e) : 8;
+    from_env = e != nullptr && *e != 0;
+    n = from_env ? atoi(e) : 8;
     if (n < 1) n = 1;
     if (n > 32) n = 32;
   }
+  if (explicit_cap) *explicit_cap = from_env;
   return n;
 }
+
+// The prefix of ncclConfig_t that has been stable since NCCL 2.17 (nccl.h: ncclConfig_v21700).  NCCL copies `size` bytes,
+// checks the magic, and fills every field newer than `version` with its default, so this prefix is accepted by 2.17+.
+struct NcclConfigV21700 {
+  size_t size;
+  unsigned int magic;
+  unsigned int version;
+  int blocking;
+  int cgaClusterSize;
+  int minCTAs;
+  int maxCTAs;
+  const char* netName;
+};
 
 int engine_comm_init(Engine* e, const uint8_t id[128], int rank, int world) {
   NcclApi* n = load_nccl();
   if (!n) return -3;
-  char buf[16];
-  snprintf(buf, sizeof(buf), "%d", comm_ctas());
-  setenv("NCCL_MAX_CTAS", buf, 0);          // read by ncclCommInitRank below; an explicit user setting wins
   NcclUid uid;
   memcpy(uid.b, id, 128);
   void* comm = nullptr;
-  const int rc = n->CommInitRank(&comm, world, uid, rank);
-  MV_REQUIRE(rc == 0, "ncclCommInitRank failed: %s", n->GetErrorString ? n->GetErrorString(rc) : "?");
+  bool cap = false;
+  const int ctas = comm_ctas(&cap);
+  int rc;
+  if (cap && n->CommInitRankConfig) {
+    constexpr int kUndef = INT_MIN;                                  // NCCL_CONFIG_UNDEF_INT
+    NcclConfigV21700 cfg{sizeof(NcclConfigV21700), 0xcafebeefu, 21700u, kUndef, kUndef, kUndef, ctas, nullptr};
+    rc = n->CommInitRankConfig(&comm, world, uid, rank, &cfg);
+    MV_REQUIRE(rc == 0, "ncclCommInitRankConfig(maxCTAs=%d) failed: %s", ctas, n->GetErrorString ? n->GetErrorString(rc) : "?");
+  } else {
+    rc = n->CommInitRank(&comm, world, uid, rank);
+    MV_REQUIRE(rc == 0, "ncclCommInitRank failed: %s", n->GetErrorString ? n->GetErrorString(rc) : "?");
+  }
   e->nccl = n; e->comm = comm; e->rank = rank; e->world = world;
   MV_CUDA_CHECK(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
   MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
