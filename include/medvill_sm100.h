@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define MV_ABI_VERSION 2   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries */
+#define MV_ABI_VERSION 3   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries
+                              3: mv_batch.drop_worst_keep */
 
 enum { MV_PREC_BF16 = 0, MV_PREC_FP32 = 1 };          /* activation / GEMM-operand precision policy */
 enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3,      /* attention-mask modes */
@@ -98,6 +99,12 @@ typedef struct mv_batch {
                                /* so that a multi-rank step needs no host round trip for the loss normalisers             */
   const float* lab_weights;    /* [n_lab] optional per-row loss weights (fine-tune masked_weights, model.py:998-1005;  */
                                /* a position masked twice is one row of weight 2); NULL = 1                            */
+  int32_t drop_worst_keep;     /* > 0: Luo's drop-worst of the fine-tune loss (model.py:1003-1010): only the                */
+                               /* drop_worst_keep = int(B * (1 - drop_worst_ratio)) samples with the smallest weighted loss   */
+                               /* contribute (an integer, so the host rounds exactly as the reference's Python does);         */
+                               /* mlm_loss_sum then receives the NORMALISED loss (kept sum / (kept weights + 1e-5)) because   */
+                               /* the denominator depends on which samples were kept; inv_n_lab_global / global_counts[0]     */
+                               /* are not used.  0 = every sample counts                                                      */
 } mv_batch;
 
 typedef struct mv_step_stats {

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmedvill_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 2          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
+ABI_VERSION = 3          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
 MV_PREC_BF16, MV_PREC_FP32 = 0, 1
 MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS, MODE_S2S_FT, MODE_BAR_FT = 0, 1, 2, 3, 4, 5
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_BIAS_TANH, EPI_RESID, EPI_DGELU = range(7)
@@ -43,7 +43,7 @@ class mv_batch(C.Structure):
                 ("lab_labels", C.c_void_p), ("inv_n_lab_global", C.c_float), ("inv_batch_global", C.c_float),
                 ("dropout_seed", C.c_uint64), ("train", C.c_int32),
                 ("sep_position", C.c_int32), ("prefix_type", C.c_int32), ("pad_lookup_grad", C.c_int32),
-                ("global_counts", C.c_void_p), ("lab_weights", C.c_void_p)]
+                ("global_counts", C.c_void_p), ("lab_weights", C.c_void_p), ("drop_worst_keep", C.c_int32)]
 
 
 class mv_step_stats(C.Structure):

@@ -256,7 +256,7 @@ void Engine::destroy() {
   cudaDeviceSynchronize();
   for (void* p : allocs) cudaFree(p);
   allocs.clear();
-  void* mlm[] = {rows_h, t_pre, t_act, t_ln, dlogits, d_tln, d_tact, d_tpre, d_rows, logits, row_lse, row_argmax};
+  void* mlm[] = {rows_h, t_pre, t_act, t_ln, dlogits, d_tln, d_tact, d_tpre, d_rows, logits, row_lse, row_argmax, row_aux};
   for (void* p : mlm) if (p) cudaFree(p);
   if (stats_host) cudaFreeHost(stats_host);
   if (comm && nccl) nccl->CommDestroy(comm);
@@ -269,7 +269,8 @@ int Engine::ensure_mlm(int n) {
   if (n <= mlm_cap) return 0;
   MV_CUDA_CHECK(cudaDeviceSynchronize());
   void** ptrs[] = {&rows_h, &t_pre, &t_act, &t_ln, &dlogits, &d_tln, &d_tact, &d_tpre, &d_rows,
-                   reinterpret_cast<void**>(&logits), reinterpret_cast<void**>(&row_lse), reinterpret_cast<void**>(&row_argmax)};
+                   reinterpret_cast<void**>(&logits), reinterpret_cast<void**>(&row_lse), reinterpret_cast<void**>(&row_argmax),
+                   reinterpret_cast<void**>(&row_aux)};
   for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   int cap = mlm_cap * 2 > n ? mlm_cap * 2 : n;
   cap = (cap + 127) / 128 * 128;
@@ -282,6 +283,7 @@ int Engine::ensure_mlm(int n) {
   MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&logits), c * Vpad * sizeof(float)));
   MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&row_lse), c * sizeof(float)));
   MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&row_argmax), c * sizeof(int)));
+  MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&row_aux), (2 * c + 4) * sizeof(float)));
   mlm_cap = cap;
   return 0;
 }
@@ -395,11 +397,30 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     MV_TRY(linear_fwd(t_ln, n, H, lay.word, cfg.vocab, lay.mlm_bias, logits, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, Vpad));
     CeArgs ca;
     ca.n = n; ca.V = cfg.vocab; ca.ldv = Vpad; ca.logits = logits; ca.labels = reinterpret_cast<const int64_t*>(b.lab_labels);
-    ca.dlogits = b.train ? dlogits : nullptr; ca.gscale = b.inv_n_lab_global;
-    ca.count_dev = b.global_counts;
-    ca.loss_sum = &stats->mlm_loss_sum; ca.correct = &stats->mlm_correct; ca.row_lse = row_lse; ca.row_argmax = row_argmax;
-    ca.row_weight = b.lab_weights;
-    MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
+    ca.correct = &stats->mlm_correct; ca.row_lse = row_lse; ca.row_argmax = row_argmax;
+    if (b.drop_worst_keep > 0) {
+      // model.py:1003-1010: which samples count is only known once every row's loss is; so one loss-only CE pass, the
+      // selection, then the gradient pass with row_scale = kept * weight / (kept weights + 1e-5)
+      float* row_loss = row_aux; float* row_scale = row_aux + mlm_cap; float* scratch = row_aux + 2 * static_cast<size_t>(mlm_cap);
+      ca.dlogits = nullptr; ca.loss_sum = scratch; ca.row_weight = nullptr; ca.row_loss = row_loss;
+      MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
+      DropWorstArgs dw;
+      dw.n = n; dw.B = B; dw.L = L; dw.keep = b.drop_worst_keep;
+      dw.row_loss = row_loss; dw.row_weight = b.lab_weights; dw.rows = reinterpret_cast<const int64_t*>(b.lab_rows);
+      dw.row_scale = row_scale; dw.loss_sum = &stats->mlm_loss_sum;
+      MV_TRY(drop_worst_select(dw, s));
+      if (b.train) {
+        ca.dlogits = dlogits; ca.gscale = 1.f; ca.count_dev = nullptr; ca.row_weight = row_scale; ca.row_loss = nullptr;
+        ca.correct = reinterpret_cast<int*>(scratch + 1); ca.row_lse = nullptr; ca.row_argmax = nullptr;
+        MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
+      }
+    } else {
+      ca.dlogits = b.train ? dlogits : nullptr; ca.gscale = b.inv_n_lab_global;
+      ca.count_dev = b.global_counts;
+      ca.loss_sum = &stats->mlm_loss_sum;
+      ca.row_weight = b.lab_weights;
+      MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
+    }
   }
   return 0;
 }

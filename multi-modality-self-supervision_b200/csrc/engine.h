@@ -49,6 +49,7 @@ struct Engine {
   void *rows_h = nullptr, *t_pre = nullptr, *t_act = nullptr, *t_ln = nullptr, *dlogits = nullptr, *d_tln = nullptr,
        *d_tact = nullptr, *d_tpre = nullptr, *d_rows = nullptr;
   float* logits = nullptr; float* row_lse = nullptr; int* row_argmax = nullptr;
+  float* row_aux = nullptr;          // drop-worst: row_loss[cap] | row_scale[cap] | scratch {float loss, int correct}
 
   // data-parallel state
   NcclApi* nccl = nullptr; void* comm = nullptr; int rank = 0, world = 1;

@@ -79,8 +79,22 @@ struct CeArgs {
   int* correct;                      // += #(argmax == label)
   float* row_lse; int* row_argmax;   // optional per-row outputs (parity aids)
   const float* row_weight = nullptr; // optional [n] per-row loss weights (fine-tune masked_weights / multiplicities)
+  float* row_loss = nullptr;         // optional [n] out: unweighted lse_i - logit_i[label_i]
 };
 int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s);
+
+// Luo's drop-worst (fine-tune model.py:1003-1010): per-sample loss = sum of weight * row_loss over the sample's rows; the
+// `keep` samples with the smallest loss stay (ties: lower sample index first).  row_scale[i] = weight_i / (sum of kept
+// weights + 1e-5) for rows of kept samples, 0 otherwise; *loss_sum += sum of kept losses / that denominator.
+struct DropWorstArgs {
+  int n, B, L, keep;
+  const float* row_loss;             // [n]
+  const float* row_weight;           // [n] or nullptr (= 1)
+  const int64_t* rows;               // [n] flattened b * L + s
+  float* row_scale;                  // [n] out
+  float* loss_sum;
+};
+int drop_worst_select(const DropWorstArgs& a, cudaStream_t s);
 
 struct ItmArgs {
   int B, H;

@@ -72,7 +72,47 @@ __global__ void __launch_bounds__(256) mlm_ce_kernel(const CeArgs a) {
     if (s_arg == label) atomicAdd(a.correct, 1);
     if (a.row_lse) a.row_lse[row] = lse;
     if (a.row_argmax) a.row_argmax[row] = s_arg;
+    if (a.row_loss) a.row_loss[row] = lse - z[label];
   }
+}
+
+// One CTA; B <= 1024 samples.  Dynamic smem: loss[B], wsum[B], keep[B].
+__global__ void __launch_bounds__(1024) drop_worst_kernel(const DropWorstArgs a) {
+  extern __shared__ float dw_smem[];
+  float* s_loss = dw_smem;
+  float* s_w = dw_smem + a.B;
+  int* s_keep = reinterpret_cast<int*>(dw_smem + 2 * a.B);
+  __shared__ float s_acc[2];
+  const int tid = threadIdx.x;
+  for (int b = tid; b < a.B; b += blockDim.x) { s_loss[b] = 0.f; s_w[b] = 0.f; }
+  if (tid < 2) s_acc[tid] = 0.f;
+  __syncthreads();
+  for (int i = tid; i < a.n; i += blockDim.x) {
+    const int b = static_cast<int>(a.rows[i] / a.L);
+    const float w = a.row_weight ? a.row_weight[i] : 1.f;
+    atomicAdd(&s_loss[b], a.row_loss[i] * w);
+    atomicAdd(&s_w[b], w);
+  }
+  __syncthreads();
+  for (int b = tid; b < a.B; b += blockDim.x) {
+    const float mine = s_loss[b];
+    int rank = 0;
+    for (int j = 0; j < a.B; ++j) {
+      const float o = s_loss[j];
+      rank += (o < mine || (o == mine && j < b)) ? 1 : 0;
+    }
+    const int k = rank < a.keep ? 1 : 0;
+    s_keep[b] = k;
+    if (k) { atomicAdd(&s_acc[0], mine); atomicAdd(&s_acc[1], s_w[b]); }
+  }
+  __syncthreads();
+  const float inv = 1.f / (s_acc[1] + 1e-5f);
+  for (int i = tid; i < a.n; i += blockDim.x) {
+    const int b = static_cast<int>(a.rows[i] / a.L);
+    const float w = a.row_weight ? a.row_weight[i] : 1.f;
+    a.row_scale[i] = s_keep[b] ? w * inv : 0.f;
+  }
+  if (tid == 0) atomicAdd(a.loss_sum, s_acc[0] * inv);
 }
 
 // One CTA per sample.  logits = pooled . W^T + b (models/cxrbert_origin.py:164-173); CE mean over the batch
@@ -234,6 +274,15 @@ int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s) {
   if (a.n <= 0) return 0;
   MV_REQUIRE(a.logits && a.labels && a.loss_sum && a.correct, "mlm_ce: null argument");
   if (f32) mlm_ce_kernel<float><<<a.n, 256, 0, s>>>(a); else mlm_ce_kernel<bf16><<<a.n, 256, 0, s>>>(a);
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+
+int drop_worst_select(const DropWorstArgs& a, cudaStream_t s) {
+  MV_REQUIRE(a.n > 0 && a.B > 0 && a.B <= 1024 && a.L > 0, "drop_worst: needs 0 < B <= 1024 and labelled rows");
+  MV_REQUIRE(a.keep >= 1 && a.keep <= a.B, "drop_worst: int(B * (1 - ratio)) = %d samples kept of %d", a.keep, a.B);
+  MV_REQUIRE(a.row_loss && a.rows && a.row_scale && a.loss_sum, "drop_worst: null argument");
+  drop_worst_kernel<<<1, 1024, 3 * a.B * sizeof(float), s>>>(a);
   MV_LAUNCH_CHECK();
   return 0;
 }

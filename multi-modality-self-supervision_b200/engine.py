@@ -114,7 +114,7 @@ class Batch:
 
     def __init__(self, engine, cls_tok, input_ids, segment, sep_tok, mode, t_len, region_idx, feats, txt_labels=None,
                  is_aligned=None, lab_rows=None, lab_labels=None, n_lab_global=None, batch_global=None, seed=0, train=True,
-                 sep_position=0, prefix_type=0, pad_lookup_grad=False, lab_weights=None, global_counts=None):
+                 sep_position=0, prefix_type=0, pad_lookup_grad=False, lab_weights=None, global_counts=None, drop_worst_keep=0):
         d = engine.dims
         dev = engine.device
         i64 = lambda t: None if t is None else torch.as_tensor(t).to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
@@ -158,7 +158,8 @@ class Batch:
             lab_rows=ptr(self.lab_rows) if self.n_lab else None, lab_labels=ptr(self.lab_labels) if self.n_lab else None,
             inv_n_lab_global=1.0 / max(1, n_glob), inv_batch_global=1.0 / max(1, b_glob), dropout_seed=int(seed) & (2 ** 64 - 1),
             train=1 if train else 0, sep_position=int(sep_position), prefix_type=int(prefix_type),
-            pad_lookup_grad=1 if pad_lookup_grad else 0, global_counts=ptr(self.global_counts), lab_weights=ptr(self.lab_weights))
+            pad_lookup_grad=1 if pad_lookup_grad else 0, global_counts=ptr(self.global_counts), lab_weights=ptr(self.lab_weights),
+            drop_worst_keep=int(drop_worst_keep))
 
 
 _LIVE_ENGINES = []      # weak references; lets optimizers locate the engine that owns a parameter view

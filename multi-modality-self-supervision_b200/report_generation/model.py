@@ -97,7 +97,7 @@ class BertForPreTrainingLossMask(nn.Module):
         return torch.from_numpy(rows), torch.from_numpy(labels), torch.from_numpy(weights.astype(np.float32)), float(w.sum())
 
     def _run(self, img, input_ids, token_type_ids, attention_mask, masked_lm_labels, masked_pos, masked_weights, train, mode=None,
-             t_len=None, feats=None, backward=False):
+             t_len=None, feats=None, backward=False, drop_worst_ratio=0.0):
         cx, A = self._cxrbert, self.A
         input_ids = torch.as_tensor(input_ids)
         token_type_ids = torch.as_tensor(token_type_ids)
@@ -120,13 +120,24 @@ class BertForPreTrainingLossMask(nn.Module):
         eng.stats_reset()
         cap = eng.max_batch
         chunks = [(s, min(B, s + cap)) for s in range(0, B, cap)]
+        keep = 0
+        if drop_worst_ratio > 0:
+            # model.py:1006-1010 ranks the samples of the whole batch: it must be one micro-batch; the kept set and its
+            # denominator live on the device and mlm_loss_sum arrives normalised (mv_batch.drop_worst_keep)
+            keep = int(B * (1 - drop_worst_ratio))                       # :1007, the reference's own rounding
+            if len(chunks) > 1:
+                raise _lib.MedvillError("drop_worst_ratio > 0 needs the batch (%d) in one micro-batch: raise args.max_micro_batch (%d)"
+                                        % (B, cap))
+            if keep < 1:
+                raise _lib.MedvillError("drop_worst_ratio %.3f keeps no sample of a batch of %d" % (drop_worst_ratio, B))
+            denom = 1.0
         for ci, (s, e) in enumerate(chunks):
             sel = (rows >= s * self.L) & (rows < e * self.L)
             _, batch = cx._encode(input_ids[s:e, :1], input_ids[s:e, A:], None, token_type_ids[s:e, A:],
                                   None if img is None else img[s:e], input_ids[s:e, A - 1:A], train=train, mode=mode[s:e], t_len=t_len[s:e],
                                   feats=None if feats is None else feats[s:e], lab_rows=rows[sel] - s * self.L, lab_labels=labels[sel],
                                   lab_weights=weights[sel], n_lab_global=denom, batch_global=float(B), sep_position=A - 1,
-                                  prefix_type=ptype, pad_lookup_grad=True)
+                                  prefix_type=ptype, pad_lookup_grad=True, drop_worst_keep=keep)
             if backward:
                 eng.backward(batch, allreduce=False)
         return eng, denom
@@ -134,30 +145,28 @@ class BertForPreTrainingLossMask(nn.Module):
     def forward(self, img, _, input_ids, token_type_ids=None, attention_mask=None, masked_lm_labels=None, ans_labels=None,
                 masked_pos=None, masked_weights=None, task_idx=None, drop_worst_ratio=0.2, vqa_inference=False, ans_type=None,
                 mode=None, t_len=None, feats=None):
-        """-> (masked_lm_loss, dummy) as at model.py:968-1054.  `drop_worst_ratio` must be 0, which is what finetune.py
-        passes unless --max_drop_worst_ratio is set (:179, :441)."""
+        """-> (masked_lm_loss, dummy) as at model.py:968-1054, including Luo's drop-worst (:1003-1010; finetune.py passes
+        --max_drop_worst_ratio, default 0, after --drop_after epochs, :179-180,440)."""
         if vqa_inference or ans_labels is not None:
             raise NotImplementedError("VQA is out of scope of the B200 path")
-        if drop_worst_ratio not in (0, 0.0):
-            raise _lib.MedvillError("drop_worst_ratio > 0 (Luo's drop-worst, model.py:1006-1010) is not implemented on the B200 "
-                                    "path; finetune.py's default --max_drop_worst_ratio 0 is")
         eng, denom = self._run(img, input_ids, token_type_ids, attention_mask, masked_lm_labels, masked_pos, masked_weights,
-                               train=self.training, mode=mode, t_len=t_len, feats=feats)
+                               train=self.training, mode=mode, t_len=t_len, feats=feats, drop_worst_ratio=drop_worst_ratio)
         st = eng.read_stats()
         dev = eng.device
         return torch.tensor(st["mlm_loss_sum"] / denom, device=dev), torch.zeros(1, device=dev)
 
     def finetune_step(self, img, input_ids, token_type_ids, attention_mask, masked_lm_labels, masked_pos, masked_weights,
-                      optimizer=None, mode=None, t_len=None, feats=None, lazy=False):
+                      optimizer=None, mode=None, t_len=None, feats=None, lazy=False, drop_worst_ratio=0.0):
         """One training step of finetune.py:427-463: forward, masked-LM loss, backward, optimizer.step() + zero_grad()."""
         eng, denom = self._run(img, input_ids, token_type_ids, attention_mask, masked_lm_labels, masked_pos, masked_weights,
-                               train=True, mode=mode, t_len=t_len, feats=feats, backward=True)
+                               train=True, mode=mode, t_len=t_len, feats=feats, backward=True, drop_worst_ratio=drop_worst_ratio)
+        n_masked = float(torch.as_tensor(masked_weights).sum())
         if optimizer is not None:
             if getattr(optimizer, "_engine", None) is None:
                 optimizer._engine = eng
             optimizer.step()
             optimizer.zero_grad()
-        finish = lambda st: dict(loss=st["mlm_loss_sum"] / denom, mlm_correct=st["mlm_correct"], n_masked=denom - 1e-5)
+        finish = lambda st: dict(loss=st["mlm_loss_sum"] / denom, mlm_correct=st["mlm_correct"], n_masked=n_masked)
         if lazy:
             pending = eng.read_stats_async()
             return lambda: finish(pending())

@@ -132,10 +132,11 @@ def pin_preprocess(data_loader, cfg, out):
     print("[pin] Preprocess4Seq2seq: %d samples over 4 variants bit-exact (ids, segments, [L,L] masks, masked ids/pos/weights)" % n_checked)
 
 
-def pin_step(name, ref_model, ref_optim, cfg, B, seed, mode="s2s", bar=False, new_segment_ids=False):
+def pin_step(name, ref_model, ref_optim, cfg, B, seed, mode="s2s", bar=False, new_segment_ids=False, drop_worst_ratio=0):
     type_vocab = 6 if new_segment_ids else 2
     cfg = orc.Cfg(**dict(cfg.__dict__, type_vocab=type_vocab))
-    print("[pin] %s: B=%d L=%d mode=%s bar=%s new_segment_ids=%s" % (name, B, cfg.L, mode, bar, new_segment_ids))
+    print("[pin] %s: B=%d L=%d mode=%s bar=%s new_segment_ids=%s drop_worst_ratio=%s" % (name, B, cfg.L, mode, bar, new_segment_ids,
+                                                                                       drop_worst_ratio))
     params = orc.synth_params(cfg, seed=0)
     batch = orc.finetune_batch(cfg, B, seed, mode=mode, bar=bar, new_segment_ids=new_segment_ids)
     model = build_reference_model(ref_model, cfg, params, type_vocab)
@@ -143,7 +144,7 @@ def pin_step(name, ref_model, ref_optim, cfg, B, seed, mode="s2s", bar=False, ne
     for p in model.parameters():
         p.grad = None
     loss, _ = model(batch["image"], None, t("input_ids"), t("segment_ids"), t("input_mask"), t("masked_ids"), None,
-                    masked_pos=t("masked_pos"), masked_weights=t("masked_weights"), task_idx=None, drop_worst_ratio=0)
+                    masked_pos=t("masked_pos"), masked_weights=t("masked_weights"), task_idx=None, drop_worst_ratio=drop_worst_ratio)
     loss = loss.mean()                                                       # finetune.py:447
     loss.backward()
     inv = {ft_key(n): n for n in orc.trainable_names(cfg)}
@@ -158,7 +159,7 @@ def pin_step(name, ref_model, ref_optim, cfg, B, seed, mode="s2s", bar=False, ne
             ref_grads[inv[n]] = p.grad.detach().clone()
     assert sorted(no_grad) == sorted(n for n in orc.FT_NO_GRAD if n.startswith("enc.pooler")), no_grad
     keep = {}
-    mine = orc.finetune_loss_and_grads(params, batch, cfg, keep=keep)
+    mine = orc.finetune_loss_and_grads(params, batch, cfg, keep=keep, drop_worst_ratio=drop_worst_ratio)
     print("   loss ref=%.6f oracle=%.6f" % (float(loss), mine["loss"]))
     assert abs(float(loss) - mine["loss"]) < 2e-5 * max(1.0, abs(float(loss)))
     assert set(ref_grads) == set(orc.finetune_trainable_names(cfg))
@@ -196,7 +197,7 @@ def pin_step(name, ref_model, ref_optim, cfg, B, seed, mode="s2s", bar=False, ne
     names = sorted(ref_grads)
     rows = np.argwhere(batch["masked_weights"] > 0)
     out = dict(cfg=json.dumps(cfg.__dict__), B=B, seed=seed, mode_name=mode, bar=int(bar), new_segment_ids=int(new_segment_ids),
-               loss=float(loss), input_ids=batch["input_ids"], segment_ids=batch["segment_ids"], masked_ids=batch["masked_ids"],
+               loss=float(loss), drop_worst_ratio=float(drop_worst_ratio), kept_samples=np.sort(keep["kept"].numpy()), input_ids=batch["input_ids"], segment_ids=batch["segment_ids"], masked_ids=batch["masked_ids"],
                masked_pos=batch["masked_pos"], masked_weights=batch["masked_weights"], modes=batch["mode"], t_len=batch["t_len"],
                ce=keep["ce"].detach().numpy(), lab_rows=rows,
                lab_lse=torch.logsumexp(keep["logits"].detach().double(), -1).numpy()[rows[:, 0], rows[:, 1]],
@@ -224,6 +225,8 @@ def main():
     pin_step("finetune_tiny_bar", ref_model, ref_optim, tiny, B=3, seed=22, bar=True)
     pin_step("finetune_tiny_bi", ref_model, ref_optim, tiny, B=3, seed=23, mode="bi", new_segment_ids=False)
     pin_step("finetune_tiny_s2s_newseg", ref_model, ref_optim, tiny, B=3, seed=24, new_segment_ids=True)
+    # Luo's drop-worst (model.py:1006-1010): int(5 * 0.7) = 3 of 5 samples kept
+    pin_step("finetune_tiny_s2s_dropworst", ref_model, ref_optim, tiny, B=5, seed=26, drop_worst_ratio=0.3)
     if a.full:
         pin_step("finetune_base_s2s", ref_model, ref_optim, orc.finetune_cfg(), B=2, seed=25)
 

@@ -759,9 +759,10 @@ def finetune_embeddings(params, batch, cfg, feats=None):
     return torch.cat([img_out, txt_out], 1)
 
 
-def finetune_loss(params, batch, cfg, feats=None, keep=None):
-    """masked-LM loss of the fine-tune step (model.py:968-1054, drop_worst_ratio = 0 — finetune.py:179 default):
-    heads on the <= max_pred gathered rows, CE(reduction='none') * weights, sum / (sum(weights) + 1e-5)."""
+def finetune_loss(params, batch, cfg, feats=None, keep=None, drop_worst_ratio=0.0):
+    """masked-LM loss of the fine-tune step (model.py:968-1054): heads on the <= max_pred gathered rows,
+    CE(reduction='none') * weights, summed per sample; the int(B * (1 - drop_worst_ratio)) samples with the SMALLEST loss
+    are kept (:1006-1007; finetune.py:179,440 default ratio 0 keeps all) and their sum is divided by their weights + 1e-5."""
     x = finetune_embeddings(params, batch, cfg, feats=feats)
     ext = extended_mask(batch["input_mask"])
     for l in range(cfg.layers):
@@ -775,10 +776,10 @@ def finetune_loss(params, batch, cfg, feats=None, keep=None):
     ce = F.cross_entropy(logits.transpose(1, 2).float(), torch.as_tensor(batch["masked_ids"]), reduction="none")   # :1047-1048
     w = torch.as_tensor(batch["masked_weights"]).to(ce.dtype)
     per_sample = (ce * w).sum(-1)                                              # :1004-1005
-    kept, idx = torch.topk(per_sample, per_sample.shape[0], largest=False)     # :1007 (ratio 0: every sample kept)
+    kept, idx = torch.topk(per_sample, int(per_sample.shape[0] * (1 - drop_worst_ratio)), largest=False)     # :1007
     denom = w.sum(-1)[idx].sum() + 1e-5                                        # :1009
     if keep is not None:
-        keep["seq"], keep["logits"], keep["ce"] = x, logits, ce
+        keep["seq"], keep["logits"], keep["ce"], keep["kept"] = x, logits, ce, idx
     return (kept / denom).sum()                                                # :1010
 
 
@@ -791,12 +792,12 @@ def finetune_trainable_names(cfg):
     return [n for n in trainable_names(cfg) if n not in FT_NO_GRAD]
 
 
-def finetune_loss_and_grads(params, batch, cfg, feats=None, keep=None):
+def finetune_loss_and_grads(params, batch, cfg, feats=None, keep=None, drop_worst_ratio=0.0):
     names = finetune_trainable_names(cfg)
     leaf = dict(params)
     for n in names:
         leaf[n] = params[n].detach().clone().requires_grad_(True)
-    loss = finetune_loss(leaf, batch, cfg, feats=feats, keep=keep)
+    loss = finetune_loss(leaf, batch, cfg, feats=feats, keep=keep, drop_worst_ratio=drop_worst_ratio)
     loss.backward()
     grads = {n: (leaf[n].grad if leaf[n].grad is not None else torch.zeros_like(leaf[n])) for n in names}
     return dict(loss=loss.item(), grads=grads)

@@ -12,7 +12,7 @@ import torch
 from oracle import medvill_oracle as orc
 from tests.util import load_golden, summarize
 
-STEP_FIXTURES = ["finetune_tiny_s2s", "finetune_tiny_bar", "finetune_tiny_bi", "finetune_tiny_s2s_newseg"]
+STEP_FIXTURES = ["finetune_tiny_s2s", "finetune_tiny_bar", "finetune_tiny_bi", "finetune_tiny_s2s_newseg", "finetune_tiny_s2s_dropworst"]
 
 
 @pytest.mark.parametrize("name", STEP_FIXTURES)
@@ -24,8 +24,12 @@ def test_oracle_reproduces_reference_finetune_step(name):
         assert np.array_equal(batch[k], g[k]), k
     assert np.array_equal(batch["mode"], g["modes"]) and np.array_equal(batch["t_len"], g["t_len"])
     params = orc.synth_params(cfg, seed=0)
-    out = orc.finetune_loss_and_grads(params, batch, cfg)
+    ratio = float(g["drop_worst_ratio"]) if "drop_worst_ratio" in g else 0.0      # Luo's drop-worst, model.py:1003-1010
+    keep = {}
+    out = orc.finetune_loss_and_grads(params, batch, cfg, keep=keep, drop_worst_ratio=ratio)
     assert abs(out["loss"] - float(g["loss"])) < 2e-5 * abs(float(g["loss"]))
+    if ratio > 0:
+        assert np.array_equal(np.sort(keep["kept"].numpy()), g["kept_samples"]) and len(g["kept_samples"]) == int(int(g["B"]) * (1 - ratio))
     names = [str(n) for n in g["grad_names"]]
     assert names == sorted(orc.finetune_trainable_names(cfg))
     for i, n in enumerate(names):

@@ -52,7 +52,7 @@ def oracle_feats(params, batch):
         return torch.flatten(orc.resnet50_trunk(params, batch["image"]), start_dim=2).transpose(1, 2).contiguous()
 
 
-def run(name, precision, explicit_mask):
+def run(name, precision, explicit_mask, drop_worst_ratio=0.0):
     g, cfg = load_golden(name)
     batch = fixture_batch(g, cfg)
     params = orc.synth_params(cfg, seed=0)
@@ -61,7 +61,7 @@ def run(name, precision, explicit_mask):
     feats = oracle_feats(params, batch)         # the trunk is gated separately (tests/test_model_gpu.py); isolate the step
     kw = dict(feats=feats) if explicit_mask else dict(feats=feats, mode=t("mode"), t_len=t("t_len"))
     out = model.finetune_step(None, t("input_ids"), t("segment_ids"), t("input_mask") if explicit_mask else None, t("masked_ids"),
-                              t("masked_pos"), t("masked_weights"), optimizer=None, **kw)
+                              t("masked_pos"), t("masked_weights"), optimizer=None, drop_worst_ratio=drop_worst_ratio, **kw)
     torch.cuda.synchronize()
     return g, cfg, batch, params, model, out
 
@@ -136,9 +136,49 @@ def test_finetune_step_bert_base_L512(precision, tol):
                         masked_weights=t("masked_weights"), drop_worst_ratio=0, mode=t("mode"), t_len=t("t_len"),
                         feats=oracle_feats(params, batch))
     assert abs(float(loss) - out["loss"]) <= 1e-5 * abs(out["loss"]) and float(dummy) == 0.0
-    with pytest.raises(Exception):
+    with pytest.raises(Exception):                                     # int(2 * 0.1) = 0 samples kept
         model(None, None, t("input_ids"), t("segment_ids"), None, t("masked_ids"), masked_pos=t("masked_pos"),
-              masked_weights=t("masked_weights"), drop_worst_ratio=0.2, mode=t("mode"), t_len=t("t_len"))
+              masked_weights=t("masked_weights"), drop_worst_ratio=0.9, mode=t("mode"), t_len=t("t_len"),
+              feats=oracle_feats(params, batch))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_finetune_drop_worst(precision, tol):
+    """Luo's drop-worst (model.py:1003-1010) at ratio 0.3, B = 5: int(3.5) = 3 samples with the smallest loss kept; loss and
+    gradients vs the reference fixture / the oracle, and forward() reports the same loss"""
+    g, cfg, batch, params, model, out = run("finetune_tiny_s2s_dropworst", precision, explicit_mask=False,
+                                            drop_worst_ratio=float(load_golden("finetune_tiny_s2s_dropworst")[0]["drop_worst_ratio"]))
+    ratio = float(g["drop_worst_ratio"])
+    assert ratio == 0.3 and len(g["kept_samples"]) == 3
+    assert abs(out["loss"] - float(g["loss"])) <= tol * abs(float(g["loss"])), (out["loss"], float(g["loss"]))
+    eng = model.engine()
+    feats = oracle_feats(params, batch)
+    ref = orc.finetune_loss_and_grads(params, batch, cfg, feats=feats, drop_worst_ratio=ratio)["grads"]
+    full = orc.finetune_loss_and_grads(params, batch, cfg, feats=feats)["grads"]
+    scale = max(float(v.norm()) for v in ref.values())
+    n_checked = 0
+    for n, r in ref.items():
+        got = eng.view(n, eng.grads).float().cpu().flatten().double()
+        r = r.flatten().double()
+        if float(r.norm()) <= 1e-4 * scale:
+            continue
+        n_checked += 1
+        cos = float(got @ r / (got.norm() * r.norm()))
+        assert cos >= (0.9999 if precision == "fp32" else 0.95), "grad cosine %s: %.5f" % (n, cos)
+        if precision == "fp32":
+            assert abs(float(got.norm()) - float(r.norm())) <= 3e-3 * float(r.norm()), n
+    assert n_checked >= 30
+    # the dropped samples matter: the all-samples gradient of the decoder bias differs visibly from the kept-only one
+    n = "mlm.predictions.bias"
+    assert float((ref[n] - full[n]).norm()) > 0.05 * float(full[n].norm())
+    t = lambda k: torch.as_tensor(batch[k])
+    loss, _ = model(None, None, t("input_ids"), t("segment_ids"), None, t("masked_ids"), masked_pos=t("masked_pos"),
+                    masked_weights=t("masked_weights"), drop_worst_ratio=ratio, mode=t("mode"), t_len=t("t_len"), feats=feats)
+    assert abs(float(loss) - out["loss"]) <= 1e-5 * abs(out["loss"])
+    small = make_model(cfg, precision, params, max_batch=2)            # 5 samples in 3 micro-batches: cannot rank the batch
+    with pytest.raises(Exception, match="one micro-batch"):
+        small.finetune_step(None, t("input_ids"), t("segment_ids"), None, t("masked_ids"), t("masked_pos"), t("masked_weights"),
+                            mode=t("mode"), t_len=t("t_len"), feats=feats, drop_worst_ratio=ratio)
 
 
 @pytest.mark.parametrize("L,A", [(512, 258), (39, 18)])
