@@ -261,6 +261,27 @@ class PretrainEngine:
         check(lib().mv_adamw_step(self._h, lr, betas[0], betas[1], eps, weight_decay, self.step_count, grad_scale,
                                   stream_ptr(self.device)), "mv_adamw_step")
 
+    def optimizer_state_dict(self):
+        """Adam moments keyed by reference parameter name (torch.optim layout: step / exp_avg / exp_avg_sq), host tensors.
+        The reference saves no optimizer state (models/train_origin.py:254-266), so a restart there resets Adam."""
+        torch.cuda.synchronize(self.device)
+        return {"step": int(self.step_count),
+                "state": {n: {"exp_avg": self.view(n, self.adam_m).detach().cpu().clone(),
+                              "exp_avg_sq": self.view(n, self.adam_v).detach().cpu().clone()} for n in self.pmap}}
+
+    def load_optimizer_state_dict(self, sd):
+        missing = sorted(set(self.pmap) - set(sd["state"]))
+        if missing:
+            raise MedvillError("optimizer state lacks %d tensors, e.g. %s" % (len(missing), missing[:3]))
+        with torch.no_grad():
+            for n in self.pmap:
+                for key, arena in (("exp_avg", self.adam_m), ("exp_avg_sq", self.adam_v)):
+                    src, dst = sd["state"][n][key], self.view(n, arena)
+                    if tuple(src.shape) != tuple(dst.shape):
+                        raise MedvillError("optimizer state %s.%s has shape %s, expected %s" % (n, key, tuple(src.shape), tuple(dst.shape)))
+                    dst.copy_(src.to(device=self.device, dtype=torch.float32))
+        self.step_count = int(sd["step"])
+
     def bert_adam_step(self, lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01, max_grad_norm=1.0):
         """BertAdam.step (fine-tune; .../sc/pytorch_pretrained_bert/optimization.py:112-182); `lr` is the scheduled rate."""
         self.step_count += 1

@@ -421,6 +421,27 @@ class CXRBERT(nn.Module):
         torch.save({k: v.detach().cpu().clone() for k, v in self.state_dict().items()},
                    os.path.join(save_directory, "pytorch_model.bin"))
 
+    OPTIMIZER_FILE = "optimizer.pt"
+
+    def save_optimizer(self, save_directory):
+        """Adam moments + step count + the dropout step counter next to pytorch_model.bin (absent in
+        the reference, whose restart at train_origin.py:28-34 silently resets Adam)."""
+        os.makedirs(save_directory, exist_ok=True)
+        sd = self.engine().optimizer_state_dict()
+        sd["dropout_step"] = int(self._dropout_step)
+        torch.save(sd, os.path.join(save_directory, self.OPTIMIZER_FILE))
+
+    def load_optimizer(self, directory):
+        """Restore what save_optimizer wrote; call after .to(device).  Returns False when the checkpoint has no
+        optimizer file (e.g. one written by the reference)."""
+        path = os.path.join(directory, self.OPTIMIZER_FILE)
+        if not os.path.isfile(path):
+            return False
+        sd = torch.load(path, map_location="cpu")
+        self.engine().load_optimizer_state_dict(sd)
+        self._dropout_step = int(sd.get("dropout_step", 0))
+        return True
+
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, state_dict=None, config=None, args=None, **kw):
         if config is None:

@@ -59,6 +59,8 @@ class CXRBERT_Trainer():
             self.model = CXRBERT(config, args).to(self.device)
 
         eng = self.model.engine()
+        if args.weight_load and self.model.load_optimizer(args.pre_trained_model_path):
+            print('optimizer state restored (step %d)' % eng.step_count)
         if self.world > 1:
             def bcast(raw):
                 box = [raw]
@@ -142,5 +144,6 @@ class CXRBERT_Trainer():
         os.makedirs(save_path_per_ep, exist_ok=True)
         os.chmod(save_path_per_ep, 0o777)
         self.model.save_pretrained(save_path_per_ep)
+        self.model.save_optimizer(save_path_per_ep)      # Adam moments + step: a restart continues instead of resetting Adam
         print(f'EP: {epoch} Model saved on {save_path_per_ep}')
         os.chmod(save_path_per_ep + '/pytorch_model.bin', 0o777)

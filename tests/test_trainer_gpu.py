@@ -78,3 +78,27 @@ def test_trainer_trains_saves_and_reloads(tmp_path, compact):
     model2 = CXRBERT.from_pretrained(str(ck), config=bc, args=args)
     for k, v in model2.state_dict().items():
         assert torch.equal(v.cpu(), sd[k]), k
+    # restart (train_origin.py:28-34 with --weight_load) continues Adam instead of resetting it: moments, step count and
+    # the dropout counter come back from optimizer.pt
+    assert (ck / "optimizer.pt").is_file()
+    args2 = types.SimpleNamespace(**{**vars(args), "weight_load": True, "pre_trained_model_path": str(ck)})
+    eng = trainer.model.engine()
+    trainer2 = CXRBERT_Trainer(args2, train_dataloader=loader, test_dataloader=None)
+    eng2 = trainer2.model.engine()
+    assert eng2.step_count == eng.step_count == 12 and trainer2.model._dropout_step == trainer.model._dropout_step
+    assert torch.equal(eng2.adam_m, eng.adam_m) and torch.equal(eng2.adam_v, eng.adam_v) and torch.equal(eng2.params, eng.params)
+    assert float(eng2.adam_v.abs().max()) > 0
+    # the same next step from both: identical update up to the order of the fp32 split-K reductions
+    batch = next(iter(loader))
+    before = eng.params.clone()
+    outs = []
+    for tr in (trainer, trainer2):
+        torch.manual_seed(7)                                           # region sampling draws from the global CPU generator
+        tr.model.train()                                               # trainer.train() left the first model in eval mode
+        cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok, mode, t_len = tr._unpack(batch)
+        outs.append(tr.model.pretrain_step(cls_tok, input_ids, txt_labels, attn_masks, img, segment, is_aligned, sep_tok, lr=args.lr,
+                                           mode=mode, t_len=t_len))
+    torch.cuda.synchronize()
+    d1, d2 = eng.params - before, eng2.params - before
+    assert abs(outs[0]["loss"] - outs[1]["loss"]) <= 1e-3 * abs(outs[0]["loss"])
+    assert float((d1 - d2).norm()) <= 2e-2 * float(d1.norm()) and float(d1.norm()) > 0
