@@ -103,8 +103,9 @@ typedef struct mv_batch {
                                /* drop_worst_keep = int(B * (1 - drop_worst_ratio)) samples with the smallest weighted loss   */
                                /* contribute (an integer, so the host rounds exactly as the reference's Python does);         */
                                /* mlm_loss_sum then receives the NORMALISED loss (kept sum / (kept weights + 1e-5)) because   */
-                               /* the denominator depends on which samples were kept; inv_n_lab_global / global_counts[0]     */
-                               /* are not used.  0 = every sample counts                                                      */
+                               /* the denominator depends on which samples were kept; global_counts[0] is not used and        */
+                               /* inv_n_lab_global is a plain multiplier on the gradient (1, or 1 / world when ranks average   */
+                               /* their gradients as DistributedDataParallel does).  0 = every sample counts                  */
 } mv_batch;
 
 typedef struct mv_step_stats {

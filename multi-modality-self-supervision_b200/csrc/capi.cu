@@ -107,12 +107,25 @@ int mv_adamw_step(mv_handle* h, float lr, float beta1, float beta2, float eps, f
   MV_CHECK_HANDLE(h);
   Engine& e = h->eng;
   MV_REQUIRE(e.params && e.grads && e.adam_m && e.adam_v, "mv_adamw_step: arenas (incl. Adam moments) not bound");
-  if (engine_comm_sync(&e, S(stream))) return -2;
   AdamArgs a;
-  a.n = e.lay.total; a.p = e.params; a.g = e.grads; a.m = e.adam_m; a.v = e.adam_v; a.shadow = e.shadow;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.step = step;
   a.grad_scale = grad_scale; a.zero_grad = 1;
-  return adamw_step(a, S(stream));
+  auto range = [&](int64_t off, int64_t n) {
+    a.n = n; a.p = e.params + off; a.g = e.grads + off; a.m = e.adam_m + off; a.v = e.adam_v + off;
+    a.shadow = e.shadow ? e.shadow + off : nullptr;
+    return adamw_step(a, S(stream));
+  };
+  const int64_t head = e.lay.layer0;          // [0, layer0) = the embeddings bucket, reduced last (bucket_plan)
+  if (e.comm_pending && e.mid_recorded && head % 4 == 0 && head > 0) {
+    // the last bucket's all-reduce (word embeddings: ~100 MB) is still in flight when backward ends: update the layers
+    // and heads behind the mid event while it finishes, then the embeddings
+    MV_CUDA_CHECK(cudaStreamWaitEvent(S(stream), e.ev_mid, 0));
+    if (range(head, e.lay.total - head)) return -2;
+    if (engine_comm_sync(&e, S(stream))) return -2;
+    return range(0, head);
+  }
+  if (engine_comm_sync(&e, S(stream))) return -2;
+  return range(0, e.lay.total);
 }
 
 // BertAdam.step of the report-generation fine-tune (optimization.py:112-182): `lr` is the already scheduled rate

@@ -167,6 +167,7 @@ int engine_comm_init(Engine* e, const uint8_t id[128], int rank, int world) {
   MV_CUDA_CHECK(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
   MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
   MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+  MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_mid, cudaEventDisableTiming));
   return 0;
 }
 
@@ -183,6 +184,7 @@ int engine_comm_sync(Engine* e, cudaStream_t s) {
     MV_CUDA_CHECK(cudaEventRecord(e->ev_done, e->comm_stream));
     MV_CUDA_CHECK(cudaStreamWaitEvent(s, e->ev_done, 0));
     e->comm_pending = false;
+    e->mid_recorded = false;
   }
   return 0;
 }
@@ -263,6 +265,7 @@ void Engine::destroy() {
   if (comm_stream) cudaStreamDestroy(comm_stream);
   if (ev_ready) cudaEventDestroy(ev_ready);
   if (ev_done) cudaEventDestroy(ev_done);
+  if (ev_mid) cudaEventDestroy(ev_mid);
 }
 
 int Engine::ensure_mlm(int n) {
@@ -410,7 +413,7 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
       dw.row_scale = row_scale; dw.loss_sum = &stats->mlm_loss_sum;
       MV_TRY(drop_worst_select(dw, s));
       if (b.train) {
-        ca.dlogits = dlogits; ca.gscale = 1.f; ca.count_dev = nullptr; ca.row_weight = row_scale; ca.row_loss = nullptr;
+        ca.dlogits = dlogits; ca.gscale = b.inv_n_lab_global; ca.count_dev = nullptr; ca.row_weight = row_scale; ca.row_loss = nullptr;
         ca.correct = reinterpret_cast<int*>(scratch + 1); ca.row_lse = nullptr; ca.row_argmax = nullptr;
         MV_TRY(mlm_ce_fwd_bwd(ca, f32, s));
       }
@@ -433,6 +436,10 @@ int Engine::bucket_done(size_t idx, int allreduce, cudaStream_t s) {
   MV_CUDA_CHECK(cudaStreamWaitEvent(comm_stream, ev_ready, 0));
   MV_TRY(engine_allreduce(this, grads + bk.offset, bk.count, comm_stream));
   comm_pending = true;
+  if (idx + 2 == buckets.size()) {          // everything except the last bucket (embeddings) is now queued on comm_stream
+    MV_CUDA_CHECK(cudaEventRecord(ev_mid, comm_stream));
+    mid_recorded = true;
+  }
   set_reserved_sms(comm_ctas());            // GEMMs launched from now on leave room for the collective's CTAs
   return 0;
 }

@@ -54,6 +54,7 @@ struct Engine {
   // data-parallel state
   NcclApi* nccl = nullptr; void* comm = nullptr; int rank = 0, world = 1;
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool comm_pending = false;
+  cudaEvent_t ev_mid = nullptr; bool mid_recorded = false;   // all buckets but the last (embeddings) have been reduced
   std::vector<Bucket> buckets;
 
   // optional per-kernel-family timing (CUDA events on the launch stream): tag 0 = tcgen05/SIMT GEMM, 1 = attention fwd,

@@ -275,6 +275,29 @@ class CXRBERT(nn.Module):
             self._engine = eng
         return self._engine
 
+    def init_distributed(self):
+        """One process per GPU under an initialised torch.distributed group: hand rank 0's NCCL unique id to the engine (it
+        all-reduces gradient buckets on its own stream while backward runs) and make the replicas identical — rank 0's
+        weights win, as nn.DataParallel broadcast them every step (models/train_origin.py:53-55).  Returns the world size."""
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 1
+        eng = self.engine()
+        if eng.world == 1:
+            def bcast(raw):
+                box = [raw]
+                dist.broadcast_object_list(box, src=0)
+                return box[0]
+            eng.comm_init(dist.get_rank(), dist.get_world_size(), bcast)
+            if dist.get_backend() == "nccl":
+                dist.broadcast(eng.params, src=0)
+            else:                                   # a CPU-only group (gloo) carries the id; weights go through the host
+                host = eng.params.cpu()
+                dist.broadcast(host, src=0)
+                eng.params.copy_(host)
+            self.sync_params()
+        return eng.world
+
     def sync_params(self):
         """Call after mutating parameters from Python (e.g. load_state_dict): refreshes the bf16 GEMM-operand shadow."""
         if self._engine is not None:

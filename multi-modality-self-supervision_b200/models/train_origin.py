@@ -62,14 +62,7 @@ class CXRBERT_Trainer():
         if args.weight_load and self.model.load_optimizer(args.pre_trained_model_path):
             print('optimizer state restored (step %d)' % eng.step_count)
         if self.world > 1:
-            def bcast(raw):
-                box = [raw]
-                torch.distributed.broadcast_object_list(box, src=0)
-                return box[0]
-            eng.comm_init(self.rank, self.world, bcast)
-            # identical replicas: rank 0's weights win (DataParallel broadcast them every step, train_origin.py:55)
-            torch.distributed.broadcast(eng.params, src=0)
-            self.model.sync_params()
+            self.model.init_distributed()
             print("Using %d GPUS for BERT" % self.world)
 
         self.train_data = train_dataloader

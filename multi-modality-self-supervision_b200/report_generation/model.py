@@ -81,6 +81,11 @@ class BertForPreTrainingLossMask(nn.Module):
     def engine(self, min_batch=1):
         return self._cxrbert.engine(min_batch)
 
+    def init_distributed(self):
+        """finetune.py:370-376 wraps the model in DistributedDataParallel; here one call joins the engine's NCCL
+        communicator (one process per GPU) and `finetune_step` averages the ranks' gradients as DDP does."""
+        return self._cxrbert.init_distributed()
+
     # -- batch assembly ------------------------------------------------------------------------------------------------
     def _labelled_rows(self, masked_pos, masked_ids, masked_weights):
         """(lab_rows, lab_labels, lab_weights, sum_w): one row per DISTINCT masked position with weight > 0; a position
@@ -131,15 +136,18 @@ class BertForPreTrainingLossMask(nn.Module):
             if keep < 1:
                 raise _lib.MedvillError("drop_worst_ratio %.3f keeps no sample of a batch of %d" % (drop_worst_ratio, B))
             denom = 1.0
+        # DistributedDataParallel semantics (finetune.py:376): every rank normalises by its OWN denominator and the gradients
+        # are averaged; folded into the loss scale so that the engine's SUM all-reduce needs no post-hoc division
+        world = eng.world
         for ci, (s, e) in enumerate(chunks):
             sel = (rows >= s * self.L) & (rows < e * self.L)
             _, batch = cx._encode(input_ids[s:e, :1], input_ids[s:e, A:], None, token_type_ids[s:e, A:],
                                   None if img is None else img[s:e], input_ids[s:e, A - 1:A], train=train, mode=mode[s:e], t_len=t_len[s:e],
                                   feats=None if feats is None else feats[s:e], lab_rows=rows[sel] - s * self.L, lab_labels=labels[sel],
-                                  lab_weights=weights[sel], n_lab_global=denom, batch_global=float(B), sep_position=A - 1,
+                                  lab_weights=weights[sel], n_lab_global=denom * world, batch_global=float(B), sep_position=A - 1,
                                   prefix_type=ptype, pad_lookup_grad=True, drop_worst_keep=keep)
             if backward:
-                eng.backward(batch, allreduce=False)
+                eng.backward(batch, allreduce=(world > 1 and ci == len(chunks) - 1))
         return eng, denom
 
     def forward(self, img, _, input_ids, token_type_ids=None, attention_mask=None, masked_lm_labels=None, ans_labels=None,
