@@ -97,7 +97,17 @@ class BertAdam:
         """fused into step() (mv_bert_adam_step writes zeros behind the gradients it consumed)"""
 
     def state_dict(self):
-        return {"state": dict(self.state), "lr": self.lr, "warmup": self.warmup, "t_total": self.t_total, "schedule": self.schedule}
+        """What finetune.py:484-486 writes to optim.{epoch}.bin: the schedule position plus, when the engine exists, the Adam
+        moments keyed by parameter name (engine.optimizer_state_dict)."""
+        sd = {"state": dict(self.state), "lr": self.lr, "warmup": self.warmup, "t_total": self.t_total, "schedule": self.schedule}
+        try:
+            sd["moments"] = self._find_engine().optimizer_state_dict()
+        except MedvillError:
+            pass                                   # no engine yet: nothing has been stepped, the moments are zero
+        return sd
 
     def load_state_dict(self, sd):
+        """finetune.py:396-402 (recover_step): restores the schedule position and the moments."""
         self.state = dict(sd.get("state", {"step": 0}))
+        if "moments" in sd:
+            self._find_engine().load_optimizer_state_dict(sd["moments"])

@@ -100,6 +100,16 @@ def test_finetune_step_fp32_matches_reference(name):
         assert np.abs(got[3:] - ref[3:]).max() <= 2e-2 * np.abs(ref[3:]).max() + 1e-8, n
     for n in orc.FT_NO_GRAD:                                           # BertAdam skips p.grad is None: not even weight decay
         assert torch.equal(eng.view(n), before[n]), n
+    # optimizer checkpoint (finetune.py:484-486 / :396-402): schedule position + Adam moments survive a round trip
+    sd = opt.state_dict()
+    m_ref, v_ref = eng.adam_m.clone(), eng.adam_v.clone()
+    assert float(v_ref.abs().max()) > 0 and sd["state"]["step"] == 3
+    eng.adam_m.zero_(); eng.adam_v.zero_()
+    opt2 = BertAdam([{"params": [p for p in model.parameters()], "weight_decay": 0.01}], lr=float(g["adam_lr"]),
+                    warmup=float(g["adam_warmup"]), t_total=int(g["adam_t_total"]))
+    opt2.load_state_dict(sd)
+    assert opt2.state["step"] == 3 and opt2.scheduled_lr() == opt.scheduled_lr()
+    assert torch.equal(eng.adam_m, m_ref) and torch.equal(eng.adam_v, v_ref)
 
 
 @pytest.mark.parametrize("name", TINY)
