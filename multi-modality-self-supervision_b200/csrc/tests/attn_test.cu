@@ -225,6 +225,56 @@ static void perf(int drop) {
          f / iters, fl / (f / iters) / 1e9, b / iters, 2.5 * fl / (b / iters) / 1e9);
 }
 
+// Reproducibility of the tcgen05 kernels at the bench shape: the same launches twice, outputs compared bit for bit.  ctx, lse,
+// dK and dV are owned by exactly one CTA each and must be identical; dQ is summed over key tiles by fp32 TMA reduce-adds in
+// arrival order, so only its fp32 accumulator may differ (and the few bf16 values that land on the other side of a rounding
+// boundary).  A difference anywhere else would mean a race in the pipelined backward.
+static int repro(int drop) {
+  const int B = 64, nh = 12, L = 436, A = 182, H = nh * 64;
+  const size_t rows = (size_t)B * L;
+  std::vector<float> qkv(rows * 3 * H), dctx(rows * H);
+  for (auto& v : qkv) v = frand() * 2.f;
+  for (auto& v : dctx) v = frand();
+  std::vector<unsigned char> mode(B, MODE_BAR);
+  std::vector<int> tlen(B, 150);
+  bf16* d_qkv = dupload_bf16(qkv);
+  bf16* d_dctx = dupload_bf16(dctx);
+  unsigned char* d_mode = dupload(mode);
+  int* d_tlen = dupload(tlen);
+  void *d_ctx, *d_dqkv;
+  float *lse, *delta, *dq_acc;
+  cudaMalloc(&d_ctx, rows * H * 2); cudaMalloc(&d_dqkv, rows * 3 * H * 2);
+  cudaMalloc(&lse, (size_t)B * nh * L * 4); cudaMalloc(&delta, (size_t)B * nh * L * 4); cudaMalloc(&dq_acc, rows * H * 4);
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.L = L; a.nh = nh; a.A = A; a.mode = d_mode; a.t_len = d_tlen; a.qkv = d_qkv; a.ctx = d_ctx; a.lse = lse;
+  a.dctx = d_dctx; a.dqkv = d_dqkv; a.dq_acc = dq_acc; a.delta = delta; a.drop_on = drop; a.drop_site = 3; a.drop = make_dropout(0.1f, 7);
+  std::vector<unsigned short> ctx[2], dqkv[2];
+  std::vector<float> l[2];
+  for (int r = 0; r < 2; ++r) {
+    cudaMemset(d_ctx, 0xff, rows * H * 2); cudaMemset(d_dqkv, 0xff, rows * 3 * H * 2);
+    if (attention_fwd_tc05(a, 0) || attention_bwd_tc05(a, 0)) { printf("  launch failed: %s\n", last_error()); return 1; }
+    cudaDeviceSynchronize();
+    ctx[r].resize(rows * H); dqkv[r].resize(rows * 3 * H);
+    cudaMemcpy(ctx[r].data(), d_ctx, rows * H * 2, cudaMemcpyDeviceToHost);
+    cudaMemcpy(dqkv[r].data(), d_dqkv, rows * 3 * H * 2, cudaMemcpyDeviceToHost);
+    l[r] = ddownload(lse, (size_t)B * nh * L);
+  }
+  size_t d_ctx_n = 0, d_lse_n = 0, d_q = 0, d_k = 0, d_v = 0;
+  for (size_t i = 0; i < rows * H; ++i) d_ctx_n += ctx[0][i] != ctx[1][i];
+  for (size_t i = 0; i < l[0].size(); ++i) d_lse_n += memcmp(&l[0][i], &l[1][i], 4) != 0;
+  for (size_t r = 0; r < rows; ++r)
+    for (int c = 0; c < 3 * H; ++c) {
+      const bool ne = dqkv[0][r * 3 * H + c] != dqkv[1][r * 3 * H + c];
+      (c < H ? d_q : (c < 2 * H ? d_k : d_v)) += ne;
+    }
+  printf("  repro (dropout=%d): differing elements  ctx %zu  lse %zu  dQ %zu (of %zu, fp32 reduce order)  dK %zu  dV %zu\n", drop,
+         d_ctx_n, d_lse_n, d_q, rows * H, d_k, d_v);
+  const bool ok = d_ctx_n == 0 && d_lse_n == 0 && d_k == 0 && d_v == 0 && d_q < rows * H / 100;
+  printf("%s\n", ok ? "ATTN REPRO PASSED" : "ATTN REPRO FAILED");
+  return ok ? 0 : 1;
+}
+
 #ifdef MV_ATTN_TIMELINE
 // phase timeline of one mid-grid CTA under full load (bench shape): clock64() marks, printed as cycle deltas
 static void timeline(int drop) {
@@ -270,6 +320,7 @@ static void timeline(int drop) {
 
 int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "--perf")) { perf(argc > 2 ? atoi(argv[2]) : 1); return 0; }
+  if (argc > 1 && !strcmp(argv[1], "--repro")) return repro(argc > 2 ? atoi(argv[2]) : 0);
 #ifdef MV_ATTN_TIMELINE
   if (argc > 1 && !strcmp(argv[1], "--timeline")) { timeline(argc > 2 ? atoi(argv[2]) : 1); return 0; }
 #endif
