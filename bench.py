@@ -141,7 +141,7 @@ def run_ours(args):
         torch.distributed.init_process_group("nccl", device_id=dev)
     B = args.batch
     margs = types.SimpleNamespace(img_hidden_sz=2048, embedding_size=768, hidden_size=768, dropout_prob=args.dropout,
-                                  img_encoder="random-pixel", num_image_embeds=180, img_size=512, seq_len=253, lr=1e-5,
+                                  img_encoder="random-pixel", allow_random_trunk=True, num_image_embeds=180, img_size=512, seq_len=253, lr=1e-5,
                                   precision="bf16", max_micro_batch=B, seed=123)
     torch.manual_seed(0)
     model = CXRBERT(BertConfig.from_pretrained("bert-base-uncased"), margs).to(dev)

@@ -30,8 +30,10 @@
 extern "C" {
 #endif
 
-#define MV_ABI_VERSION 3   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries
-                              3: mv_batch.drop_worst_keep */
+#define MV_ABI_VERSION 4   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries
+                              3: mv_batch.drop_worst_keep
+                              4: mv_config.{attn_dropout_p, img_dropout_p, flags}; mv_gemm_desc.resid_f32;
+                                 mv_step_stats.error_flags; mv_backward_external, mv_itm_head_*, mv_colsum, mv_dgelu */
 
 enum { MV_PREC_BF16 = 0, MV_PREC_FP32 = 1 };          /* activation / GEMM-operand precision policy */
 enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3,      /* attention-mask modes */
@@ -54,8 +56,21 @@ typedef struct mv_config {
   int32_t precision;          /* MV_PREC_*                                                                         */
   float ln_eps;               /* encoder / embedding LayerNorm eps (1e-12)                                         */
   float head_ln_eps;          /* MLM-head TF-style LayerNorm eps (1e-5)  models/cxrbert_origin.py:212              */
-  float dropout_p;            /* hidden / attention-prob / embedding dropout (reference default 0.1)               */
+  float dropout_p;            /* hidden-state dropout: BertConfig.hidden_dropout_prob (text / [CLS] / [SEP]        */
+                              /* embeddings and both dense outputs of every layer; upstream BertEmbeddings,        */
+                              /* BertSelfOutput, BertOutput)                                                       */
+  float attn_dropout_p;       /* attention-probability dropout: BertConfig.attention_probs_dropout_prob            */
+  float img_dropout_p;        /* image-embedding dropout: args.dropout_prob  models/cxrbert_origin.py:19,33        */
+  int32_t flags;              /* MV_FLAG_*                                                                         */
 } mv_config;
+
+enum {
+  MV_FLAG_BF16_RESIDUAL = 1,  /* bf16 mode only: keep the residual stream (pre-LayerNorm sums, LayerNorm outputs that */
+                              /* feed the next residual add) in bf16 instead of fp32 (A/B measurements; the default   */
+                              /* fp32 stream is what meets the 1e-2 logit tolerance at 12 layers)                     */
+  MV_FLAG_DETERMINISTIC = 2   /* attention backward: ordered dQ reduction (bit-reproducible; utils.set_seed turns it  */
+                              /* on, as the reference sets cudnn.deterministic, utils/utils.py:9-16)                  */
+};
 
 /* Offsets (in elements) of every trainable tensor inside the flat parameter arena.  The fp32 master parameters,
  * their gradients, both Adam moments and the bf16 shadow all use this one layout, so the torch nn.Parameters of the
@@ -112,7 +127,10 @@ typedef struct mv_step_stats {
   float mlm_loss_sum;          /* sum over labelled tokens of the token CE  (mean = sum * inv_n_lab)                */
   float itm_loss_sum;          /* sum over samples of the ITM CE                                                    */
   int32_t mlm_correct, itm_correct;   /* models/train_origin.py:133-146                                             */
+  int32_t error_flags;         /* MV_ERR_*: set by the kernels when an input is out of range (the id is clamped, the step   */
+                               /* continues); PyTorch raises IndexError in the same situations                            */
 } mv_step_stats;
+enum { MV_ERR_TOKEN_ID = 1, MV_ERR_SEGMENT_ID = 2, MV_ERR_REGION_IDX = 4, MV_ERR_MLM_LABEL = 8 };
 
 typedef struct mv_gemm_desc {
   int32_t M, N, K;
@@ -125,6 +143,7 @@ typedef struct mv_gemm_desc {
   const void* resid; int64_t ldr;
   const void* aux; int64_t ldaux;
   float dropout_p; uint64_t dropout_seed; uint32_t dropout_site;
+  int32_t resid_f32;           /* MV_EPI_BIAS_RESID / MV_EPI_RESID with an fp32 residual operand and fp32 C (c_f32 = 1)    */
 } mv_gemm_desc;
 
 const char* mv_last_error(void);

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmedvill_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 3          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
+ABI_VERSION = 4          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
 MV_PREC_BF16, MV_PREC_FP32 = 0, 1
 MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS, MODE_S2S_FT, MODE_BAR_FT = 0, 1, 2, 3, 4, 5
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_BIAS_TANH, EPI_RESID, EPI_DGELU = range(7)
@@ -24,7 +24,12 @@ class MedvillError(RuntimeError):
 class mv_config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("hidden", "heads", "layers", "inter", "vocab", "max_pos", "type_vocab",
                                          "num_image_embeds", "seq_len", "img_hidden", "grid", "max_batch", "precision")] + \
-               [("ln_eps", C.c_float), ("head_ln_eps", C.c_float), ("dropout_p", C.c_float)]
+               [("ln_eps", C.c_float), ("head_ln_eps", C.c_float), ("dropout_p", C.c_float), ("attn_dropout_p", C.c_float),
+                ("img_dropout_p", C.c_float), ("flags", C.c_int32)]
+
+
+FLAG_BF16_RESIDUAL, FLAG_DETERMINISTIC = 1, 2
+ERR_TOKEN_ID, ERR_SEGMENT_ID, ERR_REGION_IDX, ERR_MLM_LABEL = 1, 2, 4, 8
 
 
 LAYOUT_FIELDS = ("total", "word", "pos", "type", "emb_ln_g", "emb_ln_b", "img_w", "img_b", "layer0", "layer_stride",
@@ -47,7 +52,8 @@ class mv_batch(C.Structure):
 
 
 class mv_step_stats(C.Structure):
-    _fields_ = [("mlm_loss_sum", C.c_float), ("itm_loss_sum", C.c_float), ("mlm_correct", C.c_int32), ("itm_correct", C.c_int32)]
+    _fields_ = [("mlm_loss_sum", C.c_float), ("itm_loss_sum", C.c_float), ("mlm_correct", C.c_int32), ("itm_correct", C.c_int32),
+                ("error_flags", C.c_int32)]
 
 
 class mv_gemm_desc(C.Structure):
@@ -57,7 +63,7 @@ class mv_gemm_desc(C.Structure):
                 ("C", C.c_void_p), ("ldc", C.c_int64), ("c_f32", C.c_int32), ("accumulate", C.c_int32),
                 ("C2", C.c_void_p), ("ldc2", C.c_int64), ("epi", C.c_int32), ("bias", C.c_void_p),
                 ("resid", C.c_void_p), ("ldr", C.c_int64), ("aux", C.c_void_p), ("ldaux", C.c_int64),
-                ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32)]
+                ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("dropout_site", C.c_uint32), ("resid_f32", C.c_int32)]
 
 
 # every symbol include/medvill_sm100.h declares: (restype, argtypes)

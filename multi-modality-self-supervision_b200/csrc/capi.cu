@@ -255,7 +255,7 @@ int mv_gemm(const mv_gemm_desc* g, int32_t precision, void* stream) {
   d.B = g->B; d.ldb = g->ldb; d.b_mn = g->b_mn;
   d.C = g->C; d.ldc = g->ldc; d.c_f32 = g->c_f32; d.accumulate = g->accumulate;
   d.C2 = g->C2; d.ldc2 = g->ldc2;
-  d.epi = g->epi; d.bias = g->bias; d.resid = g->resid; d.ldr = g->ldr; d.aux = g->aux; d.ldaux = g->ldaux;
+  d.epi = g->epi; d.bias = g->bias; d.resid = g->resid; d.ldr = g->ldr; d.aux = g->aux; d.ldaux = g->ldaux; d.resid_f32 = g->resid_f32;
   d.drop_on = g->dropout_p > 0.f; d.drop_site = g->dropout_site; d.drop = make_dropout(g->dropout_p, g->dropout_seed);
   return precision == MV_PREC_FP32 ? gemm_f32_simt(d, S(stream)) : gemm_bf16_tc05(d, S(stream));
 }

@@ -219,23 +219,26 @@ int Engine::init(const mv_config& c) {
   if (layout_compute(c, &lay)) return -1;
   MV_REQUIRE(c.max_batch > 0, "max_batch must be positive");
   MV_REQUIRE(c.precision == MV_PREC_BF16 || c.precision == MV_PREC_FP32, "unknown precision %d", c.precision);
-  MV_REQUIRE(c.dropout_p >= 0.f && c.dropout_p < 1.f, "dropout_p out of range");
+  MV_REQUIRE(c.dropout_p >= 0.f && c.dropout_p < 1.f && c.attn_dropout_p >= 0.f && c.attn_dropout_p < 1.f && c.img_dropout_p >= 0.f &&
+             c.img_dropout_p < 1.f, "dropout probabilities out of range");
   int dev = 0, major = 0;
   MV_CUDA_CHECK(cudaGetDevice(&dev));
   MV_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   MV_REQUIRE(major == 10, "libmedvill_sm100 needs an sm_100 (Blackwell B200) GPU; device %d is sm_%d0 — no fallback path", dev, major);
   f32 = c.precision == MV_PREC_FP32;
   es = f32 ? 4 : 2;
+  rf32 = (!f32 && !(c.flags & MV_FLAG_BF16_RESIDUAL)) ? 1 : 0;
   nh = c.heads;
   A = c.num_image_embeds + 2; T = c.seq_len + 1; L = A + T;
   Vpad = static_cast<int>(lay.vocab_padded);
   const size_t M = static_cast<size_t>(c.max_batch) * L, H = c.hidden, I = c.inter, B = c.max_batch, N = c.num_image_embeds;
+  const size_t ys = rf32 ? 4 : es;          // element size of the pre-LN sums
   x.resize(c.layers + 1);
   for (auto& p : x) if (alloc(&p, M * H * es)) return -2;
   lw.resize(c.layers);
   for (auto& w : lw) {
-    if (alloc(&w.qkv, M * 3 * H * es) || alloc(&w.ctx, M * H * es) || alloc(&w.y1, M * H * es) || alloc(&w.x1, M * H * es) ||
-        alloc(&w.h1, M * I * es) || alloc(&w.g1, M * I * es) || alloc(&w.y2, M * H * es) ||
+    if (alloc(&w.qkv, M * 3 * H * es) || alloc(&w.ctx, M * H * es) || alloc(&w.y1, M * H * ys) || alloc(&w.x1, M * H * es) ||
+        alloc(&w.h1, M * I * es) || alloc(&w.g1, M * I * es) || alloc(&w.y2, M * H * ys) ||
         alloc(reinterpret_cast<void**>(&w.lse), B * nh * L * sizeof(float)))
       return -2;
   }
@@ -247,6 +250,7 @@ int Engine::init(const mv_config& c) {
       alloc(reinterpret_cast<void**>(&delta), B * nh * L * sizeof(float)) || alloc(reinterpret_cast<void**>(&zero_idx), 16) ||
       alloc(reinterpret_cast<void**>(&stats), sizeof(mv_step_stats)))
     return -2;
+  if (rf32 && (alloc(reinterpret_cast<void**>(&xres), M * H * 4) || alloc(reinterpret_cast<void**>(&x1res), M * H * 4))) return -2;
   MV_CUDA_CHECK(cudaMemset(zero_idx, 0, 16));
   MV_CUDA_CHECK(cudaMemset(stats, 0, sizeof(mv_step_stats)));
   MV_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&stats_host), sizeof(mv_step_stats)));
@@ -293,7 +297,8 @@ int Engine::ensure_mlm(int n) {
 
 // Y[M,N] = epi(X[M,K] . W[N,K]^T + b)
 int Engine::linear_fwd(const void* X, int M, int K, int64_t w_off, int N, int64_t b_off, void* Y, int epi, void* pre,
-                       const void* resid, int drop_on, uint32_t site, const DropoutCfg& dc, cudaStream_t s, int y_f32, long ldy) {
+                       const void* resid, int drop_on, uint32_t site, const DropoutCfg& dc, cudaStream_t s, int y_f32, long ldy,
+                       int resid_f32) {
   GemmDesc d;
   d.M = M; d.N = N; d.K = K;
   d.A = X; d.lda = K; d.a_mn = 0;
@@ -301,7 +306,7 @@ int Engine::linear_fwd(const void* X, int M, int K, int64_t w_off, int N, int64_
   d.C = Y; d.ldc = ldy ? ldy : N; d.c_f32 = y_f32;
   d.C2 = pre; d.ldc2 = N;
   d.epi = epi; d.bias = b_off >= 0 ? params + b_off : nullptr;
-  d.resid = resid; d.ldr = N;
+  d.resid = resid; d.ldr = N; d.resid_f32 = resid_f32;
   d.drop_on = drop_on; d.drop_site = site; d.drop = dc;
   return gemm(d, s);
 }
@@ -337,8 +342,10 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
   MV_REQUIRE(b.cls_tok && b.sep_tok && b.input_ids && b.segment && b.region_idx && b.mode && b.t_len && b.feats, "mv_batch: null input");
   MV_REQUIRE(b.n_lab >= 0 && b.n_lab <= b.B * T, "n_lab out of range");
   const int B = b.B, H = cfg.hidden, I = cfg.inter, N = cfg.num_image_embeds, M = B * L;
-  const bool drop = b.train && cfg.dropout_p > 0.f;
+  const bool drop = b.train && cfg.dropout_p > 0.f;                    // hidden-state sites
+  const bool drop_att = b.train && cfg.attn_dropout_p > 0.f, drop_emb = b.train && (cfg.dropout_p > 0.f || cfg.img_dropout_p > 0.f);
   const DropoutCfg dc = make_dropout(cfg.dropout_p, b.dropout_seed);
+  const DropoutCfg dc_att = make_dropout(cfg.attn_dropout_p, b.dropout_seed), dc_img = make_dropout(cfg.img_dropout_p, b.dropout_seed);
   MV_TRY(ensure_mlm(b.n_lab));
 
   // --- visual tokens: sample regions, project 2048 -> H (models/image.py:57-69, cxrbert_origin.py:24) ---
@@ -352,8 +359,9 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
   ea.region_idx = reinterpret_cast<const int64_t*>(b.region_idx);
   ea.word = params + lay.word; ea.pos = params + lay.pos; ea.type = params + lay.type;
   ea.gamma = params + lay.emb_ln_g; ea.beta = params + lay.emb_ln_b; ea.eps = cfg.ln_eps;
-  ea.proj = proj; ea.emb_sum = emb_sum; ea.out = x[0];
-  ea.drop_on = drop; ea.drop_site = SITE_EMB; ea.drop = dc;
+  ea.V = cfg.vocab; ea.P = cfg.max_pos; ea.TV = cfg.type_vocab; ea.err = &stats->error_flags;
+  ea.proj = proj; ea.emb_sum = emb_sum; ea.out = x[0]; ea.out32 = xres;
+  ea.drop_on = drop_emb; ea.drop_site = SITE_EMB; ea.drop = dc; ea.drop_img = dc_img;
   MV_REQUIRE(b.sep_position >= 0 && b.sep_position < cfg.max_pos && b.prefix_type >= 0 && b.prefix_type < cfg.type_vocab,
              "mv_batch: sep_position %d / prefix_type %d out of range", b.sep_position, b.prefix_type);
   ea.sep_pos = b.sep_position; ea.prefix_type = b.prefix_type;
@@ -367,15 +375,19 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     AttnArgs aa;
     memset(&aa, 0, sizeof(aa));
     aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
-    aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
+    aa.drop_on = drop_att; aa.drop_site = site_att(l); aa.drop = dc_att;
     MV_TRY(prof_begin(1, 4.0 * B * nh * static_cast<double>(L) * L * 64, s));
     MV_TRY(f32 ? attention_fwd_simt(aa, s) : attention_fwd_tc05(aa, s));
     MV_TRY(prof_end(s));
-    MV_TRY(linear_fwd(w.ctx, M, H, base + lay.l_wo, H, base + lay.l_bo, w.y1, EPI_BIAS_RESID, nullptr, x[l], drop, site_h1(l), dc, s));
-    MV_TRY(ln_fwd(w.y1, w.x1, params + base + lay.l_ln1_g, params + base + lay.l_ln1_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s));
+    // rf32: y1 / y2 and the residual operands are fp32 (the epilogue adds the unrounded LayerNorm output and stores the
+    // unrounded sum), so the residual stream sees no bf16 rounding between layers — only GEMM operands are bf16
+    MV_TRY(linear_fwd(w.ctx, M, H, base + lay.l_wo, H, base + lay.l_bo, w.y1, EPI_BIAS_RESID, nullptr, rf32 ? static_cast<const void*>(xres) : x[l],
+                      drop, site_h1(l), dc, s, rf32, 0, rf32));
+    MV_TRY(ln_fwd(w.y1, w.x1, params + base + lay.l_ln1_g, params + base + lay.l_ln1_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s, rf32, x1res));
     MV_TRY(linear_fwd(w.x1, M, H, base + lay.l_w1, I, base + lay.l_b1, w.g1, EPI_BIAS_GELU, w.h1, nullptr, 0, 0, dc, s));
-    MV_TRY(linear_fwd(w.g1, M, I, base + lay.l_w2, H, base + lay.l_b2, w.y2, EPI_BIAS_RESID, nullptr, w.x1, drop, site_h2(l), dc, s));
-    MV_TRY(ln_fwd(w.y2, x[l + 1], params + base + lay.l_ln2_g, params + base + lay.l_ln2_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s));
+    MV_TRY(linear_fwd(w.g1, M, I, base + lay.l_w2, H, base + lay.l_b2, w.y2, EPI_BIAS_RESID, nullptr, rf32 ? static_cast<const void*>(x1res) : w.x1,
+                      drop, site_h2(l), dc, s, rf32, 0, rf32));
+    MV_TRY(ln_fwd(w.y2, x[l + 1], params + base + lay.l_ln2_g, params + base + lay.l_ln2_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s, rf32, xres));
   }
   const void* seq = x[cfg.layers];
 
@@ -400,7 +412,7 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     MV_TRY(linear_fwd(t_ln, n, H, lay.word, cfg.vocab, lay.mlm_bias, logits, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, Vpad));
     CeArgs ca;
     ca.n = n; ca.V = cfg.vocab; ca.ldv = Vpad; ca.logits = logits; ca.labels = reinterpret_cast<const int64_t*>(b.lab_labels);
-    ca.correct = &stats->mlm_correct; ca.row_lse = row_lse; ca.row_argmax = row_argmax;
+    ca.correct = &stats->mlm_correct; ca.row_lse = row_lse; ca.row_argmax = row_argmax; ca.err = &stats->error_flags;
     if (b.drop_worst_keep > 0) {
       // model.py:1003-1010: which samples count is only known once every row's loss is; so one loss-only CE pass, the
       // selection, then the gradient pass with row_scale = kept * weight / (kept weights + 1e-5)
@@ -447,8 +459,9 @@ int Engine::bucket_done(size_t idx, int allreduce, cudaStream_t s) {
 int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
   MV_REQUIRE(b.train, "mv_backward needs a batch forwarded with train=1");
   const int B = b.B, H = cfg.hidden, I = cfg.inter, N = cfg.num_image_embeds, M = B * L;
-  const bool drop = cfg.dropout_p > 0.f;
+  const bool drop = cfg.dropout_p > 0.f, drop_att = cfg.attn_dropout_p > 0.f, drop_emb = cfg.dropout_p > 0.f || cfg.img_dropout_p > 0.f;
   const DropoutCfg dc = make_dropout(cfg.dropout_p, b.dropout_seed);
+  const DropoutCfg dc_att = make_dropout(cfg.attn_dropout_p, b.dropout_seed);
   void* P = dxa; void* Q = dxb; void* R = dxc;
   MV_CUDA_CHECK(cudaMemsetAsync(P, 0, static_cast<size_t>(M) * H * es, s));   // d(seq): only labelled + [CLS] rows are non-zero
 
@@ -490,7 +503,7 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     // P = d(layer output).  LN2: y2 -> x[l+1]
     void* dY2d = drop ? R : Q;
     MV_TRY(ln_bwd(P, w.y2, params + base + lay.l_ln2_g, Q, drop ? R : nullptr, g + lay.l_ln2_g, g + lay.l_ln2_b, g + lay.l_b2, M, H,
-                  cfg.ln_eps, 0, drop, site_h2(l), dc, f32, s));
+                  cfg.ln_eps, 0, drop, site_h2(l), dc, f32, s, rf32));
     MV_TRY(linear_wgrad(dY2d, H, w.g1, M, H, I, base + lay.l_w2, s));
     MV_TRY(linear_dgrad(dY2d, H, M, H, base + lay.l_w2, I, dh1, EPI_DGELU, w.h1, s));
     MV_TRY(colsum_add(dh1, I, M, I, g + lay.l_b1, f32, s));
@@ -499,14 +512,14 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     // LN1: y1 -> x1
     void* dY1d = drop ? R : Q;
     MV_TRY(ln_bwd(P, w.y1, params + base + lay.l_ln1_g, Q, drop ? R : nullptr, g + lay.l_ln1_g, g + lay.l_ln1_b, g + lay.l_bo, M, H,
-                  cfg.ln_eps, 0, drop, site_h1(l), dc, f32, s));
+                  cfg.ln_eps, 0, drop, site_h1(l), dc, f32, s, rf32));
     MV_TRY(linear_wgrad(dY1d, H, w.ctx, M, H, H, base + lay.l_wo, s));
     MV_TRY(linear_dgrad(dY1d, H, M, H, base + lay.l_wo, H, dctx, EPI_NONE, nullptr, s));
     AttnArgs aa;
     memset(&aa, 0, sizeof(aa));
     aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
     aa.dctx = dctx; aa.dqkv = dqkv; aa.dq_acc = dq_acc; aa.delta = delta;
-    aa.drop_on = drop; aa.drop_site = site_att(l); aa.drop = dc;
+    aa.drop_on = drop_att; aa.drop_site = site_att(l); aa.drop = dc_att;
     MV_TRY(prof_begin(2, 10.0 * B * nh * static_cast<double>(L) * L * 64, s));
     MV_TRY(f32 ? attention_bwd_simt(aa, s) : attention_bwd_tc05(aa, s));
     MV_TRY(prof_end(s));
@@ -517,15 +530,17 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
   }
 
   // --- embeddings: dropout-bwd + LN-bwd, scatter into the tables, image-projection wgrad ---
+  LnAltDrop alt;
+  alt.period = L; alt.lo = 1; alt.hi = N + 1; alt.drop = make_dropout(cfg.img_dropout_p, b.dropout_seed);
   MV_TRY(ln_bwd(P, emb_sum, params + lay.emb_ln_g, Q, nullptr, grads + lay.emb_ln_g, grads + lay.emb_ln_b, nullptr, M, H, cfg.ln_eps,
-                drop, 0, SITE_EMB, dc, f32, s));
+                drop_emb, 0, SITE_EMB, dc, f32, s, 0, &alt));
   EmbedBwdArgs eb;
   eb.B = B; eb.L = L; eb.H = H; eb.N = N; eb.T = T; eb.A = A; eb.V = cfg.vocab;
   eb.cls_tok = reinterpret_cast<const int64_t*>(b.cls_tok); eb.sep_tok = reinterpret_cast<const int64_t*>(b.sep_tok);
   eb.input_ids = reinterpret_cast<const int64_t*>(b.input_ids); eb.segment = reinterpret_cast<const int64_t*>(b.segment);
   eb.region_idx = reinterpret_cast<const int64_t*>(b.region_idx);
   eb.dsum = Q; eb.d_word = grads + lay.word; eb.d_pos = grads + lay.pos; eb.d_type = grads + lay.type; eb.d_proj = dproj; eb.pad_id = b.pad_lookup_grad ? -1 : 0;
-  eb.sep_pos = b.sep_position; eb.prefix_type = b.prefix_type; eb.TV = cfg.type_vocab;
+  eb.sep_pos = b.sep_position; eb.prefix_type = b.prefix_type; eb.TV = cfg.type_vocab; eb.P = cfg.max_pos;
   MV_TRY(embed_bwd_scatter(eb, f32, s));
   MV_TRY(colsum_add(dproj, H, B * N, H, grads + lay.img_b, f32, s));
   MV_TRY(linear_wgrad(dproj, H, feats_g, B * N, H, cfg.img_hidden, lay.img_w, s));

@@ -28,6 +28,7 @@ struct Engine {
   int f32 = 0;          // activation dtype is fp32 (check mode)
   size_t es = 2;        // bytes per activation element
   int L = 0, A = 0, T = 0, nh = 0, Vpad = 0;
+  int rf32 = 0;         // bf16 mode with the residual stream (pre-LN sums y1 / y2 and the LN outputs that feed the next residual add) in fp32
 
   // borrowed arenas
   float* params = nullptr; float* grads = nullptr; float* adam_m = nullptr; float* adam_v = nullptr; bf16* shadow = nullptr;
@@ -37,6 +38,7 @@ struct Engine {
   std::vector<void*> x;          // [layers + 1] : x[0] = embedding output, x[l+1] = output of layer l
   std::vector<LayerWs> lw;
   void *emb_sum = nullptr, *proj = nullptr, *feats_g = nullptr;
+  float *xres = nullptr, *x1res = nullptr;   // rf32: fp32 copies of x[l] / x1 (transient: consumed by the next residual epilogue)
   void *cls_rows = nullptr, *pooled = nullptr, *d_pre = nullptr, *d_cls = nullptr;
   float* itm_logits = nullptr;
   void *dxa = nullptr, *dxb = nullptr, *dxc = nullptr, *dh1 = nullptr, *dqkv = nullptr, *dctx = nullptr, *dproj = nullptr;
@@ -82,7 +84,8 @@ struct Engine {
     return prof_end(s);
   }
   int linear_fwd(const void* X, int M, int K, int64_t w_off, int N, int64_t b_off, void* Y, int epi, void* pre,
-                 const void* resid, int drop_on, uint32_t site, const DropoutCfg& dc, cudaStream_t s, int y_f32 = 0, long ldy = 0);
+                 const void* resid, int drop_on, uint32_t site, const DropoutCfg& dc, cudaStream_t s, int y_f32 = 0, long ldy = 0,
+                 int resid_f32 = 0);
   int linear_dgrad(const void* dY, long lddy, int M, int N, int64_t w_off, int K, void* dX, int epi, const void* extra, cudaStream_t s);
   int linear_wgrad(const void* dY, long lddy, const void* X, int M, int N, int K, int64_t w_off, cudaStream_t s);
 

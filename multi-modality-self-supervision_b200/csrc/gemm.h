@@ -29,7 +29,8 @@ struct GemmDesc {
   void* C2 = nullptr; long ldc2 = 0;                    // optional pre-activation output (activation dtype)
   int epi = EPI_NONE;
   const float* bias = nullptr;                          // [N] fp32 (master parameter, never shadowed)
-  const void* resid = nullptr; long ldr = 0;            // [M,N] activation dtype
+  const void* resid = nullptr; long ldr = 0;            // [M,N] activation dtype, or fp32 when resid_f32 (then c_f32 too)
+  int resid_f32 = 0;                                    // fp32 residual stream: resid AND C are fp32 (EPI_BIAS_RESID only)
   const void* aux = nullptr; long ldaux = 0;            // [M,N] activation dtype
   int drop_on = 0; uint32_t drop_site = 0; DropoutCfg drop = {0.f, 0u, 1.f, 0ull};
   int splitk = 0;                                       // 0 = auto (only used when accumulate=1)

@@ -104,6 +104,14 @@ __device__ __forceinline__ void stage_bf16_half(uint8_t* stg, int lane, int half
     *reinterpret_cast<uint4*>(stg + sw128_off(lane, half * 4 + j)) = u;
   }
 }
+// read 32 fp32 (row `lane`) from a swizzled [32 x 32] fp32 staging tile
+__device__ __forceinline__ void unstage_f32(const uint8_t* stg, int lane, float (&out)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 u = *reinterpret_cast<const float4*>(stg + sw128_off(lane, j));
+    out[4 * j] = u.x; out[4 * j + 1] = u.y; out[4 * j + 2] = u.z; out[4 * j + 3] = u.w;
+  }
+}
 // write 32 fp32 values into a [32 rows x 32 cols] fp32 swizzled staging tile
 __device__ __forceinline__ void stage_f32(uint8_t* stg, int lane, const float (&f)[32]) {
 #pragma unroll
@@ -315,7 +323,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto issue_in = [&](uint32_t chunk_cnt, int m0, int n0, int c) {   // lane 0 only: prefetch the epilogue input tile
       const uint32_t b = chunk_cnt & 1u;
       mbar_expect_tx(&in_bar[b], STG_BYTES);
-      tma_load_2d(&tmX, &in_bar[b], my_stg + b * STG_BYTES, n0 + c * 64, m0 + q * 32);
+      tma_load_2d(&tmX, &in_bar[b], my_stg + b * STG_BYTES, n0 + c * CHUNK_COLS, m0 + q * 32);
     };
     int it = 0;
     const uint32_t tempty_remote = TWO ? mapa_cluster(smem_u32(&bars->tempty[acc]), 0) : 0u;   // leader's barrier
@@ -378,6 +386,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float f[32], pre[32], in[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (has_in) unstage_f32(s2, lane, in);       // fp32 residual stream: the input tile is fp32 too, replaced in place
           const float bias_cur = bias_next;
           bias_next = bias_at(n0 + c * 32 + 32 + lane);
           epilogue_apply(p, f, pre, in, row, n0 + c * 32, bias_cur);
@@ -450,6 +459,8 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   tmX = tmC;
   if (d.C2) {
     rc = tmap_encode_2d(&tmX, TMAP_BF16, d.C2, d.N, d.M, d.ldc2 * 2, 64, 32);
+  } else if ((d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID) && d.resid_f32) {
+    rc = tmap_encode_2d(&tmX, TMAP_F32, d.resid, d.N, d.M, d.ldr * 4, 32, 32);
   } else if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID) {
     rc = tmap_encode_2d(&tmX, TMAP_BF16, d.resid, d.N, d.M, d.ldr * 2, 64, 32);
   } else if (d.epi == EPI_DGELU) {
@@ -561,7 +572,8 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   if (d.epi == EPI_BIAS || d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_RESID || d.epi == EPI_BIAS_TANH)
     MV_REQUIRE(d.bias != nullptr, "gemm: epilogue %d needs bias", d.epi);
   if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID)
-    MV_REQUIRE(d.resid != nullptr && d.N % 32 == 0 && d.ldr % 8 == 0 && !d.c_f32, "gemm: residual epilogue needs resid, N%%32==0, bf16 out");
+    MV_REQUIRE(d.resid != nullptr && d.N % 32 == 0 && d.ldr % 8 == 0 && (d.c_f32 != 0) == (d.resid_f32 != 0) && !(d.c_f32 && d.accumulate),
+               "gemm: residual epilogue needs resid, N%%32==0, and resid / C of the same type (bf16, or fp32 with resid_f32)");
   if (d.epi == EPI_DGELU)
     MV_REQUIRE(d.aux != nullptr && d.N % 32 == 0 && d.ldaux % 8 == 0 && !d.c_f32, "gemm: DGELU epilogue needs aux, N%%32==0, bf16 out");
   GemmParams p;

@@ -20,7 +20,11 @@ struct EmbedArgs {
   const void* proj;                  // [B*N, H] activation dtype: img projection + bias (GEMM output)
   void* emb_sum;                     // [B*L, H] pre-LayerNorm sum (saved for backward)
   void* out;                         // [B*L, H] LN + dropout output = encoder input
+  float* out32 = nullptr;            // optional fp32 copy of `out` (residual operand of layer 0 when the residual stream is fp32)
   int drop_on; uint32_t drop_site; DropoutCfg drop;
+  DropoutCfg drop_img;               // region rows 1..N: ImageBertEmbeddings.dropout (args.dropout_prob); the rest: BertEmbeddings.dropout
+  int V = 0, P = 0, TV = 0;          // table sizes (vocab, max_pos, type vocab) for the range checks; 0 = unchecked
+  int* err = nullptr;                // device error-flag word (MV_ERR_*): out-of-range ids are clamped to 0 and reported
   int sep_pos = 0;                   // position id of the prefix [SEP]: 0 (pre-training, cxrbert_origin.py:119) or A-1
                                      // (fine-tune model, .../pytorch_pretrained_bert/model.py:886-892)
   int prefix_type = 0;               // token type of [CLS] / regions / [SEP]: 0, or 4 with new_segment_ids (data_loader.py:344)
@@ -38,18 +42,23 @@ struct EmbedBwdArgs {
                                      // (-1: keep it — the vendored fine-tune BertEmbeddings has no padding_idx, model.py:228)
   int sep_pos = 0, prefix_type = 0;  // as EmbedArgs
   int TV = 2;                        // token-type vocabulary size (rows of d_type), <= 8
+  int P = 0;                         // max_pos (0 = unchecked): ids outside the tables are clamped to 0 as in the forward
 };
 int embed_bwd_scatter(const EmbedBwdArgs& a, int f32, cudaStream_t s);
 
 // ---- LayerNorm (eps is an argument: 1e-12 encoder, 1e-5 TF-style MLM head, models/cxrbert_origin.py:189-202)
+// x_f32 (bf16 mode only): x is an fp32 pre-LN sum (fp32 residual stream); y32 (optional): fp32 copy of the output
 int ln_fwd(const void* x, void* y, const float* gamma, const float* beta, int rows, int H, float eps, int drop_on,
-           uint32_t drop_site, const DropoutCfg& drop, int f32, cudaStream_t s);
+           uint32_t drop_site, const DropoutCfg& drop, int f32, cudaStream_t s, int x_f32 = 0, float* y32 = nullptr);
+// rows r with (r % period) in [lo, hi) use `drop` instead of ln_bwd's main DropoutCfg for in_drop (the region rows of the
+// joint embedding have their own dropout probability)
+struct LnAltDrop { int period, lo, hi; DropoutCfg drop; };
 // dy: grad w.r.t. LN output (with in_drop: grad w.r.t. dropout(LN(x)), mask re-generated from drop_site)
 // dx: grad w.r.t. x; dx_drop (optional, out_drop): dx * dropout mask of `drop_site` (grad of the dense output that
 // was dropped before the residual add). dgamma/dbeta/dbias are fp32 and accumulated atomically (dbias <- dx_drop or dx).
 int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta,
            float* dbias, int rows, int H, float eps, int in_drop, int out_drop, uint32_t drop_site,
-           const DropoutCfg& drop, int f32, cudaStream_t s);
+           const DropoutCfg& drop, int f32, cudaStream_t s, int x_f32 = 0, const struct LnAltDrop* alt = nullptr);
 
 // ---- small utilities
 int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, cudaStream_t s);   // out[c] += sum_r x[r,c]
@@ -80,6 +89,7 @@ struct CeArgs {
   float* row_lse; int* row_argmax;   // optional per-row outputs (parity aids)
   const float* row_weight = nullptr; // optional [n] per-row loss weights (fine-tune masked_weights / multiplicities)
   float* row_loss = nullptr;         // optional [n] out: unweighted lse_i - logit_i[label_i]
+  int* err = nullptr;                // device error-flag word: a label outside [0, V) is clamped to 0 and reported (MV_ERR_MLM_LABEL)
 };
 int mlm_ce_fwd_bwd(const CeArgs& a, int f32, cudaStream_t s);
 
@@ -107,6 +117,7 @@ struct ItmArgs {
   float* loss_sum; int* correct;
   void* d_pre;                       // [B, H] activation dtype: grad w.r.t. pooler pre-activation; null = forward only
   float* dw; float* db;              // fp32 grads (atomic)
+  const float* ext_dlogits = nullptr;  // optional [B, 2]: gradient w.r.t. the logits supplied by the caller (autograd path) instead of the CE
 };
 int itm_head_fwd_bwd(const ItmArgs& a, int f32, cudaStream_t s);
 // out[b] = softmax(logits[b, :2])[1]: the image-report match probability used as the retrieval similarity

@@ -55,7 +55,11 @@ __global__ void __launch_bounds__(256) mlm_ce_kernel(const CeArgs a) {
   __syncthreads();
   const float total = s_bcast[1];
   const float inv = 1.0f / total;
-  const int label = static_cast<int>(a.labels[row]);
+  int label = static_cast<int>(a.labels[row]);
+  if (label < 0 || label >= a.V) {       // PyTorch's CE raises for a target outside [0, V): clamp and report
+    if (tid == 0 && a.err) atomicOr(a.err, 8);
+    label = 0;
+  }
   const float rw = a.row_weight ? a.row_weight[row] : 1.f;       // fine-tune masked_weights (model.py:998-1005)
   if (a.dlogits) {
     T* d = static_cast<T*>(a.dlogits) + static_cast<long>(row) * a.ldv;
@@ -138,7 +142,11 @@ __global__ void __launch_bounds__(256) itm_kernel(const ItmArgs a) {
     for (int w = 0; w < 8; ++w) { z0 += s_red[0][w]; z1 += s_red[1][w]; }
     a.logits[2 * b] = z0;
     a.logits[2 * b + 1] = z1;
-    if (a.labels == nullptr) { s_dl[0] = 0.f; s_dl[1] = 0.f; }   // forward-only: logits are all that is asked
+    if (a.ext_dlogits != nullptr) {                              // gradient handed in by the caller (autograd path)
+      const float d0 = a.ext_dlogits[2 * b], d1 = a.ext_dlogits[2 * b + 1];
+      s_dl[0] = d0; s_dl[1] = d1;
+      if (a.d_pre) { atomicAdd(a.db, d0); atomicAdd(a.db + 1, d1); }
+    } else if (a.labels == nullptr) { s_dl[0] = 0.f; s_dl[1] = 0.f; }   // forward-only: logits are all that is asked
     else {
     const int y = static_cast<int>(a.labels[b]);
     const float mx = fmaxf(z0, z1);
@@ -290,7 +298,7 @@ int drop_worst_select(const DropWorstArgs& a, cudaStream_t s) {
 int itm_head_fwd_bwd(const ItmArgs& a, int f32, cudaStream_t s) {
   if (a.B <= 0) return 0;
   MV_REQUIRE(a.pooled && a.w && a.b && a.logits && a.loss_sum && a.correct, "itm: null argument");
-  MV_REQUIRE(a.labels || !a.d_pre, "itm: backward needs labels");
+  MV_REQUIRE(a.labels || a.ext_dlogits || !a.d_pre, "itm: backward needs labels or an external logit gradient");
   if (f32) itm_kernel<float><<<a.B, 256, 0, s>>>(a); else itm_kernel<bf16><<<a.B, 256, 0, s>>>(a);
   MV_LAUNCH_CHECK();
   return 0;

@@ -77,22 +77,28 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const EmbedArgs a) {
   const float* wrow = nullptr;
   const T* prow = nullptr;
   int pos_id = 0, type_id = 0;
+  // ids index the embedding tables: PyTorch raises IndexError when one is out of range; here it is clamped to row 0 and
+  // reported through the step's error flags (a tokenizer vocabulary larger than config.vocab_size is the usual cause)
+  auto checked = [&](long id, int hi, int flag) -> long {
+    if (hi > 0 && (id < 0 || id >= hi)) { if (lane == 0 && a.err) atomicOr(a.err, flag); return 0; }
+    return id;
+  };
   if (s == 0) {
-    wrow = a.word + a.cls_tok[b] * H;                                         // [CLS]: position 0, prefix type
+    wrow = a.word + checked(a.cls_tok[b], a.V, 1) * H;                        // [CLS]: position 0, prefix type
     type_id = a.prefix_type;
   } else if (s <= a.N) {
     prow = static_cast<const T*>(a.proj) + (static_cast<long>(b) * a.N + (s - 1)) * H;
-    pos_id = static_cast<int>(a.region_idx[s - 1]);                           // grid index as position id
+    pos_id = static_cast<int>(checked(a.region_idx[s - 1], a.P, 4));          // grid index as position id
     type_id = a.prefix_type;
   } else if (s == a.N + 1) {
-    wrow = a.word + a.sep_tok[b] * H;                                         // [SEP]: position restarts at 0 (pre-training)
+    wrow = a.word + checked(a.sep_tok[b], a.V, 1) * H;                        // [SEP]: position restarts at 0 (pre-training)
     pos_id = a.sep_pos;                                                       // or continues at A-1 (fine-tune model)
     type_id = a.prefix_type;
   } else {
     const int i = s - a.A;
-    wrow = a.word + a.input_ids[static_cast<long>(b) * a.T + i] * H;
+    wrow = a.word + checked(a.input_ids[static_cast<long>(b) * a.T + i], a.V, 1) * H;
     pos_id = i;
-    type_id = static_cast<int>(a.segment[static_cast<long>(b) * a.T + i]);
+    type_id = static_cast<int>(checked(a.segment[static_cast<long>(b) * a.T + i], a.TV, 2));
   }
   const float* posrow = a.pos + static_cast<long>(pos_id) * H;
   const float* typerow = a.type + static_cast<long>(type_id) * H;
@@ -121,16 +127,19 @@ __global__ void __launch_bounds__(256) embed_ln_fwd_kernel(const EmbedArgs a) {
       load8<float>(a.beta + ch * 8, bt);
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = (x[c][j] - mean) * rstd * g[j] + bt[j];
-      if (a.drop_on) apply_dropout8(y, a.drop, a.drop_site, warp, H, ch * 8);
+      if (a.drop_on) apply_dropout8(y, (s >= 1 && s <= a.N) ? a.drop_img : a.drop, a.drop_site, warp, H, ch * 8);
       store8<T>(static_cast<T*>(a.out) + static_cast<long>(warp) * H + ch * 8, y);
+      if (a.out32) store8<float>(a.out32 + static_cast<long>(warp) * H + ch * 8, y);
     }
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* gamma,
-                                                     const float* beta, int rows, int H, float eps, int drop_on,
-                                                     uint32_t site, DropoutCfg drop) {
+// TX: dtype of the pre-LN sum (fp32 when the residual stream is kept in fp32), T: activation dtype of the
+// output; y32 (optional): the same output unrounded, the fp32 residual operand of the next GEMM epilogue.
+template <typename TX, typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, T* __restrict__ y, float* __restrict__ y32,
+                                                     const float* gamma, const float* beta, int rows, int H, float eps,
+                                                     int drop_on, uint32_t site, DropoutCfg drop) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nch = H >> 3;
@@ -138,7 +147,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T*
 #pragma unroll
   for (int c = 0; c < kMaxChunks; ++c) {
     const int ch = lane + 32 * c;
-    if (ch < nch) load8<T>(x + static_cast<long>(warp) * H + ch * 8, v[c]);
+    if (ch < nch) load8<TX>(x + static_cast<long>(warp) * H + ch * 8, v[c]);
   }
   float mean, rstd;
   row_stats(v, nch, lane, H, eps, mean, rstd);
@@ -153,6 +162,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T*
       for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + bt[j];
       if (drop_on) apply_dropout8(o, drop, site, warp, H, ch * 8);
       store8<T>(y + static_cast<long>(warp) * H + ch * 8, o);
+      if (y32) store8<float>(y32 + static_cast<long>(warp) * H + ch * 8, o);
     }
   }
 }
@@ -166,53 +176,48 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T* __restrict__ x, T*
 // projection terms  s1 = mean(dy*g),  s2 = mean(dy*g*xhat) = rstd * (sum dy*g*x' - mean' * sum dy*g) / H,
 // so the dependency chain per row is load -> one 4-wide reduction -> store (it was four serial reductions).  The bf16
 // instantiation also prefetches the next row's operands (raw 16-byte vectors) under the current row's arithmetic.
-template <typename T, int NC>
-struct RawRow;
-template <int NC>
-struct RawRow<bf16, NC> { uint4 x[NC], d[NC]; };
-template <int NC>
-struct RawRow<float, NC> { float4 x[NC][2], d[NC][2]; };
+template <typename T>
+struct Raw8;                                 // 8 consecutive elements as raw 16-byte vectors
+template <>
+struct Raw8<bf16> { uint4 u; };
+template <>
+struct Raw8<float> { float4 u[2]; };
+__device__ __forceinline__ void raw_load8(Raw8<bf16>& r, const bf16* p) { r.u = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void raw_load8(Raw8<float>& r, const float* p) {
+  r.u[0] = *reinterpret_cast<const float4*>(p);
+  r.u[1] = *reinterpret_cast<const float4*>(p + 4);
+}
+template <typename TX, typename T, int NC>
+struct RawRow { Raw8<TX> x[NC]; Raw8<T> d[NC]; };
 
-template <int NC>
-__device__ __forceinline__ void raw_load(RawRow<bf16, NC>& r, const bf16* x, const bf16* dy, long row, int H, int nch, int lane) {
+template <typename TX, typename T, int NC>
+__device__ __forceinline__ void raw_load(RawRow<TX, T, NC>& r, const TX* x, const T* dy, long row, int H, int nch, int lane) {
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nch) {
-      r.x[c] = *reinterpret_cast<const uint4*>(x + row * H + ch * 8);
-      r.d[c] = *reinterpret_cast<const uint4*>(dy + row * H + ch * 8);
+      raw_load8(r.x[c], x + row * H + ch * 8);
+      raw_load8(r.d[c], dy + row * H + ch * 8);
     }
   }
 }
-template <int NC>
-__device__ __forceinline__ void raw_load(RawRow<float, NC>& r, const float* x, const float* dy, long row, int H, int nch, int lane) {
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int ch = lane + 32 * c;
-    if (ch < nch) {
-      r.x[c][0] = *reinterpret_cast<const float4*>(x + row * H + ch * 8);
-      r.x[c][1] = *reinterpret_cast<const float4*>(x + row * H + ch * 8 + 4);
-      r.d[c][0] = *reinterpret_cast<const float4*>(dy + row * H + ch * 8);
-      r.d[c][1] = *reinterpret_cast<const float4*>(dy + row * H + ch * 8 + 4);
-    }
-  }
-}
-__device__ __forceinline__ void raw_unpack(const uint4& u, float (&v)[8]) {
+__device__ __forceinline__ void raw_unpack(const Raw8<bf16>& r, float (&v)[8]) {
+  const uint4& u = r.u;
   const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
   v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
-__device__ __forceinline__ void raw_unpack(const float4 (&u)[2], float (&v)[8]) {
-  v[0] = u[0].x; v[1] = u[0].y; v[2] = u[0].z; v[3] = u[0].w; v[4] = u[1].x; v[5] = u[1].y; v[6] = u[1].z; v[7] = u[1].w;
+__device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.u[0].x; v[1] = r.u[0].y; v[2] = r.u[0].z; v[3] = r.u[0].w; v[4] = r.u[1].x; v[5] = r.u[1].y; v[6] = r.u[1].z; v[7] = r.u[1].w;
 }
 
-template <typename T, int NC>
-__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+template <typename TX, typename T, int NC>
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy, const TX* __restrict__ x,
                                                         const float* __restrict__ gamma, T* __restrict__ dx,
                                                         T* __restrict__ dx_drop, float* dgamma, float* dbeta, float* dbias,
                                                         int rows, int H, float eps, int in_drop, int out_drop, uint32_t site,
-                                                        DropoutCfg drop) {
+                                                        DropoutCfg drop, LnAltDrop alt) {
   extern __shared__ float red[];  // [8 warps][3][H]
-  constexpr bool kPrefetch = sizeof(T) == 2;
+  constexpr bool kPrefetch = sizeof(T) == 2;      // production mode (bf16 gradients): prefetch the next row under the arithmetic
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nch = H >> 3;
   const float inv_h = 1.f / static_cast<float>(H);
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy
   __syncwarp();
   const long stride = static_cast<long>(gridDim.x) * 8;
   long row = static_cast<long>(blockIdx.x) * 8 + warp;
-  RawRow<T, NC> cur;
+  RawRow<TX, T, NC> cur;
   if (kPrefetch && row < rows) raw_load(cur, x, dy, row, H, nch, lane);
   for (; row < rows; row += stride) {
     if (!kPrefetch) raw_load(cur, x, dy, row, H, nch, lane);
@@ -232,7 +237,10 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy
       if (ch < nch) {
         raw_unpack(cur.x[c], xv[c]);
         raw_unpack(cur.d[c], dv[c]);
-        if (in_drop) apply_dropout8(dv[c], drop, site, row, H, ch * 8);
+        if (in_drop) {
+          const int rr = alt.period > 0 ? static_cast<int>(row % alt.period) : -1;
+          apply_dropout8(dv[c], (rr >= alt.lo && rr < alt.hi) ? alt.drop : drop, site, row, H, ch * 8);
+        }
       }
     }
     if (kPrefetch && row + stride < rows) raw_load(cur, x, dy, row + stride, H, nch, lane);
@@ -327,8 +335,9 @@ __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const EmbedBwdAr
   for (int i = threadIdx.x; i < a.TV * H; i += 256) s_type[i] = 0.f;
   __syncthreads();
   const bool is_img = s >= 1 && s <= a.N, is_txt = s >= a.A;
+  auto clamped = [](long id, int hi) -> long { return (hi > 0 && (id < 0 || id >= hi)) ? 0 : id; };   // as embed_ln_fwd (which reports)
   int pos_id = 0;
-  if (is_img) pos_id = static_cast<int>(a.region_idx[s - 1]);
+  if (is_img) pos_id = static_cast<int>(clamped(a.region_idx[s - 1], a.P));
   else if (s == a.N + 1) pos_id = a.sep_pos;
   else if (is_txt) pos_id = s - a.A;
   float acc[kMaxChunks][8];
@@ -341,12 +350,12 @@ __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const EmbedBwdAr
     long word_id = -1;
     int type_id = a.prefix_type;
     T* proj_row = nullptr;
-    if (s == 0) word_id = a.cls_tok[b];
+    if (s == 0) word_id = clamped(a.cls_tok[b], a.V);
     else if (is_img) proj_row = static_cast<T*>(a.d_proj) + (static_cast<long>(b) * a.N + (s - 1)) * H;
-    else if (s == a.N + 1) word_id = a.sep_tok[b];
+    else if (s == a.N + 1) word_id = clamped(a.sep_tok[b], a.V);
     else {
-      word_id = a.input_ids[static_cast<long>(b) * a.T + (s - a.A)];
-      type_id = static_cast<int>(a.segment[static_cast<long>(b) * a.T + (s - a.A)]);
+      word_id = clamped(a.input_ids[static_cast<long>(b) * a.T + (s - a.A)], a.V);
+      type_id = static_cast<int>(clamped(a.segment[static_cast<long>(b) * a.T + (s - a.A)], a.TV));
     }
     const T* src = static_cast<const T*>(a.dsum) + (static_cast<long>(b) * a.L + s) * H;
 #pragma unroll
@@ -580,45 +589,63 @@ int embed_bwd_scatter(const EmbedBwdArgs& a, int f32, cudaStream_t s) {
 }
 
 int ln_fwd(const void* x, void* y, const float* gamma, const float* beta, int rows, int H, float eps, int drop_on,
-           uint32_t drop_site, const DropoutCfg& drop, int f32, cudaStream_t s) {
+           uint32_t drop_site, const DropoutCfg& drop, int f32, cudaStream_t s, int x_f32, float* y32) {
   if (check_h(H)) return -1;
   if (rows <= 0) return 0;
-  MV_DISPATCH_T(f32, (ln_fwd_kernel<T><<<rows_grid(rows), 256, 0, s>>>(static_cast<const T*>(x), static_cast<T*>(y), gamma,
-                                                                       beta, rows, H, eps, drop_on, drop_site, drop)));
+  if (f32) {
+    ln_fwd_kernel<float, float><<<rows_grid(rows), 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y), y32, gamma, beta,
+                                                                 rows, H, eps, drop_on, drop_site, drop);
+  } else if (x_f32) {
+    ln_fwd_kernel<float, bf16><<<rows_grid(rows), 256, 0, s>>>(static_cast<const float*>(x), static_cast<bf16*>(y), y32, gamma, beta,
+                                                                rows, H, eps, drop_on, drop_site, drop);
+  } else {
+    ln_fwd_kernel<bf16, bf16><<<rows_grid(rows), 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), y32, gamma, beta, rows,
+                                                               H, eps, drop_on, drop_site, drop);
+  }
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename TX, typename T, int NC>
+static int ln_bwd_launch(const void* dy, const void* x, const float* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta,
+                         float* dbias, int rows, int H, float eps, int in_drop, int out_drop, uint32_t drop_site,
+                         const DropoutCfg& drop, const LnAltDrop& alt, int grid, size_t smem, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<TX, T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    attr = true;
+  }
+  ln_bwd_kernel<TX, T, NC><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const TX*>(x), gamma, static_cast<T*>(dx),
+                                                   static_cast<T*>(dx_drop), dgamma, dbeta, dbias, rows, H, eps, in_drop, out_drop,
+                                                   drop_site, drop, alt);
   MV_LAUNCH_CHECK();
   return 0;
 }
 
 int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx_drop, float* dgamma, float* dbeta,
            float* dbias, int rows, int H, float eps, int in_drop, int out_drop, uint32_t drop_site,
-           const DropoutCfg& drop, int f32, cudaStream_t s) {
+           const DropoutCfg& drop, int f32, cudaStream_t s, int x_f32, const LnAltDrop* alt_in) {
   if (check_h(H)) return -1;
   if (rows <= 0) return 0;
   MV_REQUIRE(!out_drop || dx_drop != nullptr, "ln_bwd: out_drop needs dx_drop");
+  LnAltDrop alt;
+  if (alt_in) alt = *alt_in; else { alt.period = 0; alt.lo = 0; alt.hi = 0; alt.drop = drop; }
   int grid = (rows + 7) / 8;
   const int cap = device_sm_count() * 2;
   if (grid > cap) grid = cap;
   const size_t smem = static_cast<size_t>(8) * 3 * H * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
-    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<bf16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
-    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<float, kMaxChunks>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
-    MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<bf16, kMaxChunks>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
-    attr = true;
-  }
   // H <= 768 (BERT-base): three 8-element chunks per lane, which keeps the whole row + the prefetched next row in registers
+#define MV_LN_BWD(TX, T, NC) \
+  return ln_bwd_launch<TX, T, NC>(dy, x, gamma, dx, dx_drop, dgamma, dbeta, dbias, rows, H, eps, in_drop, out_drop, drop_site, drop, alt, grid, smem, s)
   if (H <= 768) {
-    MV_DISPATCH_T(f32, (ln_bwd_kernel<T, 3><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
-                                                                    static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
-                                                                    dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
-  } else {
-    MV_DISPATCH_T(f32, (ln_bwd_kernel<T, kMaxChunks><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma,
-                                                                             static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta,
-                                                                             dbias, rows, H, eps, in_drop, out_drop, drop_site, drop)));
+    if (f32) MV_LN_BWD(float, float, 3);
+    if (x_f32) MV_LN_BWD(float, bf16, 3);
+    MV_LN_BWD(bf16, bf16, 3);
   }
-  MV_LAUNCH_CHECK();
-  return 0;
+  if (f32) MV_LN_BWD(float, float, kMaxChunks);
+  if (x_f32) MV_LN_BWD(float, bf16, kMaxChunks);
+  MV_LN_BWD(bf16, bf16, kMaxChunks);
+#undef MV_LN_BWD
 }
 
 int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, cudaStream_t s) {

@@ -30,7 +30,10 @@ class EngineDims:
     grid: int = 256
     ln_eps: float = 1e-12
     head_ln_eps: float = 1e-5
-    dropout_p: float = 0.1
+    dropout_p: float = 0.1          # hidden-state dropout (BertConfig.hidden_dropout_prob)
+    attn_dropout_p: float = None    # attention-probability dropout (None: same as dropout_p)
+    img_dropout_p: float = None     # image-embedding dropout, args.dropout_prob (None: same as dropout_p)
+    flags: int = 0                  # _lib.FLAG_*
 
     @property
     def A(self):
@@ -48,7 +51,9 @@ class EngineDims:
         return _lib.mv_config(hidden=self.hidden, heads=self.heads, layers=self.layers, inter=self.inter, vocab=self.vocab,
                               max_pos=self.max_pos, type_vocab=self.type_vocab, num_image_embeds=self.num_image_embeds,
                               seq_len=self.seq_len, img_hidden=self.img_hidden, grid=self.grid, max_batch=max_batch,
-                              precision=precision, ln_eps=self.ln_eps, head_ln_eps=self.head_ln_eps, dropout_p=self.dropout_p)
+                              precision=precision, ln_eps=self.ln_eps, head_ln_eps=self.head_ln_eps, dropout_p=self.dropout_p,
+                              attn_dropout_p=self.dropout_p if self.attn_dropout_p is None else self.attn_dropout_p,
+                              img_dropout_p=self.dropout_p if self.img_dropout_p is None else self.img_dropout_p, flags=int(self.flags))
 
 
 def query_layout(dims, max_batch=1, precision=_lib.MV_PREC_BF16):
@@ -160,6 +165,15 @@ class Batch:
             train=1 if train else 0, sep_position=int(sep_position), prefix_type=int(prefix_type),
             pad_lookup_grad=1 if pad_lookup_grad else 0, global_counts=ptr(self.global_counts), lab_weights=ptr(self.lab_weights),
             drop_worst_keep=int(drop_worst_keep))
+
+
+def _raise_on_error_flags(flags):
+    """mv_step_stats.error_flags: the kernels clamp an out-of-range id and report it; PyTorch raises IndexError there."""
+    if flags:
+        what = [n for bit, n in ((_lib.ERR_TOKEN_ID, "token id >= vocab_size"), (_lib.ERR_SEGMENT_ID, "segment id >= type_vocab_size"),
+                                 (_lib.ERR_REGION_IDX, "region index >= max_position_embeddings"),
+                                 (_lib.ERR_MLM_LABEL, "MLM label outside [0, vocab_size)")) if flags & bit]
+        raise MedvillError("index out of range in the last step: " + "; ".join(what))
 
 
 _LIVE_ENGINES = []      # weak references; lets optimizers locate the engine that owns a parameter view
@@ -291,6 +305,7 @@ class PretrainEngine:
     def read_stats(self):
         st = _lib.mv_step_stats()
         check(lib().mv_read_stats(self._h, C.byref(st), stream_ptr(self.device)), "mv_read_stats")
+        _raise_on_error_flags(st.error_flags)
         return dict(mlm_loss_sum=st.mlm_loss_sum, itm_loss_sum=st.itm_loss_sum, mlm_correct=st.mlm_correct, itm_correct=st.itm_correct)
 
     def read_stats_async(self):
@@ -298,7 +313,7 @@ class PretrainEngine:
         that copy (only) and yields the same dict as read_stats().  Lets a trainer keep the GPU queue full and look at
         the loss one step (or `log_freq` steps) later."""
         if not hasattr(self, "_stat_slots"):
-            self._stat_slots = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(8)]
+            self._stat_slots = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(8)]
             self._stat_next = 0
         slot = self._stat_slots[self._stat_next % len(self._stat_slots)]
         self._stat_next += 1
@@ -309,6 +324,7 @@ class PretrainEngine:
         def resolve():
             ev.synchronize()
             f = slot.view(torch.float32)
+            _raise_on_error_flags(int(slot[4]))
             return dict(mlm_loss_sum=float(f[0]), itm_loss_sum=float(f[1]), mlm_correct=int(slot[2]), itm_correct=int(slot[3]))
         return resolve
 

@@ -68,6 +68,9 @@ def build_parser():
     p.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--compact_masks", action="store_true", help="ship (mode, t_len) instead of the [L, L] mask tensor")
     p.add_argument("--max_micro_batch", type=int, default=64)
+    p.add_argument("--allow_random_trunk", action="store_true",
+                   help="construct the frozen ResNet-50 with random weights when the ImageNet checkpoint is not in the torch-hub cache")
+    p.add_argument("--resnet_weights", type=str, default=None, help="path of resnet50-0676ba61.pth (default: torch-hub cache)")
     return p
 
 

@@ -232,7 +232,12 @@ class CXRBERT(nn.Module):
         return EngineDims(hidden=c.hidden_size, heads=c.num_attention_heads, layers=c.num_hidden_layers, inter=c.intermediate_size,
                           vocab=c.vocab_size, max_pos=c.max_position_embeddings, type_vocab=c.type_vocab_size,
                           num_image_embeds=a.num_image_embeds, seq_len=a.seq_len, img_hidden=a.img_hidden_sz, grid=grid,
-                          ln_eps=c.layer_norm_eps, head_ln_eps=1e-5, dropout_p=float(a.dropout_prob))
+                          ln_eps=c.layer_norm_eps, head_ln_eps=1e-5,
+                          # dropout sites as in the reference: BERT's own probabilities inside the encoder and the text
+                          # embeddings, args.dropout_prob only for the image embeddings (cxrbert_origin.py:19)
+                          dropout_p=float(getattr(c, "hidden_dropout_prob", a.dropout_prob)),
+                          attn_dropout_p=float(getattr(c, "attention_probs_dropout_prob", a.dropout_prob)),
+                          img_dropout_p=float(a.dropout_prob), flags=int(getattr(a, "engine_flags", 0)))
 
     def _trainable(self):
         """reference-named trainable parameters (aliases de-duplicated, ResNet excluded)"""
@@ -247,8 +252,20 @@ class CXRBERT(nn.Module):
             self._engine = None
 
     def _apply(self, fn, *a, **k):
-        self._release_engine()      # .to() / .cuda() / .float() re-allocate parameters: re-adopt lazily afterwards
-        return super()._apply(fn, *a, **k)
+        # .to() / .cuda() / .float() re-allocate parameters: re-adopt lazily afterwards.  The optimizer state moves with the
+        # model (host copy -> new engine); a live communicator cannot be carried over, so that case fails loudly.
+        carry = None
+        if self._engine is not None:
+            if self._engine.world > 1:
+                raise _lib.MedvillError("CXRBERT.to()/.cuda() after init_distributed(): move the model first, then initialise "
+                                        "the data-parallel group (the NCCL communicator lives in the engine)")
+            if self._engine.step_count > 0:
+                carry = self._engine.optimizer_state_dict()
+        self._release_engine()
+        out = super()._apply(fn, *a, **k)
+        if carry is not None:
+            self._carry_optimizer = carry
+        return out
 
     def engine(self, min_batch=1):
         dev = self.enc.pooler.dense.weight.device
@@ -257,6 +274,12 @@ class CXRBERT(nn.Module):
                                     "call .to('cuda') first")
         cap = max(min_batch, int(getattr(self.args, "max_micro_batch", 64)))
         if self._engine is not None and self._engine.max_batch < min_batch:
+            # a rebuilt engine starts with zero Adam moments, step 0 and no NCCL communicator: never do that behind the
+            # caller's back once training state exists (forward / pretrain_step / eval_step chunk by max_batch instead)
+            if self._engine.step_count > 0 or self._engine.world > 1:
+                raise _lib.MedvillError("batch of %d exceeds the engine's micro-batch capacity %d after training started: set "
+                                        "args.max_micro_batch before the first step (optimizer state and the communicator "
+                                        "live in the engine)" % (min_batch, self._engine.max_batch))
             self._release_engine()
         if self._engine is None:
             eng = PretrainEngine(self.dims(), dev, precision=getattr(self.args, "precision", "bf16"), max_batch=cap)
@@ -272,6 +295,9 @@ class CXRBERT(nn.Module):
                     p.grad = eng.view(n, eng.grads)
             eng.refresh_shadow()
             self.enc.img_encoder.model.to(memory_format=torch.channels_last)
+            if getattr(self, "_carry_optimizer", None) is not None:
+                eng.load_optimizer_state_dict(self._carry_optimizer)
+                self._carry_optimizer = None
             self._engine = eng
         return self._engine
 
@@ -289,12 +315,17 @@ class CXRBERT(nn.Module):
                 dist.broadcast_object_list(box, src=0)
                 return box[0]
             eng.comm_init(dist.get_rank(), dist.get_world_size(), bcast)
-            if dist.get_backend() == "nccl":
-                dist.broadcast(eng.params, src=0)
-            else:                                   # a CPU-only group (gloo) carries the id; weights go through the host
-                host = eng.params.cpu()
-                dist.broadcast(host, src=0)
-                eng.params.copy_(host)
+            # rank 0's weights win — the trainable arena AND the frozen ResNet trunk with its BatchNorm buffers (main_origin
+            # seeds with seed + rank before the model is built, so without this every rank would train against its own trunk)
+            trunk = [t for t in list(self.enc.img_encoder.parameters()) + list(self.enc.img_encoder.buffers())]
+            for t in [eng.params] + trunk:
+                if dist.get_backend() == "nccl":
+                    dist.broadcast(t.data, src=0)
+                else:                               # a CPU-only group (gloo) carries the id; weights go through the host
+                    host = t.data.cpu()
+                    dist.broadcast(host, src=0)
+                    t.data.copy_(host)
+            self.enc.img_encoder._exec = None       # cached dtype / layout copies of the conv weights are stale now
             self.sync_params()
         return eng.world
 
@@ -397,7 +428,9 @@ class CXRBERT(nn.Module):
                                     train=True, mode=mode[sl], t_len=t_len[sl], txt_labels=lab[sl], is_aligned=is_aligned[sl],
                                     feats=None if feats is None else feats[sl], n_lab_global=n_lab_g, batch_global=b_g,
                                     global_counts=counts)
-            eng.backward(batch, allreduce=(eng.world > 1 and ci == len(chunks) - 1))
+            # gradients are exchanged only by the call that also steps the optimizer: with optimizer_step=False the local
+            # sums stay local, so a later call adds to them and all-reduces ONCE (summed twice they would be scaled by world)
+            eng.backward(batch, allreduce=(optimizer_step and eng.world > 1 and ci == len(chunks) - 1))
         if optimizer_step:
             eng.adamw_step(lr=float(self.args.lr if lr is None else lr))
 

@@ -181,12 +181,26 @@ class ImageEncoder_cnn(nn.Module):
     def __init__(self, args):
         super().__init__()
         self.args = args
-        # reference: resnet50(pretrained=True) (image.py:50).  Use the ImageNet checkpoint only when it is already in the
-        # local torch-hub cache (no network here); otherwise the same architecture with random init.
-        ckpt = os.path.join(torch.hub.get_dir(), "checkpoints", "resnet50-0676ba61.pth")
+        # reference: resnet50(pretrained=True) (image.py:50).  The ImageNet checkpoint is taken from the local torch-hub
+        # cache (or args.resnet_weights); there is no network download here.  The trunk is frozen, so a silently random
+        # trunk would stay random for the whole run: without the checkpoint construction FAILS unless the caller opts in
+        # with args.allow_random_trunk (--allow_random_trunk) or MEDVILL_ALLOW_RANDOM_TRUNK=1 (benchmarks, parity runs, a
+        # state_dict loaded right after construction).
+        ckpt = getattr(args, "resnet_weights", None) or os.path.join(torch.hub.get_dir(), "checkpoints", "resnet50-0676ba61.pth")
         model = torchvision.models.resnet50(weights=None)
-        if os.path.isfile(ckpt):
+        self.pretrained_trunk = os.path.isfile(ckpt)
+        if self.pretrained_trunk:
             model.load_state_dict(torch.load(ckpt, map_location="cpu"))
+        elif not (getattr(args, "allow_random_trunk", False) or os.environ.get("MEDVILL_ALLOW_RANDOM_TRUNK", "0") not in ("0", "")):
+            raise _lib.MedvillError(
+                "ImageNet ResNet-50 weights not found at %s (the reference uses resnet50(pretrained=True), models/image.py:50) and the "
+                "trunk is frozen.  Put resnet50-0676ba61.pth there, pass args.resnet_weights, or opt in to a randomly initialised "
+                "trunk with args.allow_random_trunk=True (--allow_random_trunk) or MEDVILL_ALLOW_RANDOM_TRUNK=1" % ckpt)
+        else:
+            import warnings
+
+            warnings.warn("ImageEncoder_cnn: ImageNet weights not found (%s): the frozen ResNet-50 trunk is RANDOMLY initialised "
+                          "until a state_dict is loaded" % ckpt, stacklevel=2)
         self.model = nn.Sequential(*list(model.children())[:-2])
         self.region_idx_override = None     # parity runs inject the sampled regions (the reference uses the CPU RNG)
         self._exec = None
@@ -206,11 +220,10 @@ class ImageEncoder_cnn(nn.Module):
 
     def grid_features(self, x, dtype=None):
         """[B, 3, h, w] -> [B, (h/32)*(w/32), 2048], contiguous, channels-last under the hood."""
-        if x.is_cuda:
-            with torch.no_grad():
-                out = self.executor(dtype or x.dtype)(x, self.training)       # cuDNN convs + mv_bn_forward
-        else:
-            out = self.model(x if dtype is None else x.to(dtype))             # host-side use of the container only
+        if not x.is_cuda:
+            raise _lib.MedvillError("ImageEncoder_cnn needs CUDA tensors (sm_100a): there is no CPU fallback")
+        with torch.no_grad():
+            out = self.executor(dtype or x.dtype)(x, self.training)           # cuDNN convs + mv_bn_forward
         B, Cc = out.shape[0], out.shape[1]
         return out.permute(0, 2, 3, 1).reshape(B, -1, Cc)      # free view when `out` is channels-last
 

@@ -50,7 +50,9 @@ class BertForPreTrainingLossMask(nn.Module):
         inner = types.SimpleNamespace(img_hidden_sz=args.img_hidden_sz, embedding_size=args.hidden_size, hidden_size=args.hidden_size,
                                       dropout_prob=drop, img_encoder="random-pixel", num_image_embeds=len_vis_input, img_size=img_size,
                                       seq_len=max_b, lr=getattr(args, "learning_rate", 3e-5), precision=getattr(args, "precision", "bf16"),
-                                      max_micro_batch=int(getattr(args, "max_micro_batch", 64)), seed=int(getattr(args, "seed", 123)))
+                                      max_micro_batch=int(getattr(args, "max_micro_batch", 64)), seed=int(getattr(args, "seed", 123)),
+                                      allow_random_trunk=bool(getattr(args, "allow_random_trunk", False)),
+                                      resnet_weights=getattr(args, "resnet_weights", None), engine_flags=int(getattr(args, "engine_flags", 0)))
         cx = CXRBERT(cfg, inner)
         object.__setattr__(self, "_cxrbert", cx)                          # engine owner, not a registered sub-module
         self.txt_embeddings = cx.enc.txt_embeddings                        # model.py:907-923

@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# tests build the model on synthetic / fixture weights: a randomly initialised trunk is what they want (the product refuses it)
+os.environ.setdefault("MEDVILL_ALLOW_RANDOM_TRUNK", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

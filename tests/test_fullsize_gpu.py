@@ -1,5 +1,10 @@
-"""Full-size checks (BASELINE.json configs[1]: BERT-base, 64 samples, 180 regions + 253 report tokens, L = 436, bf16) through
-size-independent properties — the CPU oracle needs minutes per sample at this size, so parity here is structural:
+"""Full-size checks (BASELINE.json configs[1]: BERT-base, 64 samples, 180 regions + 253 report tokens, L = 436, bf16).
+
+1. `test_full_size_oracle_parity`: the CPU oracle on the SAME 64 samples (micro-batches of 8 with the global loss
+   normalisers, ~1 minute of host time) against the engine: losses, every labelled row's logits over the whole vocabulary,
+   MLM / ITM counters, and every gradient tensor.  This is the size at which the 256-row CTA-pair GEMM tiles, the split-K
+   weight gradients over K = 27 904 rows and the 4 x 4 attention tile schedule actually run.
+2. `test_full_size_step_properties`: size-independent properties of the same step:
 
   * micro-batch additivity: 64 samples in one launch sequence == the same samples as 4 micro-batches of 16 with the global
     loss normalisers (loss sums, accuracy counters and every gradient: a checksum of checksums);
@@ -104,3 +109,96 @@ def test_full_size_step_properties():
     assert small.engine(CHUNK).max_batch == CHUNK
     chunked, g_chunk = _step(small, batch, feats)
     _close(chunked, ref, g_chunk.to(g_ref.device), g_ref)
+
+
+def _oracle_chunked(orc, params, batch, cfg, feats, chunk=8):
+    """loss_and_grads of the CPU oracle over the 64 samples in micro-batches (fp32; the [B, 12, L, L] attention tensors of a
+    full batch would need ~25 GB of host memory for autograd): each chunk's loss is its CE SUMS over the GLOBAL counts, so
+    the accumulated gradient equals the single-batch gradient of models/train_origin.py:118-130 exactly."""
+    import torch.nn.functional as F
+
+    names = orc.trainable_names(cfg)
+    leaf = dict(params)
+    for n in names:
+        leaf[n] = params[n].detach().clone().requires_grad_(True)
+    B = batch["input_ids"].shape[0]
+    labels = torch.as_tensor(batch["txt_labels"])
+    n_lab = int((labels != -100).sum())
+    tot = dict(mlm=0.0, itm=0.0, mlm_correct=0, itm_correct=0)
+    lab_logits = []
+    per_sample = ("cls_tok", "input_ids", "txt_labels", "attn_masks", "segment", "sep_tok", "is_aligned", "mode", "t_len")
+    for s0 in range(0, B, chunk):
+        sl = slice(s0, min(B, s0 + chunk))
+        sub = {k: (v[sl] if k in per_sample else v) for k, v in batch.items() if k != "image"}
+        logits, itm = orc.forward(leaf, sub, cfg, feats=feats[sl])
+        lab = labels[sl]
+        mlm_sum = F.cross_entropy(logits.transpose(1, 2), lab, ignore_index=-100, reduction="sum")
+        itm_sum = F.cross_entropy(itm, torch.as_tensor(sub["is_aligned"]), reduction="sum")
+        (mlm_sum / n_lab + itm_sum / B).backward()
+        ic, mc, _ = orc.step_metrics(logits.detach(), itm.detach(), sub)
+        tot["mlm"] += float(mlm_sum.detach()); tot["itm"] += float(itm_sum.detach()); tot["mlm_correct"] += mc; tot["itm_correct"] += ic
+        lab_logits.append(logits.detach()[lab != -100])
+    grads = {n: leaf[n].grad for n in names}
+    return dict(mlm_loss=tot["mlm"] / n_lab, itm_loss=tot["itm"] / B, mlm_correct=tot["mlm_correct"], itm_correct=tot["itm_correct"],
+                n_lab=n_lab, lab_logits=torch.cat(lab_logits), grads=grads)
+
+
+def test_full_size_oracle_parity():
+    """configs[1] shapes end to end against the CPU oracle (north_star tolerances: bf16 losses / logits 1e-2 relative)."""
+    import time
+
+    import numpy as np
+
+    import medvill_b200 as m
+    from oracle import medvill_oracle as orc
+
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    cfg = orc.Cfg()                                                    # BERT-base, N = 180, S = 253 -> L = 436
+    assert cfg.L == 436 and cfg.hidden == 768 and cfg.layers == 12
+    params = orc.synth_params(cfg, seed=0, resnet=False)
+    batch = orc.synthetic_batch(cfg, B, seed=77, mode=orc.MODE_BAR)
+    # grid features handed to both sides (values exactly representable in bf16, so both see the same operand)
+    feats = (torch.randn(B, cfg.grid, cfg.img_hidden, generator=torch.Generator().manual_seed(5)) * 0.5).to(torch.bfloat16).float()
+    t0 = time.time()
+    ref = _oracle_chunked(orc, params, batch, cfg, feats)
+    print("oracle: %.1f s on %d threads, mlm %.5f itm %.5f, %d labelled rows" % (time.time() - t0, torch.get_num_threads(), ref["mlm_loss"],
+                                                                                ref["itm_loss"], ref["n_lab"]))
+    dims = m.EngineDims(hidden=cfg.hidden, heads=cfg.heads, layers=cfg.layers, inter=cfg.inter, vocab=cfg.vocab, max_pos=cfg.max_pos,
+                        type_vocab=cfg.type_vocab, num_image_embeds=cfg.num_image_embeds, seq_len=cfg.seq_len, img_hidden=cfg.img_hidden,
+                        grid=cfg.grid, ln_eps=cfg.ln_eps, head_ln_eps=cfg.head_ln_eps, dropout_p=0.0)
+    eng = m.PretrainEngine(dims, "cuda:0", precision="bf16", max_batch=B)
+    eng.load_params(params)
+    b = eng.make_batch(cls_tok=batch["cls_tok"], input_ids=batch["input_ids"], segment=batch["segment"], sep_tok=batch["sep_tok"],
+                       mode=batch["mode"], t_len=batch["t_len"], region_idx=batch["region_idx"], feats=feats,
+                       txt_labels=batch["txt_labels"], is_aligned=batch["is_aligned"], seed=1, train=True)
+    assert b.n_lab == ref["n_lab"]
+    eng.zero_grads(); eng.stats_reset()
+    eng.forward(b)
+    st = eng.read_stats()
+    ld = eng.layout["vocab_padded"]
+    logits = eng.peek("logits", shape=(b.n_lab, ld), dtype=torch.float32)[:, :cfg.vocab].double()
+    eng.backward(b)
+    torch.cuda.synchronize()
+    mlm, itm = st["mlm_loss_sum"] / b.n_lab, st["itm_loss_sum"] / b.B
+    want = ref["lab_logits"].double()
+    rel_l2 = float((logits - want).norm() / want.norm())
+    print("full size: mlm %.5f (ref %.5f) itm %.5f (ref %.5f); labelled-row logits rel-L2 %.3e; mlm_correct %d/%d itm_correct %d/%d" % (
+        mlm, ref["mlm_loss"], itm, ref["itm_loss"], rel_l2, st["mlm_correct"], ref["mlm_correct"], st["itm_correct"], ref["itm_correct"]))
+    assert abs(mlm - ref["mlm_loss"]) <= 1e-2 * ref["mlm_loss"] and abs(itm - ref["itm_loss"]) <= 1e-2 * max(1.0, ref["itm_loss"])
+    assert rel_l2 <= 1e-2, rel_l2
+    assert abs(st["itm_correct"] - ref["itm_correct"]) <= 1      # a logit pair within bf16 noise of a tie may flip
+    scale = max(float(v.norm()) for v in ref["grads"].values())
+    worst_cos, worst_norm = 1.0, 0.0
+    for n, r in ref["grads"].items():
+        got = eng.view(n, eng.grads).float().cpu().flatten().double()
+        r = r.flatten().double()
+        if float(r.norm()) <= 1e-4 * scale:                      # analytically-zero gradients (key biases)
+            assert float(got.norm()) <= 1e-3 * scale, n
+            continue
+        cos = float(got @ r / (got.norm() * r.norm()))
+        ratio = abs(float(got.norm() / r.norm()) - 1.0)
+        worst_cos, worst_norm = min(worst_cos, cos), max(worst_norm, ratio)
+        assert cos >= 0.99, "grad cosine %s: %.5f" % (n, cos)
+        assert ratio <= 0.05, "grad norm %s: %.4e vs %.4e" % (n, float(got.norm()), float(r.norm()))
+    print("full size: worst gradient cosine %.5f, worst norm deviation %.4f over %d tensors" % (worst_cos, worst_norm, len(ref["grads"])))
+    eng.close()

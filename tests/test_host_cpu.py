@@ -127,4 +127,4 @@ def test_main_origin_parser_keeps_the_reference_command_line():
             assert set(spec["choices"]) <= set(act.choices), flag
         if spec.get("type") in ("int", "float", "str"):
             assert act.type is {"int": int, "float": float, "str": str}[spec["type"]], flag
-    assert set(ours) - set(ref) == {"--precision", "--compact_masks", "--max_micro_batch"}
+    assert set(ours) - set(ref) == {"--precision", "--compact_masks", "--max_micro_batch", "--allow_random_trunk", "--resnet_weights"}

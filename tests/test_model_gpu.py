@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import medvill_oracle as orc
-from tests.util import golden_batch, load_golden
+from tests.util import oracle_feats, golden_batch, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -133,8 +133,11 @@ def test_stem_tail_bn_relu_maxpool_vs_torch(dtype, tol):
     assert (y.float().cpu() - ref).abs().max() <= tol * ref.abs().max()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 0.5)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
 def test_resnet_trunk_with_library_batchnorm(precision, tol):
+    """fp32: element probes against the reference fixture (max-norm 2e-4).  bf16 (the production trunk: cuDNN bf16
+    convolutions + the library's bf16 BatchNorm kernels, 53 train-mode BN layers): relative Frobenius error over the FULL
+    [B, grid, 2048] feature map against the CPU oracle's fp32 trunk; measured 1.1e-2 (profiles/r02_trunk_bf16_error.txt)."""
     g, cfg = load_golden("tiny_bar")
     batch = golden_batch(g, cfg)
     model, params = make_model(cfg, precision)
@@ -144,7 +147,12 @@ def test_resnet_trunk_with_library_batchnorm(precision, tol):
     assert feats.shape == (3, cfg.grid, 2048)
     ref = g["feats_sample"]
     got = feats[:, :: max(1, cfg.grid // 8), ::64].numpy()
-    assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
+    if precision == "fp32":
+        assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
+    full = oracle_feats(params, batch).double()
+    rel_l2 = float((feats.double() - full).norm() / full.norm())
+    print("trunk %s: rel-L2 over the full map %.3e, probes max-norm %.3e" % (precision, rel_l2, np.abs(got - ref).max() / np.abs(ref).max()))
+    assert rel_l2 <= tol, rel_l2
     # running statistics were updated once with momentum 0.1 (train-mode BN on frozen weights)
     bn1 = model.enc.img_encoder.model[1]
     assert int(bn1.num_batches_tracked) == 1

@@ -163,10 +163,11 @@ def autocast_logit_error(o):
 
 
 def test_step_bf16_config1():
-    """BERT-base, L=436, B=2 (BASELINE.json configs[0] shapes) in the production bf16 mode.  Losses: 1e-2 relative.
-    Logits: relative Frobenius error <= 2e-2 and <= 1.5x the PyTorch-autocast bf16 floor (see autocast_logit_error)."""
+    """BERT-base, L=436, B=2 (BASELINE.json configs[0] shapes) in the production bf16 mode.  Losses and logits: 1e-2
+    relative (north_star); logits also <= 1.3x the PyTorch-autocast bf16 floor (see autocast_logit_error) — met because
+    the residual stream (pre-LayerNorm sums and the LayerNorm outputs that feed the next residual add) is kept in fp32."""
     o = run_step("config1_bar", "bf16")
-    check_forward(o, 2e-2, 4e-2)
+    check_forward(o, 1e-2, 3e-2)
     g = o["g"]
     assert abs(o["mlm_loss"] - float(g["mlm_loss"])) <= 1e-2 * float(g["mlm_loss"])
     assert abs(o["mlm_loss"] + o["itm_loss"] - float(g["loss"])) <= 1e-2 * float(g["loss"])
@@ -174,6 +175,6 @@ def test_step_bf16_config1():
     ours = np.linalg.norm(diff) / np.linalg.norm(g["lab_logits"].astype(np.float64))
     floor = autocast_logit_error(o)
     print("bf16 logits rel-L2: ours %.3e, torch autocast floor %.3e" % (ours, floor))
-    assert ours <= 2.0 * floor        # our residual stream is stored in bf16; autocast keeps LN outputs / residuals in fp32
+    assert ours <= 1.3 * floor        # same rounding points as autocast: bf16 GEMM operands, fp32 residual stream
     w = check_grads_vs_oracle(o, 0.99, 0.08)
     print("worst grad cosine %.5f" % w)

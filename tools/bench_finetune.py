@@ -25,7 +25,7 @@ ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 B = a.batch
-args = types.SimpleNamespace(img_hidden_sz=2048, hidden_size=768, img_postion=True, img_encoding="fully_use_cnn", len_vis_input=256,
+args = types.SimpleNamespace(img_hidden_sz=2048, hidden_size=768, img_postion=True, img_encoding="fully_use_cnn", allow_random_trunk=True, len_vis_input=256,
                              img_size=512, max_len_b=253, precision="bf16", max_micro_batch=B, tasks="report_generation")
 torch.manual_seed(0)
 model = BertForPreTrainingLossMask(BertConfig.from_pretrained("bert-base-uncased"), args, len_vis_input=256).to(dev).train()

@@ -27,7 +27,7 @@ ap.add_argument("--reports", type=int, default=256)
 ap.add_argument("--pair-batch", type=int, default=64)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-margs = types.SimpleNamespace(img_hidden_sz=2048, embedding_size=768, hidden_size=768, dropout_prob=0.1, img_encoder="random-pixel",
+margs = types.SimpleNamespace(img_hidden_sz=2048, embedding_size=768, hidden_size=768, dropout_prob=0.1, img_encoder="random-pixel", allow_random_trunk=True,
                               num_image_embeds=180, img_size=512, seq_len=253, lr=1e-5, precision="bf16", max_micro_batch=a.pair_batch,
                               seed=123, weight_load=False)
 torch.manual_seed(0)

@@ -20,7 +20,7 @@ ap.add_argument("--dropout", type=float, default=0.1)
 ap.add_argument("--warmup", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-margs = types.SimpleNamespace(img_hidden_sz=2048, embedding_size=768, hidden_size=768, dropout_prob=a.dropout, img_encoder="random-pixel",
+margs = types.SimpleNamespace(img_hidden_sz=2048, embedding_size=768, hidden_size=768, dropout_prob=a.dropout, img_encoder="random-pixel", allow_random_trunk=True,
                               num_image_embeds=180, img_size=512, seq_len=253, lr=1e-5, precision="bf16", max_micro_batch=a.batch, seed=123)
 torch.manual_seed(0)
 model = CXRBERT(BertConfig.from_pretrained("bert-base-uncased"), margs).to(dev).train()
