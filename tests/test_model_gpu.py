@@ -133,26 +133,71 @@ def test_stem_tail_bn_relu_maxpool_vs_torch(dtype, tol):
     assert (y.float().cpu() - ref).abs().max() <= tol * ref.abs().max()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
-def test_resnet_trunk_with_library_batchnorm(precision, tol):
-    """fp32: element probes against the reference fixture (max-norm 2e-4).  bf16 (the production trunk: cuDNN bf16
-    convolutions + the library's bf16 BatchNorm kernels, 53 train-mode BN layers): relative Frobenius error over the FULL
-    [B, grid, 2048] feature map against the CPU oracle's fp32 trunk; measured 1.1e-2 (profiles/r02_trunk_bf16_error.txt)."""
+def _damp_last_bn(model, params, gamma3):
+    """every bottleneck's last BatchNorm scale (bn3.weight) <- gamma3, in the module and in the oracle's parameter dict"""
+    with torch.no_grad():
+        for n, p in model.enc.img_encoder.named_parameters():
+            if n.endswith("bn3.weight"):
+                p.fill_(gamma3)
+                params["enc.img_encoder." + n] = torch.full_like(params["enc.img_encoder." + n], gamma3)
+    model.enc.img_encoder._exec = None
+
+
+def test_resnet_trunk_bf16_production_path():
+    """The production trunk (cuDNN bf16 convolutions + the library's bf16 BatchNorm kernels, 53 train-mode BN layers) over the
+    FULL [B, grid, 2048] feature map, relative Frobenius error against fp32:
+      * well-conditioned weights (every block's last BN scale damped to 0.1, zero_init_residual-style — what a trained trunk
+        looks like to rounding noise): <= 3e-2 against the CPU oracle;
+      * the fixture's random-init weights: a BatchNorm'd random ReLU network amplifies ANY perturbation layer by layer (our own
+        fp32 path vs torch fp32 already differ by 2e-4 from 1e-7 roundings), so no bf16 implementation can be close to fp32
+        there — measured 0.55 for this path AND for torch.autocast(bf16) of the torchvision module at 512 x 512, B = 16
+        (profiles/r02_trunk_bf16_error.txt).  Gate: not worse than 1.25x that autocast floor."""
+    g, cfg = load_golden("tiny_bar")
+    batch = golden_batch(g, cfg)
+    model, params = make_model(cfg, "bf16")
+    model.train()
+    enc = model.enc.img_encoder
+    img = batch["image"].to("cuda:0")
+    state = {k: v.clone() for k, v in enc.state_dict().items()}
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+
+    def floor_and_ours(ref):
+        enc.load_state_dict(state)
+        ours = enc.grid_features(img, dtype=torch.bfloat16).float().cpu()
+        enc.load_state_dict(state)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            ac = enc.model(img).permute(0, 2, 3, 1).reshape(img.shape[0], -1, 2048).float().cpu()
+        enc.load_state_dict(state)
+        return rel(ours, ref), rel(ac, ref)
+
+    ours, floor = floor_and_ours(oracle_feats(params, batch))
+    print("trunk bf16, random-init fixture weights: ours %.3e, torch autocast floor %.3e" % (ours, floor))
+    assert ours <= 1.25 * floor + 1e-3
+    _damp_last_bn(model, params, 0.1)
+    state = {k: v.clone() for k, v in enc.state_dict().items()}
+    ours, floor = floor_and_ours(oracle_feats(params, batch))
+    print("trunk bf16, damped weights (bn3.weight = 0.1): ours %.3e, torch autocast floor %.3e" % (ours, floor))
+    assert ours <= 3e-2, ours
+    assert ours <= 1.25 * floor + 1e-3
+
+
+def test_resnet_trunk_with_library_batchnorm():
+    """fp32 check mode: element probes against the reference fixture (max-norm 2e-4) and the full map against the oracle"""
+    precision, tol = "fp32", 2e-4
     g, cfg = load_golden("tiny_bar")
     batch = golden_batch(g, cfg)
     model, params = make_model(cfg, precision)
     model.train()
-    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    dt = torch.float32
     feats = model.enc.img_encoder.grid_features(batch["image"].to("cuda:0"), dtype=dt).float().cpu()
     assert feats.shape == (3, cfg.grid, 2048)
     ref = g["feats_sample"]
     got = feats[:, :: max(1, cfg.grid // 8), ::64].numpy()
-    if precision == "fp32":
-        assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
+    assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), np.abs(got - ref).max() / np.abs(ref).max()
     full = oracle_feats(params, batch).double()
     rel_l2 = float((feats.double() - full).norm() / full.norm())
-    print("trunk %s: rel-L2 over the full map %.3e, probes max-norm %.3e" % (precision, rel_l2, np.abs(got - ref).max() / np.abs(ref).max()))
-    assert rel_l2 <= tol, rel_l2
+    print("trunk fp32: rel-L2 over the full map %.3e, probes max-norm %.3e" % (rel_l2, np.abs(got - ref).max() / np.abs(ref).max()))
+    assert rel_l2 <= 2e-4, rel_l2
     # running statistics were updated once with momentum 0.1 (train-mode BN on frozen weights)
     bn1 = model.enc.img_encoder.model[1]
     assert int(bn1.num_batches_tracked) == 1
