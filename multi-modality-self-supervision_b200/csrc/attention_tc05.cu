@@ -7,6 +7,8 @@
 //   * probabilities never touch HBM: forward keeps one row per thread (online softmax), backward recomputes P from
 //     the saved row log-sum-exp; attention-probability dropout is regenerated from a counter-based RNG.
 // Reference arithmetic: upstream BertSelfAttention (twin: .../pytorch_pretrained_bert/model.py:301-320).
+#include <limits.h>
+
 #include "attn_common.cuh"
 #include "kernels.h"
 #include "tc05.cuh"
@@ -117,6 +119,14 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
   int m_lo, m_hi;
   mask_row_interval(mode, min(q, L - 1), A, tl, L, m_lo, m_hi);
   const uint32_t m_span = static_cast<uint32_t>(m_hi - m_lo);
+  // warp-level bounds of the rows' allowed key intervals (rows past the sequence end excluded): a 32-column chunk starting
+  // at c_lo can hold an allowed entry only if c_lo < w_hi and c_lo + 31 >= w_lo; chunks that cannot cost one zero store
+  int w_lo = q < L ? m_lo : INT_MAX, w_hi = q < L ? m_hi : INT_MIN;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    w_lo = min(w_lo, __shfl_xor_sync(0xffffffffu, w_lo, o));
+    w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
+  }
   float o_acc[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
@@ -168,8 +178,16 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
       ref = (mx == -INFINITY ? mx_any : mx) * scale2;
     }
     float m_raw = -INFINITY;                 // running max of the RAW scores of this tile
+    const int n_kk = (min(TK, L - k_lo) + 15) >> 4;     // the PV product spans only the key columns that exist
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+      const int c_lo = kc0 + c * 32;
+      if (c_lo - k_lo >= 16 * n_kk) break;               // beyond the PV product's K extent: never read
+      if (!(c_lo < w_hi && c_lo + 31 >= w_lo)) {         // no row of this warp sees these keys: P = 0
+        const uint32_t zero[16] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        store_pk32(sP, r, ch * 2 + c, zero);
+        continue;
+      }
       uint32_t v[32];
       tmem_ld32(t_lane + ch * 64 + c * 32, v);
       tmem_ld_wait();
@@ -201,12 +219,13 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
         // dropped probabilities are zeroed with one AND per bf16 pair; the 1/(1-p) keep-scale is applied once to O
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (kc0 + c * 32 + 16 * g) >> 4));
-          const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
+          const uint4 rnd = dropout_rand16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (kc0 + c * 32 + 16 * g) >> 4));
+          const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            pk[8 * g + 2 * w] &= __byte_perm(kw[w], 0, 0x1100);
-            pk[8 * g + 2 * w + 1] &= __byte_perm(kw[w], 0, 0x3322);
+            const uint32_t fl = keep_flags4_any(rw[w], a.drop.thresh4);
+            pk[8 * g + 2 * w] &= keep_mask_pair(fl, 0);
+            pk[8 * g + 2 * w + 1] &= keep_mask_pair(fl, 1);
           }
         }
       }
@@ -221,8 +240,7 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
       mbar_wait(&sh->bar_v, ph);
       const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
       if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < TK / 16; ++kk)
+        for (int kk = 0; kk < n_kk; ++kk)
           umma_bf16(tmem + 128, make_smem_desc_sw128(pa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
                     make_smem_desc_sw128(va + kk * 2048, 8192, 1024), idesc_o, kk > 0);
         umma_commit(&sh->bar_o);
@@ -529,6 +547,14 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mask_row_interval(mode, q_ok ? q : 0, A, tl, L, m_lo, m_hi);
     const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L) &&
                       (q_lo + TQ <= L);
+    // warp-level bounds of the rows' allowed key intervals (rows past the sequence end excluded): a 16-column chunk that no
+    // row of this warp can see is stored as zeros without touching TMEM, the exponentials or the dropout generator
+    int w_lo = q_ok ? m_lo : INT_MAX, w_hi = q_ok ? m_hi : INT_MIN;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      w_lo = min(w_lo, __shfl_xor_sync(0xffffffffu, w_lo, o));
+      w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
+    }
     TL_MARK();
     mbar_wait(&sh->bar_s, it & 1u);
     tc_fence_after();
@@ -536,6 +562,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int col = cq * 32 + c * 16;                  // column inside the 128-wide tile
+      uint32_t pk[8], dk[8];
+      if (k_lo + col < w_hi && k_lo + col + 15 >= w_lo) {
       uint32_t sv[16], dv[16];
       tmem_ld16(t_lane + col, sv);
       tmem_ld16(t_lane + 128 + col, dv);
@@ -556,20 +584,23 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         for (int e = 0; e < 16; ++e)
           p[e] = (static_cast<uint32_t>(e - rel_lo) < span) ? ex2(fmaf(__uint_as_float(sv[e]), scale2, -lse2)) : 0.f;
       }
-      uint32_t pk[8], dk[8];
       if (a.drop_on) {
-        const uint4 keep = dropout_keep16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + col) >> 4));
-        const uint32_t kw[4] = {keep.x, keep.y, keep.z, keep.w};
+        const uint4 rnd = dropout_rand16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + col) >> 4));
+        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
+          const uint32_t fl = keep_flags4_any(rw[w], a.drop.thresh4);
+          // per-lane masks: byte j of `fl` has bit 7 set iff element 4 w + j is kept
+          const uint32_t m01 = keep_mask_pair(fl, 0), m23 = keep_mask_pair(fl, 1);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int e = 4 * w + 2 * hh;
-            // dP masked by the keep bytes (all-ones / zero per element), then dS = p * (dP * keep_scale - delta)
-            const float t0 = __uint_as_float(dv[e] & __byte_perm(kw[w], 0, hh ? 0x2222 : 0x0000));
-            const float t1 = __uint_as_float(dv[e + 1] & __byte_perm(kw[w], 0, hh ? 0x3333 : 0x1111));
+            const uint32_t mp = hh ? m23 : m01;
+            // dP masked by the keep masks (all-ones / zero per element), then dS = p * (dP * keep_scale - delta)
+            const float t0 = __uint_as_float(dv[e] & keep_mask_elem(fl, 2 * hh));
+            const float t1 = __uint_as_float(dv[e + 1] & keep_mask_elem(fl, 2 * hh + 1));
             dk[e >> 1] = pack_bf16x2(p[e] * fmaf(t0, a.drop.scale, -delta), p[e + 1] * fmaf(t1, a.drop.scale, -delta));
-            pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]) & __byte_perm(kw[w], 0, hh ? 0x3322 : 0x1100);
+            pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]) & mp;
           }
         }
       } else {
@@ -578,6 +609,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           dk[e >> 1] = pack_bf16x2(p[e] * (__uint_as_float(dv[e]) - delta), p[e + 1] * (__uint_as_float(dv[e + 1]) - delta));
           pk[e >> 1] = pack_bf16x2(p[e], p[e + 1]);
         }
+      }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { pk[e] = 0u; dk[e] = 0u; }
       }
       // this staging buffer last held tile it-2: its products were waited for when dQ(it-2) was drained; the
       // reduce-add of that dQ (staged in the P half) must have read it too
@@ -651,7 +686,8 @@ constexpr uint32_t kBwdSmem = 1024 + 6 * TILE_BYTES + 4 * P_BYTES + sizeof(BwdSm
 
 }  // namespace
 
-int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s) {
+// r01 forward (one query tile per CTA, serial S -> softmax -> PV); kept for A/B runs and for dropout thresholds > 128
+int attention_fwd_legacy_tc05(const AttnArgs& a, cudaStream_t s) {
   MV_REQUIRE(a.qkv && a.ctx && a.lse && a.mode && a.t_len, "attention_fwd: null argument");
   const int H = a.nh * D;
   CUtensorMap tm;

@@ -140,6 +140,28 @@ __device__ __forceinline__ uint4 dropout_keep16(const DropoutCfg& d, uint32_t si
   r.z = __vcmpgeu4(r.z, d.thresh4); r.w = __vcmpgeu4(r.w, d.thresh4);
   return r;
 }
+// The raw 128 random bits of group `g` (16 x 8-bit lanes): dropout_keep16 == byte-wise (lane >= threshold) of this.
+__device__ __forceinline__ uint4 dropout_rand16(const DropoutCfg& d, uint32_t site, uint64_t g) {
+  return philox4x32_7(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), site, 0x4d56u, static_cast<uint32_t>(d.seed),
+                      static_cast<uint32_t>(d.seed >> 32));
+}
+// Keep FLAGS of four 8-bit lanes: bit 7 of byte i is set iff lane i >= threshold (the same decision as __vcmpgeu4, whose
+// software emulation costs ~10 instructions per word; this is 3).  Valid for thresholds <= 128, i.e. p <= 0.5:
+//   lane >= 128: bit 7 of r itself;  lane < 128: (lane | 0x80) - T = 128 + lane - T has bit 7 set iff lane >= T, and never
+//   borrows from the next byte because 128 + lane - T >= 128 - T >= 0.
+__device__ __forceinline__ uint32_t keep_flags4(uint32_t r, uint32_t thresh4) { return ((r | 0x80808080u) - thresh4) | r; }
+// any threshold: thresholds above 128 (p > 0.5) take the emulated byte compare, whose 0xFF / 0x00 lanes are valid flags too
+__device__ __forceinline__ uint32_t keep_flags4_any(uint32_t r, uint32_t thresh4) {
+  return (thresh4 & 0xFFu) <= 128u ? keep_flags4(r, thresh4) : __vcmpgeu4(r, thresh4);
+}
+// Expand the flags of lanes (2j, 2j+1) of `flags` into a bf16x2 AND-mask: PRMT with sign replication (selector bit 3)
+// copies bit 7 of the selected byte into all eight bits of the destination byte.
+__device__ __forceinline__ uint32_t keep_mask_pair(uint32_t flags, int j) {     // j = 0: lanes 0,1;  j = 1: lanes 2,3
+  uint32_t m;                          // inline PTX: the __byte_perm intrinsic documents only selector bits [2:0] of each nibble
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(flags), "r"(0u), "r"(j ? 0xBBAAu : 0x9988u));
+  return m;
+}
+
 __device__ __forceinline__ bool keep16_bit(const uint4& m, int i) {   // i in [0,16)
   const uint32_t w = i < 4 ? m.x : (i < 8 ? m.y : (i < 12 ? m.z : m.w));
   return (w >> (8 * (i & 3))) & 1u;
@@ -155,6 +177,13 @@ __device__ __forceinline__ uint32_t keep16_half_bits(const uint4& m, int half) {
 // 8 consecutive elements starting at flat element index e (e % 8 == 0): bit j = element j kept
 __device__ __forceinline__ uint32_t dropout_keep8(const DropoutCfg& d, uint32_t site, uint64_t e) {
   return keep16_half_bits(dropout_keep16(d, site, e >> 4), static_cast<int>((e >> 3) & 1));
+}
+
+// all-ones / zero 32-bit mask of lane j (0..3) of `flags` (for fp32 operands)
+__device__ __forceinline__ uint32_t keep_mask_elem(uint32_t flags, int j) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(m) : "r"(flags), "r"(0u), "r"(0x8888u + 0x1111u * static_cast<uint32_t>(j)));
+  return m;
 }
 
 // ---- warp / block reductions ----
