@@ -132,6 +132,18 @@ typedef struct mv_step_stats {
 } mv_step_stats;
 enum { MV_ERR_TOKEN_ID = 1, MV_ERR_SEGMENT_ID = 2, MV_ERR_REGION_IDX = 4, MV_ERR_MLM_LABEL = 8 };
 
+/* Gradients computed by the CALLER for mv_backward_external: the torch.autograd drop-in path runs the reference's own loss
+ * code on the outputs of CXRBERT.forward (models/train_origin.py:118-130) and hands d(loss)/d(outputs) back.  Every pointer is
+ * optional (NULL = that output received no gradient). */
+typedef struct mv_external_grads {
+  int32_t n_rows;              /* rows of the [B*L, V] prediction scores whose gradient is not identically zero              */
+  const int64_t* rows;         /* [n_rows] flattened b * L + s, ascending (device)                                            */
+  const void* dlogits;         /* [n_rows, vocab_padded] activation dtype: gradient of those rows, pad columns zero (device)  */
+  const float* d_itm;          /* [B, 2] fp32: gradient of the ITM logits (device)                                            */
+  const void* d_seq;           /* [B*L, hidden] activation dtype: gradient of the final hidden states (CXRBertEncoder output) */
+  const void* d_pooled;        /* [B, hidden] activation dtype: gradient of the pooled output (CXRBertEncoder output)         */
+} mv_external_grads;
+
 typedef struct mv_gemm_desc {
   int32_t M, N, K;
   const void* A; int64_t lda; int32_t a_mn;   /* a_mn = 0: A is [M,K] row-major; 1: stored [K,M]                    */
@@ -162,6 +174,8 @@ int mv_stats_reset(mv_handle* h, void* stream);
 int mv_forward(mv_handle* h, const mv_batch* b, void* stream);           /* fwd + both losses + metrics             */
 int mv_backward(mv_handle* h, const mv_batch* b, int32_t allreduce, void* stream);  /* grads += ; optional bucketed */
                                                                          /* NCCL all-reduce overlapped with bwd     */
+/* backward from caller-supplied output gradients (grads +=), same bucketed all-reduce option as mv_backward */
+int mv_backward_external(mv_handle* h, const mv_batch* b, const mv_external_grads* g, int32_t allreduce, void* stream);
 int mv_zero_grads(mv_handle* h, void* stream);
 int mv_adamw_step(mv_handle* h, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                   float grad_scale, void* stream);                       /* waits for pending all-reduces; zeroes g */
@@ -234,6 +248,11 @@ int mv_normalize_u8_s2d(const uint8_t* src, void* dst, int32_t B, int32_t H, int
 int mv_bn_relu_maxpool(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, const float* gamma, const float* beta,
                        float* running_mean, float* running_var, float momentum, float eps, int32_t training, float* workspace,
                        int64_t ws_floats, int32_t precision, void* stream);
+/* ImageTextMatching.forward as a stand-alone op (models/cxrbert_origin.py:164-173; Downstream_task/Retrieval/retrieval.py:32):
+ * logits[B,2] = pooled[B,H] . w[2,H]^T + b; with dlogits != NULL also the backward: d_pooled[B,H] (activation dtype),
+ * dw[2,H] += , db[2] += (fp32). */
+int mv_itm_head(const void* pooled, const float* w, const float* b, float* logits, int32_t B, int32_t H, const float* dlogits,
+                void* d_pooled, float* dw, float* db, int32_t precision, void* stream);
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
 

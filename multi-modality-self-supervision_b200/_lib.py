@@ -56,6 +56,11 @@ class mv_step_stats(C.Structure):
                 ("error_flags", C.c_int32)]
 
 
+class mv_external_grads(C.Structure):
+    _fields_ = [("n_rows", C.c_int32), ("rows", C.c_void_p), ("dlogits", C.c_void_p), ("d_itm", C.c_void_p), ("d_seq", C.c_void_p),
+                ("d_pooled", C.c_void_p)]
+
+
 class mv_gemm_desc(C.Structure):
     _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("A", C.c_void_p), ("lda", C.c_int64), ("a_mn", C.c_int32),
@@ -80,6 +85,7 @@ SYMBOLS = {
     "mv_stats_reset": (_I, [_P, _P]),
     "mv_forward": (_I, [_P, C.POINTER(mv_batch), _P]),
     "mv_backward": (_I, [_P, C.POINTER(mv_batch), _I, _P]),
+    "mv_backward_external": (_I, [_P, C.POINTER(mv_batch), C.POINTER(mv_external_grads), _I, _P]),
     "mv_zero_grads": (_I, [_P, _P]),
     "mv_adamw_step": (_I, [_P, _F, _F, _F, _F, _F, _I, _F, _P]),
     "mv_bert_adam_step": (_I, [_P, _F, _F, _F, _F, _F, _F, _P]),
@@ -109,6 +115,7 @@ SYMBOLS = {
     "mv_normalize_u8": (_I, [_P, _P, _L, _L, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _P]),
     "mv_normalize_u8_s2d": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _P]),
     "mv_bn_relu_maxpool": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _F, _F, _I, _P, _L, _I, _P]),
+    "mv_itm_head": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
     "mv_adamw": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _I, _P]),
 }
 

@@ -95,6 +95,12 @@ int mv_backward(mv_handle* h, const mv_batch* b, int32_t allreduce, void* stream
   return h->eng.backward(*b, allreduce, S(stream));
 }
 
+int mv_backward_external(mv_handle* h, const mv_batch* b, const mv_external_grads* g, int32_t allreduce, void* stream) {
+  MV_CHECK_HANDLE(h);
+  MV_REQUIRE(b && g, "mv_backward_external: null argument");
+  return h->eng.backward_external(*b, *g, allreduce, S(stream));
+}
+
 int mv_zero_grads(mv_handle* h, void* stream) {
   MV_CHECK_HANDLE(h);
   MV_REQUIRE(h->eng.grads, "arenas not bound");
@@ -340,6 +346,19 @@ int mv_bn_relu_maxpool(const void* x, void* y, int32_t B, int32_t H, int32_t W, 
                        int64_t ws_floats, int32_t precision, void* stream) {
   return bn_relu_maxpool(x, y, B, H, W, C, gamma, beta, running_mean, running_var, momentum, eps, training, workspace, ws_floats,
                          precision == MV_PREC_FP32, S(stream));
+}
+
+int mv_itm_head(const void* pooled, const float* w, const float* b, float* logits, int32_t B, int32_t H, const float* dlogits,
+                void* d_pooled, float* dw, float* db, int32_t precision, void* stream) {
+  MV_REQUIRE(pooled && w && b && logits && B > 0 && H > 0, "mv_itm_head: bad arguments");
+  MV_REQUIRE(!dlogits || (d_pooled && dw && db), "mv_itm_head: backward needs d_pooled, dw, db");
+  static float* scratch = nullptr;            // loss / accuracy sinks the fused kernel always writes
+  if (!scratch) MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&scratch), 16));
+  ItmArgs a;
+  a.B = B; a.H = H; a.pooled = pooled; a.w = w; a.b = b; a.labels = nullptr; a.gscale = 1.f; a.logits = logits;
+  a.loss_sum = scratch; a.correct = reinterpret_cast<int*>(scratch + 1);
+  a.d_pre = dlogits ? d_pooled : nullptr; a.dw = dw; a.db = db; a.ext_dlogits = dlogits; a.no_tanh = 1;
+  return itm_head_fwd_bwd(a, precision == MV_PREC_FP32, S(stream));
 }
 
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,

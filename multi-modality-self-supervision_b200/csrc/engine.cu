@@ -406,9 +406,7 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
   if (b.n_lab > 0) {
     MV_REQUIRE(b.lab_rows && b.lab_labels, "mv_batch: n_lab > 0 needs lab_rows / lab_labels");
     const int n = b.n_lab;
-    MV_TRY(gather_rows(seq, rows_h, reinterpret_cast<const int64_t*>(b.lab_rows), n, n, 0, H, f32, s));
-    MV_TRY(linear_fwd(rows_h, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
-    MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, n, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
+    MV_TRY(mlm_head_rows(reinterpret_cast<const int64_t*>(b.lab_rows), n, dc, s));
     MV_TRY(linear_fwd(t_ln, n, H, lay.word, cfg.vocab, lay.mlm_bias, logits, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, Vpad));
     CeArgs ca;
     ca.n = n; ca.V = cfg.vocab; ca.ldv = Vpad; ca.logits = logits; ca.labels = reinterpret_cast<const int64_t*>(b.lab_labels);
@@ -440,6 +438,55 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
   return 0;
 }
 
+// MLM head up to the decoder input for the given rows of the final hidden states (cxrbert_origin.py:205-218)
+int Engine::mlm_head_rows(const int64_t* rows, int n, const DropoutCfg& dc, cudaStream_t s) {
+  const int H = cfg.hidden;
+  MV_TRY(ensure_mlm(n));
+  MV_TRY(gather_rows(x[cfg.layers], rows_h, rows, n, n, 0, H, f32, s));
+  MV_TRY(linear_fwd(rows_h, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
+  MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, n, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
+  return 0;
+}
+
+// Backward from gradients the CALLER computed (the torch.autograd drop-in path: loss functions run in PyTorch on the
+// [B, L, V] / [B, 2] outputs, models/train_origin.py:118-130).  Only rows of the logit gradient that are not identically
+// zero are handed over (CrossEntropy(ignore_index=-100) zeroes every unlabelled position); the head is re-run for those rows
+// to rebuild what its backward needs, then the common backward runs.
+int Engine::backward_external(const mv_batch& b_in, const mv_external_grads& g, int allreduce, cudaStream_t s) {
+  MV_REQUIRE(b_in.train, "mv_backward_external needs a batch forwarded with train=1");
+  MV_REQUIRE(g.n_rows >= 0 && g.n_rows <= b_in.B * L, "mv_backward_external: n_rows out of range");
+  MV_REQUIRE(g.n_rows == 0 || (g.rows && g.dlogits), "mv_backward_external: rows / dlogits missing");
+  const int H = cfg.hidden, B = b_in.B;
+  const DropoutCfg dc0 = make_dropout(0.f, 0);
+  mv_batch b = b_in;
+  b.n_lab = g.n_rows; b.lab_rows = g.rows; b.lab_labels = nullptr;
+  if (g.n_rows > 0) MV_TRY(mlm_head_rows(reinterpret_cast<const int64_t*>(g.rows), g.n_rows, dc0, s));
+  // pooler pre-activation gradient: from the ITM logits' gradient (through the ITM linear layer) and / or from a gradient
+  // on the pooled output itself
+  bool have_pre = false;
+  if (g.d_itm) {
+    ItmArgs ia;
+    ia.B = B; ia.H = H; ia.pooled = pooled; ia.w = params + lay.itm_w; ia.b = params + lay.itm_b; ia.labels = nullptr;
+    ia.gscale = 1.f; ia.logits = itm_logits; ia.loss_sum = &stats->itm_loss_sum; ia.correct = &stats->itm_correct;
+    ia.d_pre = d_pre; ia.dw = grads + lay.itm_w; ia.db = grads + lay.itm_b; ia.ext_dlogits = g.d_itm;
+    MV_TRY(itm_head_fwd_bwd(ia, f32, s));
+    have_pre = true;
+  }
+  if (g.d_pooled) {
+    MV_TRY(tanh_bwd(g.d_pooled, pooled, d_pre, static_cast<long>(B) * H, have_pre ? 1 : 0, f32, s));
+    have_pre = true;
+  }
+  mv_batch bb = b;
+  static const int64_t kDummy = 0;
+  bb.is_aligned = have_pre ? &kDummy : nullptr;      // backward() only tests it for null (d_pre is ready)
+  ext_dlogits = g.n_rows > 0 ? g.dlogits : nullptr;
+  ext_dseq = g.d_seq;
+  const int rc = backward(bb, allreduce, s);
+  ext_dlogits = nullptr;
+  ext_dseq = nullptr;
+  return rc;
+}
+
 int Engine::bucket_done(size_t idx, int allreduce, cudaStream_t s) {
   if (!allreduce || world <= 1) return 0;
   MV_REQUIRE(comm != nullptr, "allreduce requested but mv_comm_init was not called");
@@ -463,7 +510,9 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
   const DropoutCfg dc = make_dropout(cfg.dropout_p, b.dropout_seed);
   const DropoutCfg dc_att = make_dropout(cfg.attn_dropout_p, b.dropout_seed);
   void* P = dxa; void* Q = dxb; void* R = dxc;
-  MV_CUDA_CHECK(cudaMemsetAsync(P, 0, static_cast<size_t>(M) * H * es, s));   // d(seq): only labelled + [CLS] rows are non-zero
+  if (ext_dseq) MV_CUDA_CHECK(cudaMemcpyAsync(P, ext_dseq, static_cast<size_t>(M) * H * es, cudaMemcpyDeviceToDevice, s));
+  else MV_CUDA_CHECK(cudaMemsetAsync(P, 0, static_cast<size_t>(M) * H * es, s));   // d(seq): only labelled + [CLS] rows are non-zero
+  const void* dlogits = ext_dlogits ? ext_dlogits : this->dlogits;                // shadows the member on purpose
 
   // --- MLM head backward ---
   if (b.n_lab > 0) {
@@ -484,7 +533,7 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     MV_TRY(colsum_add(d_tpre, H, n, H, grads + lay.mlm_tb, f32, s));
     MV_TRY(linear_wgrad(d_tpre, H, rows_h, n, H, H, lay.mlm_tw, s));
     MV_TRY(linear_dgrad(d_tpre, H, n, H, lay.mlm_tw, H, d_rows, EPI_NONE, nullptr, s));
-    MV_TRY(scatter_rows(d_rows, P, reinterpret_cast<const int64_t*>(b.lab_rows), n, n, 0, H, 0, f32, s));
+    MV_TRY(scatter_rows(d_rows, P, reinterpret_cast<const int64_t*>(b.lab_rows), n, n, 0, H, ext_dseq ? 1 : 0, f32, s));
   }
   // --- pooler backward (d_pre was produced by the ITM kernel in forward) ---
   if (b.is_aligned) {
@@ -598,12 +647,16 @@ int Engine::bert_adam(float lr, float beta1, float beta2, float eps, float weigh
 int Engine::full_logits(const mv_batch& b, float* out, int64_t ld, cudaStream_t s) {
   const int H = cfg.hidden, M = b.B * L;
   MV_REQUIRE(ld >= cfg.vocab && ld % 4 == 0, "full_logits: ld must be >= vocab and a multiple of 4");
-  MV_TRY(ensure_mlm(M));
+  // in row chunks through the head's existing [mlm_cap, H] buffers (growing them to B*L rows would also grow the
+  // [rows, V] logit / gradient buffers of the training path: ~5 GB at B = 64)
   const DropoutCfg dc = make_dropout(0.f, 0);
-  const void* seq = x[cfg.layers];
-  MV_TRY(linear_fwd(seq, M, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
-  MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, M, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
-  MV_TRY(linear_fwd(t_ln, M, H, lay.word, cfg.vocab, lay.mlm_bias, out, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, ld));
+  const char* seq = static_cast<const char*>(x[cfg.layers]);
+  for (int r0 = 0; r0 < M; r0 += mlm_cap) {
+    const int n = M - r0 < mlm_cap ? M - r0 : mlm_cap;
+    MV_TRY(linear_fwd(seq + static_cast<size_t>(r0) * H * es, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
+    MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, n, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
+    MV_TRY(linear_fwd(t_ln, n, H, lay.word, cfg.vocab, lay.mlm_bias, out + static_cast<size_t>(r0) * ld, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, ld));
+  }
   return 0;
 }
 

@@ -92,6 +92,10 @@ struct Engine {
   int forward(const mv_batch& b, cudaStream_t s);
   int backward(const mv_batch& b, int allreduce, cudaStream_t s);
   int full_logits(const mv_batch& b, float* out, int64_t ld, cudaStream_t s);
+  int mlm_head_rows(const int64_t* rows, int n, const DropoutCfg& dc, cudaStream_t s);   // rows of x[layers] -> rows_h, t_pre, t_act, t_ln
+  int backward_external(const mv_batch& b, const mv_external_grads& g, int allreduce, cudaStream_t s);
+  const void* ext_dlogits = nullptr;     // backward(): gradient of the labelled-row logits supplied by the caller (autograd path)
+  const void* ext_dseq = nullptr;        // backward(): gradient w.r.t. the final hidden states [B*L, H] supplied by the caller
   int bucket_done(size_t idx, int allreduce, cudaStream_t s);
 };
 

@@ -69,6 +69,8 @@ int gather_rows(const void* src, void* dst, const int64_t* idx, int n, int perio
 int scatter_rows(const void* src, void* dst, const int64_t* idx, int n, int period, long stride, int H, int add,
                  int f32, cudaStream_t s);
 int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaStream_t s);          // dx = dy * gelu'(pre)
+// d_pre (+)= d_out * (1 - out^2): backward of out = tanh(pre) (BertPooler)
+int tanh_bwd(const void* d_out, const void* out, void* d_pre, long n, int add, int f32, cudaStream_t s);
 int cast_f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t s);
 int cast_bf16_to_f32(const bf16* src, float* dst, long n, cudaStream_t s);
 int mask_dump(const unsigned char* mode, const int* t_len, int B, int A, int L, unsigned char* out, cudaStream_t s);
@@ -117,6 +119,7 @@ struct ItmArgs {
   float* loss_sum; int* correct;
   void* d_pre;                       // [B, H] activation dtype: grad w.r.t. pooler pre-activation; null = forward only
   float* dw; float* db;              // fp32 grads (atomic)
+  int no_tanh = 0;                     // 1: d_pre receives the gradient w.r.t. `pooled` itself (stand-alone ITM head), not w.r.t. the tanh input
   const float* ext_dlogits = nullptr;  // optional [B, 2]: gradient w.r.t. the logits supplied by the caller (autograd path) instead of the CE
 };
 int itm_head_fwd_bwd(const ItmArgs& a, int f32, cudaStream_t s);

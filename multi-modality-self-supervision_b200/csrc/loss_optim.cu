@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) itm_kernel(const ItmArgs a) {
       const float x = to_f32<T>(p[j]);
       atomicAdd(a.dw + j, d0 * x);
       atomicAdd(a.dw + a.H + j, d1 * x);
-      dp[j] = from_f32<T>((d0 * a.w[j] + d1 * a.w[a.H + j]) * (1.f - x * x));
+      dp[j] = from_f32<T>((d0 * a.w[j] + d1 * a.w[a.H + j]) * (a.no_tanh ? 1.f : (1.f - x * x)));
     }
   }
 }

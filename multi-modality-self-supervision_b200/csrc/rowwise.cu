@@ -466,6 +466,15 @@ __global__ void __launch_bounds__(256) dgelu_kernel(const T* __restrict__ dy, co
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ dpre, long n, int add) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const float y = to_f32<T>(out[i]);
+    const float g = to_f32<T>(dout[i]) * (1.f - y * y);
+    dpre[i] = from_f32<T>(add ? to_f32<T>(dpre[i]) + g : g);
+  }
+}
+
 __global__ void cast_f2b_kernel(const float* __restrict__ s, bf16* __restrict__ d, long n) {
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
     d[i] = __float2bfloat16_rn(s[i]);
@@ -686,6 +695,15 @@ int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaSt
   int grid = static_cast<int>((n8 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   MV_DISPATCH_T(f32, (dgelu_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(pre), static_cast<T*>(dx), n8)));
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+
+int tanh_bwd(const void* d_out, const void* out, void* d_pre, long n, int add, int f32, cudaStream_t s) {
+  if (n <= 0) return 0;
+  int grid = static_cast<int>((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  MV_DISPATCH_T(f32, (tanh_bwd_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(d_out), static_cast<const T*>(out), static_cast<T*>(d_pre), n, add)));
   MV_LAUNCH_CHECK();
   return 0;
 }

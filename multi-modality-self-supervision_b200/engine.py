@@ -266,6 +266,14 @@ class PretrainEngine:
     def backward(self, batch, allreduce=False):
         check(lib().mv_backward(self._h, C.byref(batch.c), 1 if allreduce else 0, stream_ptr(self.device)), "mv_backward")
 
+    def backward_external(self, batch, rows=None, dlogits=None, d_itm=None, d_seq=None, d_pooled=None, allreduce=False):
+        """Backward from output gradients computed by the caller (torch.autograd drop-in path); tensors on the device."""
+        n = 0 if rows is None else int(rows.numel())
+        g = _lib.mv_external_grads(n_rows=n, rows=ptr(rows) if n else None, dlogits=ptr(dlogits) if n else None, d_itm=ptr(d_itm),
+                                   d_seq=ptr(d_seq), d_pooled=ptr(d_pooled))
+        check(lib().mv_backward_external(self._h, C.byref(batch.c), C.byref(g), 1 if allreduce else 0, stream_ptr(self.device)),
+              "mv_backward_external")
+
     def zero_grads(self):
         check(lib().mv_zero_grads(self._h, stream_ptr(self.device)), "mv_zero_grads")
 

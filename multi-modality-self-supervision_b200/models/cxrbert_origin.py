@@ -29,6 +29,66 @@ _FUSED_MSG = ("%s.forward is fused into libmedvill_sm100 (mv_forward); call CXRB
               "CXRBERT.pretrain_step instead")
 
 
+class _JointForward(torch.autograd.Function):
+    """CXRBERT.forward / CXRBertEncoder.forward under torch.autograd: the reference's own training loop
+    (`mlm, itm = model(...)`; `loss = CE(mlm.transpose(1, 2), labels) + CE(itm, is_aligned)`; `loss.backward()`;
+    `optimizer.step()` — models/train_origin.py:106-131) and Retrieval/retrieval.py:29-32 run on it unmodified.
+    forward = mv_forward (+ mv_full_logits); backward = mv_backward_external, which accumulates straight into the
+    gradient arena the nn.Parameters' .grad tensors are views of (so no per-parameter gradient is returned here)."""
+
+    @staticmethod
+    def forward(ctx, anchor, owner, kind, cls_tok, input_txt, attn_mask, segment, input_img, sep_tok):
+        if int(input_txt.shape[0]) > owner.engine().max_batch:
+            raise _lib.MedvillError("autograd forward: batch %d exceeds args.max_micro_batch = %d (one set of saved activations)"
+                                    % (int(input_txt.shape[0]), owner.engine().max_batch))
+        eng, batch = owner._encode(cls_tok, input_txt, attn_mask, segment, input_img, sep_tok, train=True)
+        owner._generation += 1
+        ctx.owner, ctx.eng, ctx.batch, ctx.kind, ctx.generation = owner, eng, batch, kind, owner._generation
+        d = eng.dims
+        if kind == "logits":
+            logits = eng.full_logits(batch)
+            itm = torch.empty(batch.B, 2, dtype=torch.float32, device=eng.device)
+            owner._peek_into("itm_logits", 0, itm)
+            return logits, itm
+        seq = torch.empty(batch.B * d.L, d.hidden, dtype=eng.act_dtype, device=eng.device)
+        owner._peek_into("x", d.layers, seq)
+        pooled = torch.empty(batch.B, d.hidden, dtype=eng.act_dtype, device=eng.device)
+        owner._peek_into("pooled", 0, pooled)
+        return seq.view(batch.B, d.L, d.hidden).float(), pooled.float()
+
+    @staticmethod
+    def backward(ctx, g_a, g_b):
+        owner, eng, batch = ctx.owner, ctx.eng, ctx.batch
+        if owner._generation != ctx.generation or owner._engine is not eng:
+            raise _lib.MedvillError("backward through a CXRBERT forward whose activations were overwritten by a later forward "
+                                    "(the engine keeps ONE set of saved activations): call backward before the next forward")
+        owner._prepare_grads()
+        d = eng.dims
+        kw = {}
+        if ctx.kind == "logits":
+            if g_a is not None:
+                M, V, ld = batch.B * d.L, d.vocab, eng.layout["vocab_padded"]
+                g = g_a.reshape(M, V)
+                rows = torch.nonzero((g != 0).any(dim=1)).reshape(-1)       # CE(ignore_index=-100): unlabelled rows are exactly 0
+                if rows.numel():
+                    dl = torch.zeros(rows.numel(), ld, dtype=eng.act_dtype, device=eng.device)
+                    dl[:, :V] = g.index_select(0, rows)
+                    kw.update(rows=rows, dlogits=dl)
+            if g_b is not None:
+                kw["d_itm"] = g_b.to(torch.float32).contiguous()
+        else:
+            if g_a is not None:
+                kw["d_seq"] = g_a.reshape(batch.B * d.L, d.hidden).to(eng.act_dtype).contiguous()
+            if g_b is not None:
+                kw["d_pooled"] = g_b.to(eng.act_dtype).contiguous()
+        eng.backward_external(batch, allreduce=eng.world > 1, **kw)
+        if eng.world > 1:            # DistributedDataParallel semantics: the ranks' gradients are averaged
+            eng.comm_sync()
+            eng.grads.mul_(1.0 / eng.world)
+        owner._generation += 1       # the saved activations are consumed
+        return (None,) * 9
+
+
 # ---- parameter containers with the upstream (HF BertModel) attribute names -------------------------------------------
 class _Embeddings(nn.Module):
     def __init__(self, config):
@@ -150,6 +210,9 @@ class CXRBertEncoder(nn.Module):
         if self._owner is None:
             raise RuntimeError("CXRBertEncoder must be owned by a CXRBERT (the engine lives on the top-level module)")
         owner = self._owner()
+        if owner._wants_grad():
+            seq, pooled = _JointForward.apply(owner._anchor(), owner, "enc", cls_tok, input_txt, attn_mask, segment, input_img, sep_tok)
+            return seq, pooled, None
         eng, batch = owner._encode(cls_tok, input_txt, attn_mask, segment, input_img, sep_tok, train=self.training)
         d = eng.dims
         seq = torch.empty(batch.B * d.L, d.hidden, dtype=eng.act_dtype, device=eng.device)
@@ -157,6 +220,38 @@ class CXRBertEncoder(nn.Module):
         pooled = torch.empty(batch.B, d.hidden, dtype=eng.act_dtype, device=eng.device)
         owner._peek_into("pooled", 0, pooled)
         return seq.view(batch.B, d.L, d.hidden).float(), pooled.float(), None
+
+
+class _ItmHead(torch.autograd.Function):
+    """Linear(hidden, 2) on the pooled output through mv_itm_head (forward and backward)"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if not x.is_cuda:
+            raise _lib.MedvillError("ImageTextMatching needs CUDA tensors (sm_100a): there is no CPU fallback")
+        act = torch.float32 if x.dtype == torch.float32 else torch.bfloat16
+        xa = x.detach().to(act).contiguous()
+        B, H = xa.shape
+        out = torch.empty(B, 2, dtype=torch.float32, device=x.device)
+        prec = _lib.MV_PREC_FP32 if act == torch.float32 else _lib.MV_PREC_BF16
+        _lib.check(_lib.lib().mv_itm_head(_lib.ptr(xa), _lib.ptr(weight.detach()), _lib.ptr(bias.detach()), _lib.ptr(out), B, H, None, None,
+                                          None, None, prec, _lib.stream_ptr(x.device)), "mv_itm_head")
+        ctx.save_for_backward(xa, weight, bias)
+        ctx.prec, ctx.x_dtype = prec, x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xa, weight, bias = ctx.saved_tensors
+        B, H = xa.shape
+        g = g.to(torch.float32).contiguous()
+        dx = torch.empty_like(xa)
+        dw, db = torch.zeros(2, H, dtype=torch.float32, device=xa.device), torch.zeros(2, dtype=torch.float32, device=xa.device)
+        scratch = torch.empty(B, 2, dtype=torch.float32, device=xa.device)
+        _lib.check(_lib.lib().mv_itm_head(_lib.ptr(xa), _lib.ptr(weight.detach()), _lib.ptr(bias.detach()), _lib.ptr(scratch), B, H,
+                                          _lib.ptr(g), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), ctx.prec, _lib.stream_ptr(xa.device)),
+                   "mv_itm_head")
+        return dx.to(ctx.x_dtype), dw, db
 
 
 class ImageTextMatching(nn.Module):
@@ -167,7 +262,8 @@ class ImageTextMatching(nn.Module):
         self.linear = nn.Linear(hidden, 2)
 
     def forward(self, x):
-        raise RuntimeError(_FUSED_MSG % "ImageTextMatching")
+        """Linear(hidden, 2) on a pooled output, as Downstream_task/Retrieval/retrieval.py:29-32 composes it"""
+        return _ItmHead.apply(x, self.linear.weight, self.linear.bias)
 
 
 class BertLayerNorm(nn.Module):
@@ -222,6 +318,37 @@ class CXRBERT(nn.Module):
         self.enc._owner = weakref.ref(self)
         self._engine = None
         self._dropout_step = 0
+        self._generation = 0         # bumped by every autograd forward / backward (one set of saved activations)
+
+    # -- torch.autograd drop-in path --
+    def _wants_grad(self):
+        return self.training and torch.is_grad_enabled() and self.enc.pooler.dense.weight.requires_grad
+
+    def _anchor(self):
+        """a leaf that requires grad, so that autograd calls _JointForward.backward (its own gradient is None there: the
+        engine accumulates into the arena that IS every parameter's .grad)"""
+        eng = self.engine()
+        eng.refresh_shadow()         # an external optimizer may have stepped the fp32 master parameters in place
+        return self.itm.linear.bias
+
+    def _prepare_grads(self):
+        """Before an accumulating backward: parameters whose .grad was dropped (optimizer.zero_grad(set_to_none=True)) mean a
+        fresh gradient -> zero the arena once and re-attach the .grad views (in-place zero_grad keeps the views)."""
+        eng = self._engine
+        named = self._trainable()
+        if all(p.grad is None for p in named.values()):
+            eng.zero_grads()
+            for n, p in named.items():
+                p.grad = eng.view(n, eng.grads)
+            return
+        for n, p in named.items():          # mixed state (e.g. ImageTextMatching's own backward already ran): tensor by tensor
+            view = eng.view(n, eng.grads)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
 
     # -- engine plumbing --
     def dims(self):
@@ -391,12 +518,23 @@ class CXRBERT(nn.Module):
         return eng, batch
 
     def forward(self, cls_tok, input_txt, attn_mask, segment, input_img, sep_tok):
-        """-> (prediction_scores [B, L, V] fp32, itm_logits [B, 2] fp32), detached.  Signature: cxrbert_origin.py:144."""
-        eng, batch = self._encode(cls_tok, input_txt, attn_mask, segment, input_img, sep_tok, train=False)
-        logits = eng.full_logits(batch)
-        itm = torch.empty(batch.B, 2, dtype=torch.float32, device=eng.device)
-        self._peek_into("itm_logits", 0, itm)
-        return logits, itm
+        """-> (prediction_scores [B, L, V] fp32, itm_logits [B, 2] fp32).  Signature: cxrbert_origin.py:144.  In training mode
+        with autograd enabled the outputs carry a grad_fn (see _JointForward); otherwise they are plain tensors."""
+        if self._wants_grad():
+            return _JointForward.apply(self._anchor(), self, "logits", cls_tok, input_txt, attn_mask, segment, input_img, sep_tok)
+        B = int(input_txt.shape[0])
+        cap = self.engine(min(B, int(getattr(self.args, "max_micro_batch", 64)))).max_batch
+        outs = []
+        for s0 in range(0, B, cap):                  # micro-batches of at most max_batch samples, as eval_step does
+            sl = slice(s0, min(B, s0 + cap))
+            eng, batch = self._encode(cls_tok[sl], input_txt[sl], attn_mask[sl], segment[sl], input_img[sl], sep_tok[sl], train=self.training)
+            logits = eng.full_logits(batch)
+            itm = torch.empty(batch.B, 2, dtype=torch.float32, device=eng.device)
+            self._peek_into("itm_logits", 0, itm)
+            outs.append((logits, itm))
+        if len(outs) == 1:
+            return outs[0]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
 
     def pretrain_step(self, cls_tok, input_ids, txt_labels, attn_masks, image, segment, is_aligned, sep_tok, lr=None,
                       mode=None, t_len=None, optimizer_step=True, feats=None, lazy=False):

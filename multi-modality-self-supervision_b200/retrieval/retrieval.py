@@ -52,6 +52,9 @@ class CXRBertForRetrieval(nn.Module):
     def forward(self, cls_tok, input_txt, attn_mask, segment, input_img, sep_tok):
         """-> ITM logits [B, 2] fp32 (retrieval.py:29-32): pooled [CLS] of the joint encoder -> Linear(768, 2)."""
         owner = self._cxrbert
+        if owner._wants_grad():                             # training: exactly the reference's composition, differentiable
+            _, cls, _ = self.enc(cls_tok, input_txt, attn_mask, segment, input_img, sep_tok)
+            return self.itm(cls)
         eng, batch = owner._encode(cls_tok, input_txt, attn_mask, segment, input_img, sep_tok, train=self.training)
         itm = torch.empty(batch.B, 2, dtype=torch.float32, device=eng.device)
         owner._peek_into("itm_logits", 0, itm)

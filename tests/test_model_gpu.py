@@ -217,12 +217,15 @@ def test_forward_dropin_full_logits_fp32(name):
     model.enc.img_encoder.region_idx_override = batch["region_idx"]
     t = lambda k: torch.as_tensor(batch[k]).to("cuda:0")
     logits, itm = model(t("cls_tok"), t("input_ids"), t("attn_masks"), t("segment"), batch["image"].to("cuda:0"), t("sep_tok"))
+    assert logits.grad_fn is not None and itm.grad_fn is not None      # training mode: the outputs are differentiable
+    logits, itm = logits.detach(), itm.detach()
     assert logits.shape == (int(g["B"]), cfg.L, cfg.vocab) and itm.shape == (int(g["B"]), 2)
     rows = g["lab_rows"]
     got = logits[rows[:, 0], rows[:, 1]][:, torch.as_tensor(g["lab_cols"]).to("cuda:0")].cpu().numpy()
     assert np.abs(got - g["lab_logits"]).max() <= 2e-4 * np.abs(g["lab_logits"]).max()
     assert np.abs(itm.cpu().numpy() - g["itm_logits"]).max() <= 2e-4
-    seq, pooled, att = model.enc(t("cls_tok"), t("input_ids"), t("attn_masks"), t("segment"), batch["image"].to("cuda:0"), t("sep_tok"))
+    with torch.no_grad():
+        seq, pooled, att = model.enc(t("cls_tok"), t("input_ids"), t("attn_masks"), t("segment"), batch["image"].to("cuda:0"), t("sep_tok"))
     assert att is None and pooled.shape == (int(g["B"]), cfg.hidden)
     ref = g["seq_sample"]
     got = seq[:, :: max(1, cfg.L // 16), :: max(1, cfg.hidden // 32)].cpu().numpy()
