@@ -273,7 +273,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
     set_maxnreg_inc<104>();
     // =============================================== softmax groups ===============================================
     // 8 warps per group: TMEM lane quarter lq = warp % 4 (32 query rows), column half ch: TWO threads per query row, each
-    // owning 64 of the 128 key columns of S / P and 32 of the 64 columns of O.  Four softmax warps per scheduler: a warp
+    // owning two of the four 32-column chunks of S / P (interleaved: ch, ch + 2) and 32 of the 64 columns of O.  Four softmax warps per scheduler: a warp
     // that has just issued a MUFU.EX2 (8 issue cycles on the 16-lane XU) or waits on a Philox dependency leaves the slot
     // to three others (one thread per row left two warps per scheduler at 0.27 IPC, profiles/r02_attn_fwd_ws_notes.md).
     const int w = warp >> 3;
@@ -281,7 +281,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
     const int lq = w8 & 3, ch = w8 >> 2;
     const int r = lq * 32 + lane;
     const uint32_t t_lane = tmem + (static_cast<uint32_t>(lq * 32) << 16);
-    const uint32_t t_s = t_lane + 128 * w + 64 * ch, t_o = t_lane + 256 + 64 * w + 32 * ch;
+    const uint32_t t_s = t_lane + 128 * w + 32 * ch, t_o = t_lane + 256 + 64 * w + 32 * ch;
     uint8_t* sPw = smem + OFF_P + w * P_BYTES;
     const float scale2 = 0.125f * kLog2e;
     const bool drop_on = a.drop_on != 0;
@@ -320,10 +320,29 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
       for (int j = 0; j < n_kv; ++j) {
         if (!act(it, w, j)) continue;
         const int k_lo = j * TK;
+        const int n_col = ((min(TK, L - k_lo) + 15) >> 4) << 4;             // key columns the PV product reads
+        // Dropout keep flags of this thread's two 32-column chunks, generated BEFORE waiting for S: the Philox rounds depend
+        // only on (b, h, q, key group), so they run in the shadow of the S = Q K^T round trip instead of after it.
+        uint32_t kf[2][8];
+        if (drop_on && !warp_oob) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int c_lo = k_lo + 32 * ch + 64 * c;
+            if (32 * ch + 64 * c < n_col && c_lo < hi_max && c_lo + 31 >= lo_min) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) {
+                const uint4 rnd = dropout_rand16(a.drop, a.drop_site, attn_drop_group(it.b, a.nh, it.h, L, qc, (c_lo + 16 * g) >> 4));
+                kf[c][4 * g + 0] = keep_flags4(rnd.x, a.drop.thresh4);
+                kf[c][4 * g + 1] = keep_flags4(rnd.y, a.drop.thresh4);
+                kf[c][4 * g + 2] = keep_flags4(rnd.z, a.drop.thresh4);
+                kf[c][4 * g + 3] = keep_flags4(rnd.w, a.drop.thresh4);
+              }
+            }
+          }
+        }
         mbar_wait(&sh->s_full[w], s_cnt & 1u);
         ++s_cnt;
         tc_fence_after();
-        const int n_col = ((min(TK, L - k_lo) + 15) >> 4) << 4;             // key columns the PV product reads
         float m_raw = -INFINITY;
         if (!warp_oob) {
           if (!have_prev) {
@@ -353,14 +372,16 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
           }
 #pragma unroll 1
           for (int c = 0; c < 2; ++c) {
-            const int cc = 64 * ch + 32 * c;               // first column of the chunk inside the tile
+            const int cc = 32 * ch + 64 * c;               // first column of the chunk inside the tile: the two threads of a row
+                                                           // own INTERLEAVED chunks (ch, ch + 2), so a tile that is half past the
+                                                           // sequence end or half masked still splits evenly between them
             if (cc >= n_col) break;
             const int c_lo = k_lo + cc;
             uint32_t pk[16];
             const bool any = c_lo < hi_max && c_lo + 31 >= lo_min;      // hi_max <= L
             if (any) {
               uint32_t v[32];
-              tmem_ld32(t_s + 32 * c, v);
+              tmem_ld32(t_s + 64 * c, v);
               tmem_ld_wait();
               const int rel_lo = m_lo - c_lo, rel_hi = m_hi - c_lo;
               const bool full = warp_whole && lo_max <= c_lo && c_lo + 32 <= hi_min;
@@ -387,15 +408,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
               }
               if (drop_on) {
 #pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                  const uint4 rnd = dropout_rand16(a.drop, a.drop_site, attn_drop_group(it.b, a.nh, it.h, L, qc, (c_lo + 16 * g) >> 4));
-                  const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-#pragma unroll
-                  for (int x = 0; x < 4; ++x) {
-                    const uint32_t fl = keep_flags4(rw[x], a.drop.thresh4);
-                    pk[8 * g + 2 * x] &= keep_mask_pair(fl, 0);
-                    pk[8 * g + 2 * x + 1] &= keep_mask_pair(fl, 1);
-                  }
+                for (int x = 0; x < 8; ++x) {
+                  const uint32_t fl = c == 0 ? kf[0][x] : kf[1][x];
+                  pk[2 * x] &= keep_mask_pair(fl, 0);
+                  pk[2 * x + 1] &= keep_mask_pair(fl, 1);
                 }
               }
             } else {
@@ -403,10 +419,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
               for (int i = 0; i < 16; ++i) pk[i] = 0u;
             }
             if (c == 0 && have_prev) wait_prev_o();          // the previous PV product has finished reading this P buffer
-            store_pk32(sPw, r, 2 * ch + c, pk);
+            store_pk32(sPw, r, ch + 2 * c, pk);
           }
           if (have_prev) {
-            if (64 * ch >= n_col) wait_prev_o();             // (this thread stored nothing above)
+            if (32 * ch >= n_col) wait_prev_o();             // (this thread stored nothing above)
             if (__any_sync(0xffffffffu, alpha_pend != 1.f)) {
               // rare: some row of this warp moved its reference: rescale its O columns in TMEM (tcgen05.ld / st are
               // warp-collective; rows that did not move multiply by 1).  The previous PV product is complete (waited above).

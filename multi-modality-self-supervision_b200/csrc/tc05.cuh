@@ -66,12 +66,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Rare path of the wait loops, kept out of line so that the loop body is try_wait + counter only: a waiting warp re-executes
+// its loop every time the hardware wakes it (r02 ncu: ~30 wake-ups per wait in the attention kernel), and with the clock
+// read inlined each wake-up cost 13 issue slots that the math warps on the same scheduler wanted.
+static __device__ __noinline__ void mbar_timeout_check(long long& t0) {
+  const long long now = clock64();
+  if (t0 == 0) t0 = now;
+  else if (now - t0 > MV_SPIN_TIMEOUT_CYCLES) __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > MV_SPIN_TIMEOUT_CYCLES) __trap();
+    if ((++spins & 0x3FFFu) == 0) mbar_timeout_check(t0);
   }
 }
 
@@ -195,10 +203,10 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait_cluster(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if ((++spins & 0x3FFu) == 0 && clock64() - t0 > MV_SPIN_TIMEOUT_CYCLES) __trap();
+    if ((++spins & 0x3FFFu) == 0) mbar_timeout_check(t0);
   }
 }
 // TMA load issued by either CTA of the pair; the bytes are accounted on `bar_cluster_addr` (the LEADER's barrier)
