@@ -245,9 +245,17 @@ def run_ours(args):
     _lib.check(_lib.lib().mv_profile(eng._h, 1))
     for i in range(2):
         step_device(i)
-    pms, pfl, pcn = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_int32 * 3)()
-    _lib.check(_lib.lib().mv_profile_read(eng._h, pms, pfl, pcn))
+    NT = 8
+    tms, tfl, tcn = (C.c_double * NT)(), (C.c_double * NT)(), (C.c_int32 * NT)()
+    _lib.check(_lib.lib().mv_profile_read(eng._h, tms, tfl, tcn, NT))
     _lib.check(_lib.lib().mv_profile(eng._h, 0))
+    GEMM_TAGS = {0: "plain fwd/dgrad", 3: "wgrad (fp32 reduce-add)", 4: "GELU-forward epilogue", 5: "GELU-backward epilogue", 6: "residual epilogue (fp32 stream)"}
+    # tag 0 of the three-entry view = the whole tcgen05 GEMM family
+    pms = [sum(tms[t] for t in GEMM_TAGS), tms[1], tms[2]]
+    pfl = [sum(tfl[t] for t in GEMM_TAGS), tfl[1], tfl[2]]
+    pcn = [sum(tcn[t] for t in GEMM_TAGS), tcn[1], tcn[2]]
+    gemm_classes = {name: {"launches_per_step": tcn[t] // 2, "ms_per_step": tms[t] / 2,
+                           "tflops": (tfl[t] / (tms[t] * 1e-3) / 1e12) if tms[t] > 0 else None} for t, name in GEMM_TAGS.items()}
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -277,7 +285,7 @@ def run_ours(args):
     roofline = {"bound": "tensor", "kernel": "gemm_tc05_kernel (all %d launches of a step)" % (pcn[0] // 2), "achieved": gemm_tf,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf, "traffic": traffic, "traffic_unit": "bytes/launch (DRAM)",
                 "traffic_source": traffic_src, "algorithmic_flops_per_launch": pfl[0] / 2 / n_gemm, "peak_source": peak_src,
-                "gemm_ms_per_step": pms[0] / 2, "attn_fwd_ms_per_step": pms[1] / 2, "attn_bwd_ms_per_step": pms[2] / 2,
+                "gemm_classes": gemm_classes, "gemm_ms_per_step": pms[0] / 2, "attn_fwd_ms_per_step": pms[1] / 2, "attn_bwd_ms_per_step": pms[2] / 2,
                 "attn_fwd_tflops_dense": pfl[1] / (pms[1] * 1e-3) / 1e12 if pms[1] > 0 else None,
                 "attn_bwd_tflops_dense": pfl[2] / (pms[2] * 1e-3) / 1e12 if pms[2] > 0 else None,
                 "encoder_gemm_plus_attention_ms": enc_ms, "encoder_gemm_plus_attention_tflops_dense": enc_scope_tf,

@@ -41,7 +41,9 @@ enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3
                                                       rows see the prefix only (.../sc/data_loader.py:394-408)          */
 enum {                                                 /* GEMM epilogues (mv_gemm) */
   MV_EPI_NONE = 0, MV_EPI_BIAS = 1, MV_EPI_BIAS_GELU = 2, MV_EPI_BIAS_RESID = 3, MV_EPI_BIAS_TANH = 4,
-  MV_EPI_RESID = 5, MV_EPI_DGELU = 6
+  MV_EPI_RESID = 5, MV_EPI_DGELU = 6,
+  MV_EPI_BIAS_GELU_GRAD = 7,   /* C = gelu(acc + bias), C2 = gelu'(acc + bias): saves the derivative instead of the pre-activation */
+  MV_EPI_MUL = 8               /* C = acc * aux[m,n] (the backward partner of MV_EPI_BIAS_GELU_GRAD)                              */
 };
 
 typedef struct mv_handle mv_handle;
@@ -201,7 +203,9 @@ int mv_peek(mv_handle* h, const char* name, int32_t layer, void* dst, int64_t ma
 /* ---- measurement aids (bench.py): launch counter; CUDA-event timing per kernel family on the launch stream ---- */
 long mv_launch_count(void);                                              /* kernels launched by this library so far  */
 int mv_profile(mv_handle* h, int32_t enable);
-int mv_profile_read(mv_handle* h, double ms[3], double flops[3], int32_t count[3]);  /* 0 GEMM, 1 attn fwd, 2 attn bwd */
+int mv_profile_read(mv_handle* h, double* ms, double* flops, int32_t* count, int32_t n_tags);
+                                             /* tags: 0 plain GEMM, 1 attn fwd, 2 attn bwd, 3 wgrad GEMM, 4 GELU-fwd GEMM, 5 GELU-bwd GEMM, */
+                                             /* 6 residual-epilogue GEMM; arrays of n_tags (>= 3) entries                                 */
 
 /* ---- data-parallel gradient exchange (one process per GPU) ---- */
 int mv_comm_unique_id(uint8_t out[128]);

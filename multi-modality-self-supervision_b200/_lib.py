@@ -14,7 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 4          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
 MV_PREC_BF16, MV_PREC_FP32 = 0, 1
 MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS, MODE_S2S_FT, MODE_BAR_FT = 0, 1, 2, 3, 4, 5
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_BIAS_TANH, EPI_RESID, EPI_DGELU = range(7)
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_BIAS_TANH, EPI_RESID, EPI_DGELU, EPI_BIAS_GELU_GRAD, EPI_MUL = range(9)
 
 
 class MedvillError(RuntimeError):
@@ -97,7 +97,7 @@ SYMBOLS = {
     "mv_peek": (_I, [_P, C.c_char_p, _I, _P, _L, C.POINTER(_L), _P]),
     "mv_launch_count": (C.c_long, []),
     "mv_profile": (_I, [_P, _I]),
-    "mv_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I)]),
+    "mv_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_I), _I]),
     "mv_comm_unique_id": (_I, [_P]),
     "mv_comm_init": (_I, [_P, _P, _I, _I]),
     "mv_comm_allreduce_f32": (_I, [_P, _P, _L, _P]),

@@ -223,14 +223,17 @@ int mv_profile(mv_handle* h, int32_t enable) {
   return 0;
 }
 
-// Sum the recorded event pairs per tag (0 GEMM, 1 attention fwd, 2 attention bwd); syncs, then clears the records.
-int mv_profile_read(mv_handle* h, double ms[3], double flops[3], int32_t count[3]) {
+// Sum the recorded event pairs per tag (engine.h: 0 / 3 / 4 / 5 / 6 GEMM classes, 1 attention fwd, 2 attention bwd); syncs,
+// then clears the records.  The arrays hold n_tags entries (tags >= n_tags are folded into tag 0).
+int mv_profile_read(mv_handle* h, double* ms, double* flops, int32_t* count, int32_t n_tags) {
   MV_CHECK_HANDLE(h);
+  MV_REQUIRE(ms && flops && count && n_tags >= 3, "mv_profile_read: bad arguments");
   MV_CUDA_CHECK(cudaDeviceSynchronize());
-  for (int i = 0; i < 3; ++i) { ms[i] = 0; flops[i] = 0; count[i] = 0; }
+  for (int i = 0; i < n_tags; ++i) { ms[i] = 0; flops[i] = 0; count[i] = 0; }
   for (auto& r : h->eng.prof) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess && r.tag >= 0 && r.tag < 3) { ms[r.tag] += t; flops[r.tag] += r.flops; count[r.tag] += 1; }
+    const int tag = (r.tag >= 0 && r.tag < n_tags) ? r.tag : 0;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[tag] += t; flops[tag] += r.flops; count[tag] += 1; }
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }

@@ -384,7 +384,8 @@ int Engine::forward(const mv_batch& b, cudaStream_t s) {
     MV_TRY(linear_fwd(w.ctx, M, H, base + lay.l_wo, H, base + lay.l_bo, w.y1, EPI_BIAS_RESID, nullptr, rf32 ? static_cast<const void*>(xres) : x[l],
                       drop, site_h1(l), dc, s, rf32, 0, rf32));
     MV_TRY(ln_fwd(w.y1, w.x1, params + base + lay.l_ln1_g, params + base + lay.l_ln1_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s, rf32, x1res));
-    MV_TRY(linear_fwd(w.x1, M, H, base + lay.l_w1, I, base + lay.l_b1, w.g1, EPI_BIAS_GELU, w.h1, nullptr, 0, 0, dc, s));
+    // h1 receives gelu'(pre-activation) — what backward needs — instead of the pre-activation itself
+    MV_TRY(linear_fwd(w.x1, M, H, base + lay.l_w1, I, base + lay.l_b1, w.g1, EPI_BIAS_GELU_GRAD, w.h1, nullptr, 0, 0, dc, s));
     MV_TRY(linear_fwd(w.g1, M, I, base + lay.l_w2, H, base + lay.l_b2, w.y2, EPI_BIAS_RESID, nullptr, rf32 ? static_cast<const void*>(x1res) : w.x1,
                       drop, site_h2(l), dc, s, rf32, 0, rf32));
     MV_TRY(ln_fwd(w.y2, x[l + 1], params + base + lay.l_ln2_g, params + base + lay.l_ln2_b, M, H, cfg.ln_eps, 0, 0, dc, f32, s, rf32, xres));
@@ -443,7 +444,7 @@ int Engine::mlm_head_rows(const int64_t* rows, int n, const DropoutCfg& dc, cuda
   const int H = cfg.hidden;
   MV_TRY(ensure_mlm(n));
   MV_TRY(gather_rows(x[cfg.layers], rows_h, rows, n, n, 0, H, f32, s));
-  MV_TRY(linear_fwd(rows_h, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
+  MV_TRY(linear_fwd(rows_h, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU_GRAD, t_pre, nullptr, 0, 0, dc, s));   // t_pre = gelu'
   MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, n, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
   return 0;
 }
@@ -529,7 +530,7 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     MV_TRY(linear_dgrad(dlogits, Vpad, n, cfg.vocab, lay.word, H, d_tln, EPI_NONE, nullptr, s));
     MV_TRY(ln_bwd(d_tln, t_act, params + lay.mlm_ln_g, d_tact, nullptr, grads + lay.mlm_ln_g, grads + lay.mlm_ln_b, nullptr, n, H,
                   cfg.head_ln_eps, 0, 0, 0, dc, f32, s));
-    MV_TRY(dgelu_mul(d_tact, t_pre, d_tpre, static_cast<long>(n) * H, f32, s));
+    MV_TRY(mul_elem(d_tact, t_pre, d_tpre, static_cast<long>(n) * H, f32, s));
     MV_TRY(colsum_add(d_tpre, H, n, H, grads + lay.mlm_tb, f32, s));
     MV_TRY(linear_wgrad(d_tpre, H, rows_h, n, H, H, lay.mlm_tw, s));
     MV_TRY(linear_dgrad(d_tpre, H, n, H, lay.mlm_tw, H, d_rows, EPI_NONE, nullptr, s));
@@ -554,7 +555,7 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     MV_TRY(ln_bwd(P, w.y2, params + base + lay.l_ln2_g, Q, drop ? R : nullptr, g + lay.l_ln2_g, g + lay.l_ln2_b, g + lay.l_b2, M, H,
                   cfg.ln_eps, 0, drop, site_h2(l), dc, f32, s, rf32));
     MV_TRY(linear_wgrad(dY2d, H, w.g1, M, H, I, base + lay.l_w2, s));
-    MV_TRY(linear_dgrad(dY2d, H, M, H, base + lay.l_w2, I, dh1, EPI_DGELU, w.h1, s));
+    MV_TRY(linear_dgrad(dY2d, H, M, H, base + lay.l_w2, I, dh1, EPI_MUL, w.h1, s));
     MV_TRY(colsum_add(dh1, I, M, I, g + lay.l_b1, f32, s));
     MV_TRY(linear_wgrad(dh1, I, w.x1, M, I, H, base + lay.l_w1, s));
     MV_TRY(linear_dgrad(dh1, I, M, I, base + lay.l_w1, H, P, EPI_RESID, Q, s));          // P = d(x1)
@@ -653,7 +654,7 @@ int Engine::full_logits(const mv_batch& b, float* out, int64_t ld, cudaStream_t 
   const char* seq = static_cast<const char*>(x[cfg.layers]);
   for (int r0 = 0; r0 < M; r0 += mlm_cap) {
     const int n = M - r0 < mlm_cap ? M - r0 : mlm_cap;
-    MV_TRY(linear_fwd(seq + static_cast<size_t>(r0) * H * es, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, t_pre, nullptr, 0, 0, dc, s));
+    MV_TRY(linear_fwd(seq + static_cast<size_t>(r0) * H * es, n, H, lay.mlm_tw, H, lay.mlm_tb, t_act, EPI_BIAS_GELU, nullptr, nullptr, 0, 0, dc, s));
     MV_TRY(ln_fwd(t_act, t_ln, params + lay.mlm_ln_g, params + lay.mlm_ln_b, n, H, cfg.head_ln_eps, 0, 0, dc, f32, s));
     MV_TRY(linear_fwd(t_ln, n, H, lay.word, cfg.vocab, lay.mlm_bias, out + static_cast<size_t>(r0) * ld, EPI_BIAS, nullptr, nullptr, 0, 0, dc, s, 1, ld));
   }

@@ -78,7 +78,11 @@ struct Engine {
 
   const void* W(int64_t off) const { return f32 ? static_cast<const void*>(params + off) : static_cast<const void*>(shadow + off); }
   int gemm(const GemmDesc& d, cudaStream_t s) {
-    if (prof_begin(0, 2.0 * d.M * d.N * d.K, s)) return -2;
+    // tags: 0 plain forward / dgrad GEMM, 3 weight-gradient GEMM (fp32 reduce-add), 4 GELU-forward epilogue,
+    //       5 GELU-backward epilogue, 6 residual epilogue (fp32 stream); 1 / 2 are the attention kernels
+    const int tag = d.accumulate ? 3 : ((d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_GELU_GRAD) ? 4 : ((d.epi == EPI_DGELU || d.epi == EPI_MUL) ? 5 :
+                    ((d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID) ? 6 : 0)));
+    if (prof_begin(tag, 2.0 * d.M * d.N * d.K, s)) return -2;
     const int rc = f32 ? gemm_f32_simt(d, s) : gemm_bf16_tc05(d, s);
     if (rc) return rc;
     return prof_end(s);

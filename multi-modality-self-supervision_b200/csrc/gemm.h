@@ -18,6 +18,9 @@ enum Epilogue : int {
   EPI_BIAS_TANH = 4,   // C = tanh(acc + bias)
   EPI_RESID = 5,       // C = acc + resid[m,n]
   EPI_DGELU = 6,       // C = acc * gelu_erf'(aux[m,n])
+  EPI_BIAS_GELU_GRAD = 7,  // C = gelu_erf(acc + bias); C2 = gelu_erf'(acc + bias): the derivative is saved INSTEAD of the pre-activation,
+                           // so the backward GEMM's epilogue is a plain multiply (EPI_MUL) rather than a second erf evaluation
+  EPI_MUL = 8,         // C = acc * aux[m,n]
 };
 
 struct GemmDesc {

@@ -65,9 +65,12 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
       if (n >= p.N) continue;
       float v = acc[i][j];
       const int epi = p.epi;
-      if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH) v += p.bias[n];
+      if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH || epi == EPI_BIAS_GELU_GRAD) v += p.bias[n];
       if (epi == EPI_BIAS_GELU) {
         if (p.C2) p.C2[m * p.ldc2 + n] = v;
+        v = gelu_erf(v);
+      } else if (epi == EPI_BIAS_GELU_GRAD) {
+        if (p.C2) p.C2[m * p.ldc2 + n] = gelu_erf_grad(v);
         v = gelu_erf(v);
       } else if (epi == EPI_BIAS_TANH) {
         v = tanhf(v);
@@ -80,6 +83,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const SimtParams p) {
         v += p.resid[m * p.ldr + n];
       } else if (epi == EPI_DGELU) {
         v *= gelu_erf_grad(p.aux[m * p.ldaux + n]);
+      } else if (epi == EPI_MUL) {
+        v *= p.aux[m * p.ldaux + n];
       }
       float* dst = p.C + m * p.ldc + n;
       if (p.accumulate) *dst += v; else *dst = v;

@@ -21,7 +21,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
+constexpr int kThreads = 320;   // EW = 4: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups (EW = 8: 576 threads)
 constexpr int kMaxStages = 8;
 constexpr uint32_t STG_BYTES = 4096;  // one staging buffer: 32 rows x 128 B (swizzled)
 // per epilogue warp: out[2] + second[2], where `second` is either the pre-activation output (EPI_BIAS_GELU) or the
@@ -64,13 +64,21 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[3
   // bias_lane: bias[col0 + lane] (0 past N), prefetched by the caller one step ahead so that its L2 latency never sits on
   // the accumulator-drain path; column j's value is fetched from lane j.
   const int epi = p.epi;
-  if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH) {
+  if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH || epi == EPI_BIAS_GELU_GRAD) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] += __shfl_sync(0xffffffffu, bias_lane, j);
   }
   if (epi == EPI_BIAS_GELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) { pre[j] = f[j]; f[j] = gelu_fast(f[j]); }
+  } else if (epi == EPI_BIAS_GELU_GRAD) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float cdf, pdf;
+      gelu_fast_parts(f[j], cdf, pdf);          // one shared exponential for the activation and its derivative
+      pre[j] = fmaf(f[j], pdf, cdf);
+      f[j] *= cdf;
+    }
   } else if (epi == EPI_BIAS_TANH) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
@@ -89,6 +97,9 @@ __device__ __forceinline__ void epilogue_apply(const GemmParams& p, float (&f)[3
   } else if (epi == EPI_DGELU) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] *= gelu_fast_grad(in[j]);
+  } else if (epi == EPI_MUL) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= in[j];
   }
 }
 
@@ -120,6 +131,68 @@ __device__ __forceinline__ void stage_f32(uint8_t* stg, int lane, const float (&
   }
 }
 
+// ---- 16-column variants for the wide epilogue (EW = 8: two warps per TMEM lane quarter, 113 registers per thread) ----
+// bf16 staging tile [32 rows x 64 cols] swizzled; `c16` = which 16-column quarter of the 64 columns
+__device__ __forceinline__ void stage_bf16_16(uint8_t* stg, int lane, int c16, const float (&f)[16]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    uint4 u;
+    u.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+    u.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+    u.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+    u.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+    *reinterpret_cast<uint4*>(stg + sw128_off(lane, c16 * 2 + j)) = u;
+  }
+}
+__device__ __forceinline__ void unstage_bf16_16(const uint8_t* stg, int lane, int c16, float (&out)[16]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(stg + sw128_off(lane, c16 * 2 + j));
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    out[8 * j + 0] = a.x; out[8 * j + 1] = a.y; out[8 * j + 2] = b.x; out[8 * j + 3] = b.y;
+    out[8 * j + 4] = c.x; out[8 * j + 5] = c.y; out[8 * j + 6] = d.x; out[8 * j + 7] = d.y;
+  }
+}
+// epilogue math on 16 consecutive columns [col0, col0 + 16) of output row `row`; bias of column j comes from lane bias_src + j
+__device__ __forceinline__ void epilogue_apply16(const GemmParams& p, float (&f)[16], float (&pre)[16], const float (&in)[16],
+                                                 int row, int col0, float bias_lane, int bias_src) {
+  const int epi = p.epi;
+  if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH || epi == EPI_BIAS_GELU_GRAD) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] += __shfl_sync(0xffffffffu, bias_lane, bias_src + j);
+  }
+  if (epi == EPI_BIAS_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { pre[j] = f[j]; f[j] = gelu_fast(f[j]); }
+  } else if (epi == EPI_BIAS_GELU_GRAD) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float cdf, pdf;
+      gelu_fast_parts(f[j], cdf, pdf);
+      pre[j] = fmaf(f[j], pdf, cdf);
+      f[j] *= cdf;
+    }
+  } else if (epi == EPI_BIAS_TANH) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = tanhf(f[j]);
+  } else if (epi == EPI_BIAS_RESID || epi == EPI_RESID) {
+    if (p.drop_on && epi == EPI_BIAS_RESID) {
+      const uint64_t e = static_cast<uint64_t>(row) * static_cast<uint64_t>(p.N) + col0;
+      const uint4 keep = dropout_keep16(p.drop, p.drop_site, e >> 4);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = keep16_bit(keep, j) ? f[j] * p.drop.scale : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] += in[j];
+  } else if (epi == EPI_DGELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] *= gelu_fast_grad(in[j]);
+  } else if (epi == EPI_MUL) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] *= in[j];
+  }
+}
+
 // Work unit -> (m tile, n tile, k-block range).  Units are walked by CTA (or CTA pair) c as c, c + stride, ...:
 //   plain GEMMs   : n tile fastest, so the CTAs running at the same time share a few row blocks of the (large) activation
 //                   operand through L2 while the whole weight matrix (a few MB) stays L2-resident;
@@ -145,8 +218,12 @@ __device__ __forceinline__ Unit decode_unit(const GemmParams& p, int unit) {
 // warps release the accumulator by arriving remotely on the leader's `tempty`.  Each SM then reads only half of B from
 // shared memory per MMA — single-CTA tiles are capped at ~60 % of the tensor pipe by shared-memory bandwidth
 // (TMA fill + UMMA operand reads, profiles/r01_ncu_gemm_*).
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool TWO>
-__global__ void __launch_bounds__(kThreads, 1)
+// EW = epilogue warps per accumulator stage.  4: one warp per TMEM lane quarter drains all BN columns (r01).  8: TWO warps per
+// lane quarter, each draining one 32-column half of every 64-column chunk into a shared staging tile (pair-synchronised with
+// a 64-thread named barrier); used for the transcendental epilogues, where one warp per scheduler could not issue the
+// ~26 instructions per element inside two MMA tile-times (profiles/r01_gemm_epilogue_notes.md).
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool TWO, int EW>
+__global__ void __launch_bounds__(64 + 64 * EW, 1)
 gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX,
                  const GemmParams p) {
@@ -183,7 +260,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tfull[a], 1);
-      mbar_init(&bars->tempty[a], TWO ? 8 : 4);     // pair mode: 4 local + 4 remote epilogue warps
+      mbar_init(&bars->tempty[a], TWO ? 2 * EW : EW);     // pair mode: local + remote epilogue warps
     }
     for (int w = 0; w < 8; ++w) { mbar_init(&bars->in_bar[w][0], 1); mbar_init(&bars->in_bar[w][1], 1); }
     fence_mbar_init();
@@ -304,6 +381,107 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (acc == 0) acc_phase ^= 1u;
       }
     }
+  } else if constexpr (EW == 8) {
+    // ===================== epilogue warps, two per TMEM lane quarter =====================
+    // Group g (accumulator stage g) = warps 2 + 8 g .. 9 + 8 g.  Warps wi and wi + 4 of a group share lane quarter q and one
+    // staging slot (2 x 4 KB): warp `hf` drains the 32-column half `hf` of every 64-column chunk, 16 columns at a time.  The
+    // half-0 warp ("leader") owns the slot's TMA traffic (input prefetch, stores, bulk-group waits); a 64-thread named barrier
+    // orders the two warps around each staging buffer.
+    static_assert(!OUT_F32, "the wide epilogue is instantiated for activation-dtype outputs only");
+    const int q = warp & 3;
+    const int ew = warp - 2;            // 0..15
+    const int grp = ew >> 3;            // == accumulator stage
+    const int hf = (ew >> 2) & 1;       // column half inside a 64-column chunk
+    const int slot = grp * 4 + q;       // staging slot / input barrier pair, 0..7
+    const bool leader = hf == 0;
+    uint8_t* my_stg = stg_base + static_cast<uint32_t>(slot) * (2 * STG_BYTES);
+    uint64_t* in_bar = bars->in_bar[slot];
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory"); };
+    const int acc = grp;
+    uint32_t acc_phase = 0;
+    uint32_t cnt = 0;
+    const bool has_in = p.has_in != 0, has_c2 = p.has_c2 != 0;
+    auto issue_in = [&](uint32_t chunk_cnt, int m0, int n0, int c) {   // leader lane 0: prefetch the epilogue input tile
+      const uint32_t b = chunk_cnt & 1u;
+      mbar_expect_tx(&in_bar[b], STG_BYTES);
+      tma_load_2d(&tmX, &in_bar[b], my_stg + b * STG_BYTES, n0 + c * 64, m0 + q * 32);
+    };
+    int it = 0;
+    const uint32_t tempty_remote = TWO ? mapa_cluster(smem_u32(&bars->tempty[acc]), 0) : 0u;
+    for (int unit = cta_id; unit < total_units; unit += cta_stride, ++it) {
+      if ((it & 1) != grp) continue;
+      const Unit u = decode_unit(p, unit);
+      const int m0 = u.m_tile * BMT + static_cast<int>(crank) * BM;
+      const int n0 = u.n_tile * BN;
+      if (has_in && leader && lane == 0) {
+        tma_wait_group_read<0>();
+        issue_in(cnt, m0, n0, 0);
+      }
+      const bool has_bias = p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID || p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_GELU_GRAD;
+      auto bias_at = [&](int col) { return (has_bias && col < p.N) ? __ldg(p.bias + col) : 0.f; };
+      float bias_next = bias_at(n0 + hf * 32 + lane);       // this warp's 32 columns of chunk 0
+      mbar_wait(&bars->tfull[acc], acc_phase);
+      acc_phase ^= 1u;
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c, ++cnt) {
+        const uint32_t buf = has_c2 ? 0u : (cnt & 1u);
+        if (leader && lane == 0) {
+          if (has_in) {
+            if (c + 1 < BN / 64) {
+              tma_wait_group_read<0>();
+              issue_in(cnt + 1, m0, n0, c + 1);
+            }
+          } else if (has_c2) {
+            tma_wait_group_read<0>();
+          } else {
+            tma_wait_group_read<1>();
+          }
+        }
+        pair_sync();                                   // staging buffer `buf` is free for both warps
+        uint8_t* s1 = my_stg + buf * STG_BYTES;
+        uint8_t* s2 = has_c2 ? my_stg + STG_BYTES : s1;
+        if (has_in) mbar_wait(&in_bar[buf], (cnt >> 1) & 1u);
+        const float bias_cur = bias_next;
+        bias_next = bias_at(n0 + (c + 1) * 64 + hf * 32 + lane);
+#pragma unroll 1
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t v[16];
+          tmem_ld16(t_row + static_cast<uint32_t>(c * 64 + hf * 32 + sub * 16), v);
+          tmem_ld_wait();
+          float f[16], pre[16], in[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (has_in) unstage_bf16_16(s2, lane, hf * 2 + sub, in);
+          epilogue_apply16(p, f, pre, in, row, n0 + c * 64 + hf * 32 + sub * 16, bias_cur, sub * 16);
+          stage_bf16_16(s1, lane, hf * 2 + sub, f);
+          if (has_c2) stage_bf16_16(s2, lane, hf * 2 + sub, pre);
+        }
+        if (c == BN / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (TWO) mbar_arrive_cluster(tempty_remote);
+            else mbar_arrive(&bars->tempty[acc]);
+          }
+        }
+        fence_proxy_async_smem();
+        pair_sync();                                   // both halves of the chunk are staged
+        if (leader && lane == 0) {
+          const int r0 = m0 + q * 32;
+          const int c0 = n0 + c * 64;
+          if (r0 < p.M && c0 < p.N) {
+            tma_store_2d(&tmC, s1, c0, r0);
+            if (has_c2) tma_store_2d(&tmX, s2, c0, r0);
+          }
+          tma_commit_group();
+        }
+      }
+    }
+    if (leader && lane == 0) tma_wait_group<0>();
+    __syncwarp();
   } else {
     // ===================== epilogue warps =====================
     // Two groups of four warps (2-5 and 6-9).  Group g drains accumulator stage g, i.e. every other work unit of this
@@ -336,7 +514,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tma_wait_group_read<0>();      // every store that read my two buffers has drained
         issue_in(cnt, m0, n0, 0);
       }
-      const bool has_bias = p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID || p.epi == EPI_BIAS_TANH;
+      const bool has_bias = p.epi == EPI_BIAS || p.epi == EPI_BIAS_GELU || p.epi == EPI_BIAS_RESID || p.epi == EPI_BIAS_TANH || p.epi == EPI_BIAS_GELU_GRAD;
       auto bias_at = [&](int col) { return (has_bias && col < p.N) ? __ldg(p.bias + col) : 0.f; };
       float bias_next = bias_at(n0 + lane);      // first 32 columns; later ones are fetched one step ahead
       mbar_wait(&bars->tfull[acc], acc_phase);
@@ -441,8 +619,9 @@ inline int pick_stages(uint32_t stage_b) {
   return s;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool TWO>
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool TWO, int EW = 4>
 int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
+  constexpr int kThreadsEw = 64 + 64 * EW;
   constexpr int BNL = TWO ? BN / 2 : BN;     // B rows / columns one CTA loads per k-block
   constexpr int BMT = TWO ? 2 * BM : BM;     // rows of one work unit
   CUtensorMap tmA, tmB, tmC, tmX;
@@ -463,7 +642,7 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
     rc = tmap_encode_2d(&tmX, TMAP_F32, d.resid, d.N, d.M, d.ldr * 4, 32, 32);
   } else if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID) {
     rc = tmap_encode_2d(&tmX, TMAP_BF16, d.resid, d.N, d.M, d.ldr * 2, 64, 32);
-  } else if (d.epi == EPI_DGELU) {
+  } else if (d.epi == EPI_DGELU || d.epi == EPI_MUL) {
     rc = tmap_encode_2d(&tmX, TMAP_BF16, d.aux, d.N, d.M, d.ldaux * 2, 64, 32);
   }
   if (rc) return rc;
@@ -497,7 +676,7 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   const int units = tiles * p.splits;
   const int grid = (units < slots ? units : slots) * (TWO ? 2 : 1);
   const uint32_t smem = 1024u + static_cast<uint32_t>(p.stages) * stage_bytes<BN, TWO>() + STG_TOTAL + sizeof(Barriers) + 64u;
-  auto kern = gemm_tc05_kernel<BN, A_MN, B_MN, OUT_F32, TWO>;
+  auto kern = gemm_tc05_kernel<BN, A_MN, B_MN, OUT_F32, TWO, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     MV_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
@@ -506,7 +685,7 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   if constexpr (TWO) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.blockDim = dim3(kThreadsEw, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -516,16 +695,30 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
     cfg.numAttrs = 1;
     MV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmX, p));
   } else {
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmX, p);
+    kern<<<grid, kThreadsEw, smem, stream>>>(tmA, tmB, tmC, tmX, p);
   }
   MV_LAUNCH_CHECK();
   return 0;
 }
 
+// MV_GEMM_EW=4 / 8 forces the epilogue width (A/B measurements); default: 8 for the transcendental epilogues
+int ew_env() {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("MV_GEMM_EW"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 template <int BN, bool TWO>
 int dispatch_major(const GemmDesc& d, const GemmParams& p, cudaStream_t s) {
-  if (!d.a_mn && !d.b_mn) return d.c_f32 ? launch<BN, false, false, true, TWO>(d, p, s) : launch<BN, false, false, false, TWO>(d, p, s);
+  bool wide = d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_GELU_GRAD || d.epi == EPI_DGELU;
+  if (ew_env() == 4) wide = false; else if (ew_env() == 8) wide = true;
+  wide = wide && !d.c_f32 && !d.a_mn;
+  if (!d.a_mn && !d.b_mn) {
+    if (wide) return launch<BN, false, false, false, TWO, 8>(d, p, s);
+    return d.c_f32 ? launch<BN, false, false, true, TWO>(d, p, s) : launch<BN, false, false, false, TWO>(d, p, s);
+  }
   if constexpr (!TWO || (BN / 2) % 64 == 0) {      // MN-major B is loaded in 64-column groups
+    if (!d.a_mn && d.b_mn && wide) return launch<BN, false, true, false, TWO, 8>(d, p, s);
     if (!d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, false, true, true, TWO>(d, p, s) : launch<BN, false, true, false, TWO>(d, p, s);
     if (d.a_mn && d.b_mn) return d.c_f32 ? launch<BN, true, true, true, TWO>(d, p, s) : launch<BN, true, true, false, TWO>(d, p, s);
   }
@@ -568,14 +761,16 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   MV_REQUIRE(d.A && d.B && d.C, "gemm: null operand");
   MV_REQUIRE(!d.accumulate || d.c_f32, "gemm: accumulate requires fp32 output");
   MV_REQUIRE(!(d.C2 && d.c_f32), "gemm: pre-activation output only with activation-dtype C");
-  MV_REQUIRE(!d.C2 || (d.epi == EPI_BIAS_GELU && d.N % 32 == 0 && d.ldc2 % 8 == 0), "gemm: C2 needs EPI_BIAS_GELU, N %% 32 == 0");
-  if (d.epi == EPI_BIAS || d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_RESID || d.epi == EPI_BIAS_TANH)
+  MV_REQUIRE(!d.C2 || ((d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_GELU_GRAD) && d.N % 32 == 0 && d.ldc2 % 8 == 0),
+             "gemm: C2 needs EPI_BIAS_GELU / EPI_BIAS_GELU_GRAD, N %% 32 == 0");
+  MV_REQUIRE(d.epi != EPI_BIAS_GELU_GRAD || d.C2, "gemm: EPI_BIAS_GELU_GRAD needs C2 (the derivative output)");
+  if (d.epi == EPI_BIAS || d.epi == EPI_BIAS_GELU || d.epi == EPI_BIAS_RESID || d.epi == EPI_BIAS_TANH || d.epi == EPI_BIAS_GELU_GRAD)
     MV_REQUIRE(d.bias != nullptr, "gemm: epilogue %d needs bias", d.epi);
   if (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID)
     MV_REQUIRE(d.resid != nullptr && d.N % 32 == 0 && d.ldr % 8 == 0 && (d.c_f32 != 0) == (d.resid_f32 != 0) && !(d.c_f32 && d.accumulate),
                "gemm: residual epilogue needs resid, N%%32==0, and resid / C of the same type (bf16, or fp32 with resid_f32)");
-  if (d.epi == EPI_DGELU)
-    MV_REQUIRE(d.aux != nullptr && d.N % 32 == 0 && d.ldaux % 8 == 0 && !d.c_f32, "gemm: DGELU epilogue needs aux, N%%32==0, bf16 out");
+  if (d.epi == EPI_DGELU || d.epi == EPI_MUL)
+    MV_REQUIRE(d.aux != nullptr && d.N % 32 == 0 && d.ldaux % 8 == 0 && !d.c_f32, "gemm: DGELU / MUL epilogue needs aux, N%%32==0, bf16 out");
   GemmParams p;
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.m_tiles = (d.M + BM - 1) / BM;
@@ -585,7 +780,7 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   p.epi = d.epi;
   p.bias = d.bias;
   p.has_c2 = d.C2 != nullptr; p.accumulate = d.accumulate;
-  p.has_in = (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID || d.epi == EPI_DGELU) ? 1 : 0;
+  p.has_in = (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID || d.epi == EPI_DGELU || d.epi == EPI_MUL) ? 1 : 0;
   p.drop_on = d.drop_on; p.drop_site = d.drop_site; p.drop = d.drop;
   bool pair = d.M > BM;                       // a single 128-row tile gains nothing from a partner SM
   if (pair_env() >= 0) pair = pair_env() != 0;

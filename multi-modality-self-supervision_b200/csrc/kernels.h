@@ -69,6 +69,7 @@ int gather_rows(const void* src, void* dst, const int64_t* idx, int n, int perio
 int scatter_rows(const void* src, void* dst, const int64_t* idx, int n, int period, long stride, int H, int add,
                  int f32, cudaStream_t s);
 int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaStream_t s);          // dx = dy * gelu'(pre)
+int mul_elem(const void* a, const void* b, void* out, long n, int f32, cudaStream_t s);             // out = a * b
 // d_pre (+)= d_out * (1 - out^2): backward of out = tanh(pre) (BertPooler)
 int tanh_bwd(const void* d_out, const void* out, void* d_pre, long n, int add, int f32, cudaStream_t s);
 int cast_f32_to_bf16(const float* src, bf16* dst, long n, cudaStream_t s);

@@ -467,6 +467,18 @@ __global__ void __launch_bounds__(256) dgelu_kernel(const T* __restrict__ dy, co
 }
 
 template <typename T>
+__global__ void __launch_bounds__(256) mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long n8) {
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    load8<T>(a + i * 8, x);
+    load8<T>(b + i * 8, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] *= y[j];
+    store8<T>(out + i * 8, x);
+  }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) tanh_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ out, T* __restrict__ dpre, long n, int add) {
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const float y = to_f32<T>(out[i]);
@@ -695,6 +707,17 @@ int dgelu_mul(const void* dy, const void* pre, void* dx, long n, int f32, cudaSt
   int grid = static_cast<int>((n8 + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   MV_DISPATCH_T(f32, (dgelu_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(dy), static_cast<const T*>(pre), static_cast<T*>(dx), n8)));
+  MV_LAUNCH_CHECK();
+  return 0;
+}
+
+int mul_elem(const void* a, const void* b, void* out, long n, int f32, cudaStream_t s) {
+  MV_REQUIRE(n % 8 == 0, "mul_elem: n %% 8");
+  if (n <= 0) return 0;
+  const long n8 = n / 8;
+  int grid = static_cast<int>((n8 + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  MV_DISPATCH_T(f32, (mul_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(a), static_cast<const T*>(b), static_cast<T*>(out), n8)));
   MV_LAUNCH_CHECK();
   return 0;
 }

@@ -112,9 +112,11 @@ static int run_case(const Case& c, bool fp32_mode, int n_samples) {
     for (int k = 0; k < K; ++k) acc += (double)A[(size_t)m * K + k] * (double)B[(size_t)n * K + k];
     double pre = acc, v = acc;
     const int epi = c.epi;
-    if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH) v += bias[n];
+    if (epi == EPI_BIAS || epi == EPI_BIAS_GELU || epi == EPI_BIAS_RESID || epi == EPI_BIAS_TANH || epi == EPI_BIAS_GELU_GRAD) v += bias[n];
     pre = v;
     if (epi == EPI_BIAS_GELU) v = gelu_d(v);
+    else if (epi == EPI_BIAS_GELU_GRAD) { pre = gelu_grad_d(v); v = gelu_d(v); }   // C2 holds the derivative
+    else if (epi == EPI_MUL) v *= R[idx];
     else if (epi == EPI_BIAS_TANH) v = tanh(v);
     else if (epi == EPI_BIAS_RESID || epi == EPI_RESID) {
       if (c.drop) {
@@ -161,6 +163,8 @@ static void perf(const char* name, int M, int N, int K, int a_mn, int b_mn, int 
   d.M = M; d.N = N; d.K = K; d.A = dA; d.lda = a_mn ? M : K; d.a_mn = a_mn; d.B = dB; d.ldb = b_mn ? N : K; d.b_mn = b_mn;
   d.C = dC; d.ldc = N; d.c_f32 = c_f32; d.accumulate = acc; d.epi = epi; d.bias = dbias; d.resid = dR; d.ldr = N;
   d.aux = dR; d.ldaux = N; d.pair = g_pair; d.bn = g_bn;
+  void* dC2 = nullptr;
+  if (epi == EPI_BIAS_GELU || epi == EPI_BIAS_GELU_GRAD) { cudaMalloc(&dC2, (size_t)M * N * 2); d.C2 = dC2; d.ldc2 = N; }   // as the engine runs it
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) gemm_bf16_tc05(d, 0);
   cudaEventRecord(e0);
@@ -169,7 +173,7 @@ static void perf(const char* name, int M, int N, int K, int a_mn, int b_mn, int 
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
   printf("  perf %-28s M=%d N=%d K=%d: %.3f ms  %.1f TFLOP/s\n", name, M, N, K, ms, 2.0 * M * N * K / ms / 1e9);
-  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dR); cudaFree(dbias);
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dR); cudaFree(dbias); if (dC2) cudaFree(dC2);
 }
 
 static void perf_one(int which) {
@@ -183,6 +187,8 @@ static void perf_one(int which) {
     case 6: perf("FFN1 wgrad", 3072, 768, 27904, 1, 1, 1, 1, EPI_NONE); break;
     case 7: perf("QKV wgrad", 2304, 768, 27904, 1, 1, 1, 1, EPI_NONE); break;
     case 8: perf("FFN1 fwd bias only", 27904, 3072, 768, 0, 0, 0, 0, EPI_BIAS); break;
+    case 9: perf("FFN1 fwd gelu+gelu'", 27904, 3072, 768, 0, 0, 0, 0, EPI_BIAS_GELU_GRAD); break;
+    case 10: perf("FFN2 dgrad mul", 27904, 3072, 768, 0, 1, 0, 0, EPI_MUL); break;
     default: perf("out wgrad", 768, 768, 27904, 1, 1, 1, 1, EPI_NONE); break;
   }
 }
@@ -199,6 +205,9 @@ int main(int argc, char** argv) {
       {"TN 300x200x136 bias (tails)", 300, 200, 136, 0, 0, 0, 0, EPI_BIAS, 0, 0},
       {"TN 872x2304x768 bias", 872, 2304, 768, 0, 0, 0, 0, EPI_BIAS, 0, 0},
       {"TN 872x3072x768 bias_gelu+C2", 872, 3072, 768, 0, 0, 0, 0, EPI_BIAS_GELU, 1, 0},
+      {"TN 872x3072x768 gelu+gelu' (C2)", 872, 3072, 768, 0, 0, 0, 0, EPI_BIAS_GELU_GRAD, 1, 0},
+      {"TN 300x192x136 gelu+gelu' tails", 300, 192, 136, 0, 0, 0, 0, EPI_BIAS_GELU_GRAD, 1, 0},
+      {"NN dgrad 872x3072x768 mul", 872, 3072, 768, 0, 1, 0, 0, EPI_MUL, 0, 0},
       {"TN 872x768x3072 bias_resid", 872, 768, 3072, 0, 0, 0, 0, EPI_BIAS_RESID, 0, 0},
       {"TN 872x768x768 bias_resid drop", 872, 768, 768, 0, 0, 0, 0, EPI_BIAS_RESID, 0, 1},
       {"TN 64x768x768 bias_tanh", 64, 768, 768, 0, 0, 0, 0, EPI_BIAS_TANH, 0, 0},
@@ -230,6 +239,8 @@ int main(int argc, char** argv) {
       {"TN 128x3072x768 bias_gelu+C2", 128, 3072, 768, 0, 0, 0, 0, EPI_BIAS_GELU, 1, 0},
       {"TN 128x768x768 bias_resid drop", 128, 768, 768, 0, 0, 0, 0, EPI_BIAS_RESID, 0, 1},
       {"NN 300x192x136 dgelu", 300, 192, 136, 0, 1, 0, 0, EPI_DGELU, 0, 0},
+      {"TN 128x3072x768 gelu+gelu' (C2)", 128, 3072, 768, 0, 0, 0, 0, EPI_BIAS_GELU_GRAD, 1, 0},
+      {"NN 300x192x136 mul", 300, 192, 136, 0, 1, 0, 0, EPI_MUL, 0, 0},
       {"TT 200x136x300 acc", 200, 136, 300, 1, 1, 1, 1, EPI_NONE, 0, 0},
   };
   for (const Case& c : fcases) if (!perf_only) fails += run_case(c, true, 40000);

@@ -87,6 +87,17 @@ def test_gemm_forward_bias_gelu(prec, tol, M, N, K):
     run_gemm(prec_id, M, N, K, X, W, Y, epi=L.EPI_BIAS_GELU, bias=b, C2=P)
     assert rel_err(P[:, :N].float(), pre) < tol
     assert rel_err(Y[:, :N].float(), gelu_erf(pre)) < tol
+    # the pair the engine uses: forward saves gelu'(pre) instead of pre, the backward epilogue multiplies by it
+    G = torch.zeros(M, ld, device=DEV, dtype=dt)
+    run_gemm(prec_id, M, N, K, X, W, Y, epi=L.EPI_BIAS_GELU_GRAD, bias=b, C2=G)
+    dgelu = 0.5 * (1.0 + torch.erf(pre * 0.7071067811865476)) + pre * torch.exp(-0.5 * pre * pre) * 0.3989422804014327
+    assert rel_err(Y[:, :N].float(), gelu_erf(pre)) < tol
+    assert rel_err(G[:, :N].float(), dgelu) < tol
+    dY = (torch.randn(M, K, device=DEV, generator=g) * 0.1).to(dt)          # dX[M,N] = (dY[M,K] . W2[K,N]) * G, W2 read MN-major
+    W2 = (torch.randn(K, N, device=DEV, generator=g) * 0.05).to(dt)
+    dX = torch.zeros(M, ld, device=DEV, dtype=dt)
+    run_gemm(prec_id, M, N, K, dY, W2, dX, a_mn=0, b_mn=1, epi=L.EPI_MUL, aux=G)
+    assert rel_err(dX[:, :N].float(), (dY.float() @ W2.float()) * G[:, :N].float()) < tol
 
 
 @pytest.mark.parametrize("prec,tol", [("bf16", 1e-2), ("fp32", 1e-4)])
