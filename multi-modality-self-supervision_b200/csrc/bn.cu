@@ -52,15 +52,9 @@ __device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, flo
 // through shared memory.  Partials: [channel block][part][64 channels][3] — per layer at most 148*4*64*3 floats, so the
 // finalize pass reads a few hundred KB instead of the nparts*C*3 table the first version wrote (14.5 MB at C = 2048).
 constexpr int kBnCh = 64;        // channels per CTA
-struct BnFinalize {                     // what the last CTA of a channel block needs to turn the partials into scale / shift
-  const float* gamma; const float* beta; float* running_mean; float* running_var; float momentum, eps;
-  float* scale_shift;                   // [2][C]
-  int* counters;                        // [channel blocks] arrival counters, zero between launches (self-resetting)
-};
-
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long rows, int C, long rows_per_cta,
-                                                       float* __restrict__ partial, const BnFinalize fin) {
+                                                       float* __restrict__ partial) {
   __shared__ float red[32][kBnCh][3];      // 24 KB
   const int ct = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int c0 = blockIdx.y * kBnCh + ct * 8;
@@ -113,56 +107,60 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
     float* o = partial + ((static_cast<long>(blockIdx.y) * gridDim.x + blockIdx.x) * kBnCh + ch) * 3;
     o[0] = n; o[1] = mean; o[2] = m2;
   }
-  // ---- fused finalize: the LAST CTA of this channel block to arrive combines the block's partials (they are L2-resident)
-  // into scale / shift and the running statistics.  Replaces one tiny single-CTA launch per BatchNorm layer (53 per trunk
-  // pass, ~9 us each plus the launch gaps).  Two division-free passes: mean = sum n_i mean_i / N,
-  // M2 = sum (M2_i + n_i (mean_i - mean)^2).
-  __shared__ int s_last;
-  __threadfence();
+}
+
+// One CTA per 64-channel block, 1024 threads = 64 channels x 16 part lanes, coalesced reads of the (L2-resident) partial
+// table.  The partials are combined in two division-free passes instead of a chain of Chan updates (whose two divisions
+// per merge made this kernel ~12 us on its single SM):  mean = sum n_i mean_i / N,  M2 = sum (M2_i + n_i (mean_i - mean)^2).
+// Thread (channel, 0) produces scale / shift and updates the running statistics (momentum, unbiased variance: PyTorch).
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nparts, int C,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           float* running_mean, float* running_var, float momentum, float eps,
+                                                           int update_running, float* __restrict__ scale_shift /* [2][C] */) {
+  __shared__ float red[16][kBnCh][2];
+  __shared__ float s_mean[kBnCh], s_n[kBnCh];
+  const int ch = threadIdx.x & (kBnCh - 1), pl = threadIdx.x >> 6;
+  const int c = blockIdx.x * kBnCh + ch;
+  const float* base = partial + static_cast<long>(blockIdx.x) * nparts * kBnCh * 3;
+  float n = 0.f, sm = 0.f;
+  for (int p = pl; p < nparts; p += 16) {
+    const float* e = base + (static_cast<long>(p) * kBnCh + ch) * 3;
+    n += e[0];
+    sm = fmaf(e[0], e[1], sm);
+  }
+  red[pl][ch][0] = n; red[pl][ch][1] = sm;
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&fin.counters[blockIdx.y], 1) == static_cast<int>(gridDim.x) - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x == 0) fin.counters[blockIdx.y] = 0;           // ready for the next layer (same stream)
-  const int nparts = static_cast<int>(gridDim.x);
-  const int fch = threadIdx.x & (kBnCh - 1), pl = threadIdx.x >> 6;        // 64 channels x 4 part lanes
-  const int c = blockIdx.y * kBnCh + fch;
-  // (__ldcg: L2 loads that bypass this SM's L1, where stale lines of the partial table may sit; independent, so unrolled)
-  const float* base = partial + static_cast<long>(blockIdx.y) * nparts * kBnCh * 3;
-  float (*fr)[kBnCh][3] = red;             // reuse: [4][64][3] needed
-  float fn = 0.f, fs = 0.f;
-#pragma unroll 8
-  for (int p = pl; p < nparts; p += 4) {
-    const float* e = base + (static_cast<long>(p) * kBnCh + fch) * 3;
-    const float en = __ldcg(e);
-    fn += en;
-    fs = fmaf(en, __ldcg(e + 1), fs);
+  if (pl == 0) {
+    float N = 0.f, S = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { N += red[k][ch][0]; S += red[k][ch][1]; }
+    s_n[ch] = N;
+    s_mean[ch] = N > 0.f ? S / N : 0.f;
   }
   __syncthreads();
-  fr[pl][fch][0] = fn; fr[pl][fch][1] = fs;
-  __syncthreads();
-  const float N = fr[0][fch][0] + fr[1][fch][0] + fr[2][fch][0] + fr[3][fch][0];
-  const float S = fr[0][fch][1] + fr[1][fch][1] + fr[2][fch][1] + fr[3][fch][1];
-  const float fmean = N > 0.f ? S / N : 0.f;
-  float fm2 = 0.f;
-#pragma unroll 8
-  for (int p = pl; p < nparts; p += 4) {
-    const float* e = base + (static_cast<long>(p) * kBnCh + fch) * 3;
-    const float d = __ldcg(e + 1) - fmean;
-    fm2 += fmaf(__ldcg(e) * d, d, __ldcg(e + 2));
+  const float mean = s_mean[ch];
+  float m2 = 0.f;
+  for (int p = pl; p < nparts; p += 16) {
+    const float* e = base + (static_cast<long>(p) * kBnCh + ch) * 3;
+    const float d = e[1] - mean;
+    m2 += fmaf(e[0] * d, d, e[2]);
   }
-  __syncthreads();
-  fr[pl][fch][2] = fm2;
+  red[pl][ch][0] = m2;
   __syncthreads();
   if (pl != 0 || c >= C) return;
-  fm2 = fr[0][fch][2] + fr[1][fch][2] + fr[2][fch][2] + fr[3][fch][2];
-  const float var = fm2 / N;                     // biased: what normalisation uses
-  const float sc = fin.gamma[c] * rsqrtf(var + fin.eps);
-  fin.scale_shift[c] = sc;
-  fin.scale_shift[C + c] = fin.beta[c] - fmean * sc;
-  fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * fmean;
-  fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (N > 1.f ? fm2 / (N - 1.f) : var);
+  m2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) m2 += red[k][ch][0];
+  n = s_n[ch];
+  const float var = m2 / n;                      // biased: what normalisation uses
+  const float invstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * invstd;
+  scale_shift[c] = sc;
+  scale_shift[C + c] = beta[c] - mean * sc;
+  if (update_running) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (n > 1.f ? m2 / (n - 1.f) : var);
+  }
 }
 
 __global__ void bn_eval_scale_kernel(int C, const float* gamma, const float* beta, const float* running_mean,
@@ -224,15 +222,11 @@ static int bn_launch_stats(const void* x, long rows, int C, const float* gamma, 
   const int cblocks = (C + kBnCh - 1) / kBnCh;
   const long rows_per_cta = (rows + nparts - 1) / nparts;
   dim3 grid(nparts, cblocks);
-  static int* counters = nullptr;             // per-process arrival counters of the fused finalize (launches on ONE stream at a time)
-  if (!counters) {
-    MV_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&counters), 256 * sizeof(int)));
-    MV_CUDA_CHECK(cudaMemset(counters, 0, 256 * sizeof(int)));
-  }
-  MV_REQUIRE(cblocks <= 256, "bn: more than 16384 channels");
-  BnFinalize fin{gamma, beta, running_mean, running_var, momentum, eps, scale_shift, counters};
-  if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace, fin);
-  else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace, fin);
+  if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
+  else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
+  MV_LAUNCH_CHECK();
+  bn_finalize_kernel<<<cblocks, 1024, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
+                                              scale_shift);
   MV_LAUNCH_CHECK();
   return 0;
 }
