@@ -74,9 +74,76 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+REF_SAMPLE = ("B = 2 of the step's samples per CPU step (BASELINE.json configs[0]: BERT-base, L = 436, Bidirectional Auto-Regressive mask, "
+              "512x512 synthetic CXR, random-init weights, fp32, model.train() with dropout 0.1, forward + CE losses + backward + "
+              "HF-3.x AdamW), all host threads; samples/s = 2 / median step time")
+
+
+def _reference_modules_step_rate(steps, warmup, batch):
+    """The reference's OWN modules (models/cxrbert_origin.py + models/image.py, vendored byte for byte into oracle/_ref by
+    oracle/make_ref.py) under oracle/ref_shim.py: CXRBERT.forward -> CE(ignore_index=-100) + CE -> backward -> HF-3.x AdamW
+    restatement (models/train_origin.py:106-131), fp32, model.train(), dropout on."""
+    import types
+
+    import numpy as np
+    import torch
+    import torch.nn as nn
+
+    os.environ["MEDVILL_REFERENCE"] = os.path.join(ROOT, "oracle", "_ref")
+    from oracle import medvill_oracle as orc
+    from oracle import ref_shim
+
+    ref_shim.REF_ROOT = os.environ["MEDVILL_REFERENCE"]
+    cxr, _ = ref_shim.load_reference_models()
+    from transformers import BertConfig
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    cfg = orc.Cfg()
+    ref_shim.set_bert_config()
+    margs = types.SimpleNamespace(bert_model="bert-base-scratch", img_hidden_sz=2048, embedding_size=768, hidden_size=768,
+                                  dropout_prob=0.1, img_postion=True, img_encoder="random-pixel", num_image_embeds=cfg.num_image_embeds,
+                                  img_size=cfg.img_size, disturbing_mask=False, vocab_size=cfg.vocab)
+    model = cxr.CXRBERT(BertConfig.from_pretrained("bert-base-uncased"), margs).train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in params]
+    mlm_crit, itm_crit = nn.CrossEntropyLoss(ignore_index=-100), nn.CrossEntropyLoss()
+    times = []
+    for i in range(warmup + steps):
+        b = orc.synthetic_batch(cfg, batch, seed=1000 + i, mode=orc.MODE_BAR)
+        t = lambda k: torch.as_tensor(b[k])
+        t0 = time.perf_counter()
+        mlm, itm = model(t("cls_tok"), t("input_ids"), t("attn_masks"), t("segment"), b["image"], t("sep_tok"))
+        loss = itm_crit(itm, t("is_aligned")) + mlm_crit(mlm.transpose(1, 2), t("txt_labels"))
+        for p in params:
+            p.grad = None
+        loss.backward()
+        step = i + 1
+        with torch.no_grad():                       # transformers-3.x AdamW, correct_bias=True, weight_decay 0, lr 1e-5
+            ss = 1e-5 * (1 - 0.999 ** step) ** 0.5 / (1 - 0.9 ** step)
+            for p, (m, v) in zip(params, state):
+                if p.grad is None:
+                    continue
+                m.mul_(0.9).add_(p.grad, alpha=0.1)
+                v.mul_(0.999).addcmul_(p.grad, p.grad, value=0.001)
+                p.addcdiv_(m, v.sqrt().add_(1e-6), value=-ss)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    assert np.isfinite(float(loss.detach()))
+    return batch / med, med, os.cpu_count() or 1
+
+
 def cpu_reference_step_rate(steps, warmup, batch=2):
-    """The reference's CPU path restated (oracle/medvill_oracle.py, pinned against the real reference): fp32, all host
-    threads, BAR mask, forward + CE losses + backward + HF-AdamW, B=2 (BASELINE.json configs[0])."""
+    """CPU arm: the reference's own modules when oracle/_ref holds them (kind "reference"), else the oracle port
+    (oracle/medvill_oracle.py, pinned against the real reference; kind "port").  Returns (samples/s, median s, cores, kind)."""
+    if os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "models", "cxrbert_origin.py")):
+        try:
+            return _reference_modules_step_rate(steps, warmup, batch) + ("reference",)
+        except Exception as e:                      # e.g. a transformers version the shims do not cover: fall back to the port
+            sys.stderr.write("bench: reference modules under oracle/_ref failed (%s: %s); timing the oracle port instead\n" % (type(e).__name__, e))
     import torch
 
     from oracle import medvill_oracle as orc
@@ -97,22 +164,28 @@ def cpu_reference_step_rate(steps, warmup, batch=2):
             times.append(dt)
     times.sort()
     med = times[len(times) // 2]
-    return batch / med, med, os.cpu_count() or 1
+    return batch / med, med, os.cpu_count() or 1, "port"
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path on this box's host cores.  Same metric / unit /
+    workload as our arm; each CPU step is a BOUNDED SAMPLE of that workload (2 of its samples) — stated in config.sample and
+    cpu_baseline.sample.  Under torchrun only rank 0 runs; the GPU count does not enter (n_gpus is echoed for the driver)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 1))
-    rate, med, cores = cpu_reference_step_rate(steps, warm)
+    rate, med, cores, kind = cpu_reference_step_rate(steps, warm)
     n = args.gpus
+    cfg = workload(args, n)
+    cfg["sample"] = REF_SAMPLE
+    cfg["runs_on"] = "host CPU, %d threads; no GPU work in this arm" % cores
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": n, "steps": steps, "warmup": warm,
             "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload(args, n),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d timed steps of the B=2 (configs[0]) step after %d warm-up, median" % (steps, warm)},
+            "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d timed steps after %d warm-up, median; %s" % (steps, warm, REF_SAMPLE)},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _JSON_OUT.write(json.dumps(line) + "\n")
     _JSON_OUT.flush()
@@ -310,11 +383,10 @@ def run_ours(args):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        rate, med, cores = cpu_reference_step_rate(3, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "3 timed steps (median) of the B=2 configs[0] step on the host, oracle port of the reference, fp32"}
+        rate, med, cores, kind = cpu_reference_step_rate(3, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": "3 timed steps after 1 warm-up, median; " + REF_SAMPLE}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 16,
                     "ms_per_step": ms_e2e / args.steps},
@@ -331,10 +403,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="fixed GLOBAL batch split evenly over the ranks (BASELINE.json configs[3]: 512 -> 256 / 128 / 64 per GPU at 2 / 4 / 8 "
+                         "GPUs, one launch sequence per step); overrides --batch and reports scaling 'strong'")
     ap.add_argument("--dropout", type=float, default=0.1)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.strong = False
+    if args.global_batch > 0:
+        world = int(os.environ.get("WORLD_SIZE", 1))
+        if args.global_batch % world:
+            raise SystemExit("--global-batch %d is not divisible by %d ranks" % (args.global_batch, world))
+        args.batch, args.strong = args.global_batch // world, True
     # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter)
     # is routed to stderr; the JSON goes to the saved descriptor.
     global _JSON_OUT
