@@ -325,6 +325,31 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
   }
 }
 
+// Deterministic mode: dQ[b, q, :] = sum over the key tiles that can see query tile (q / 128), in ASCENDING key-tile order, of
+// the per-key-tile partials the backward CTAs stored — the same terms the fp32 reduce-adds would have summed in arrival order.
+__global__ void __launch_bounds__(256) attn_dq_sum_convert_kernel(const float* __restrict__ part, bf16* __restrict__ dqkv, AttnArgs a) {
+  const int H = a.nh * D, L = a.L, n_kv = (L + TK - 1) / TK;
+  const long rows = static_cast<long>(a.B) * L;
+  const long n8 = rows * (H >> 3);
+  for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / (H >> 3);
+    const int c = static_cast<int>(i % (H >> 3)) * 8;
+    const int b = static_cast<int>(r / L), q = static_cast<int>(r % L);
+    const int mode = a.mode[b], tl = a.t_len[b];
+    const int qt = q / TQ, q_lo = qt * TQ, q_hi = min(q_lo + TQ - 1, L - 1);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kt = 0; kt < n_kv; ++kt) {
+      if (!tile_any_allowed(mode, q_lo, q_hi, kt * TK, min(kt * TK + TK - 1, L - 1), a.A, tl)) continue;
+      const float* src = part + ((static_cast<long>(kt) * a.B + b) * L + q) * H + c;
+      const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w; acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
+    }
+    uint4 u;
+    u.x = pack_bf16x2(acc[0], acc[1]); u.y = pack_bf16x2(acc[2], acc[3]); u.z = pack_bf16x2(acc[4], acc[5]); u.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dqkv + r * 3 * H + c) = u;
+  }
+}
+
 struct BwdSmem {
   uint64_t bar_kv, bar_q[2], bar_s, bar_o, bar_pd, bar_stage;
   uint32_t tmem_base;
@@ -356,7 +381,7 @@ __device__ __forceinline__ void store_pk16(uint8_t* sP, int r, int col, const ui
 //   bar_stage  the reduce-add of dQ(k) has read its staging          issuer arrives, math warps wait before tile k+2's stores
 __global__ void __launch_bounds__(544, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                     const __grid_constant__ CUtensorMap tmDQ, const AttnArgs a) {
+                     const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDQP, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -381,6 +406,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQ);
+    tma_prefetch_desc(&tmDQP);
     mbar_init(&sh->bar_kv, 1); mbar_init(&sh->bar_q[0], 1); mbar_init(&sh->bar_q[1], 1);
     mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1); mbar_init(&sh->bar_pd, 512); mbar_init(&sh->bar_stage, 1);
     fence_mbar_init();
@@ -446,8 +472,13 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       TL_MARK();
       if (it > 0 && lane == 0) {                  // previous tile's dQ: one fp32 reduce-add per 32-column half
         uint8_t* stg = sPD + (buf ^ 1u) * 2 * P_BYTES;
-        tma_reduce_add_2d(&tmDQ, stg, h * D, row0 + prev * TQ);
-        tma_reduce_add_2d(&tmDQ, stg + TILE_BYTES, h * D + 32, row0 + prev * TQ);
+        if (a.dq_part) {                           // deterministic: plain store into this key tile's partial slot (rows >= L clipped)
+          tma_store_3d(&tmDQP, stg, h * D, prev * TQ, kt * a.B + b);
+          tma_store_3d(&tmDQP, stg + TILE_BYTES, h * D + 32, prev * TQ, kt * a.B + b);
+        } else {
+          tma_reduce_add_2d(&tmDQ, stg, h * D, row0 + prev * TQ);
+          tma_reduce_add_2d(&tmDQ, stg + TILE_BYTES, h * D + 32, row0 + prev * TQ);
+        }
         tma_commit_group();
       }
       __syncwarp();
@@ -494,8 +525,13 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_wait(&sh->bar_pd, it & 1u);
       if (lane == 0) {
         uint8_t* stg = sPD + ((it - 1) & 1u) * 2 * P_BYTES;
-        tma_reduce_add_2d(&tmDQ, stg, h * D, row0 + prev * TQ);
-        tma_reduce_add_2d(&tmDQ, stg + TILE_BYTES, h * D + 32, row0 + prev * TQ);
+        if (a.dq_part) {
+          tma_store_3d(&tmDQP, stg, h * D, prev * TQ, kt * a.B + b);
+          tma_store_3d(&tmDQP, stg + TILE_BYTES, h * D + 32, prev * TQ, kt * a.B + b);
+        } else {
+          tma_reduce_add_2d(&tmDQ, stg, h * D, row0 + prev * TQ);
+          tma_reduce_add_2d(&tmDQ, stg + TILE_BYTES, h * D + 32, row0 + prev * TQ);
+        }
         tma_commit_group();
         tma_wait_group<0>();
       }
@@ -716,20 +752,28 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
   CUtensorMap tmDQ;
   rc = tmap_encode_2d(&tmDQ, TMAP_F32, a.dq_acc, H, rows, static_cast<uint64_t>(H) * 4, 32, TQ);
   if (rc) return rc;
+  CUtensorMap tmDQP = tmDQ;
+  if (a.dq_part) {     // [n_kv * B][L][H] fp32, box 32 x 128 x 1: query rows past a sample's end are clipped instead of spilling over
+    const int n_kv = (a.L + TK - 1) / TK;
+    rc = tmap_encode_3d(&tmDQP, TMAP_F32, a.dq_part, H, a.L, static_cast<uint64_t>(n_kv) * a.B, static_cast<uint64_t>(H) * 4,
+                        static_cast<uint64_t>(a.L) * H * 4, 32, TQ, 1);
+    if (rc) return rc;
+  }
   static bool attr = false;
   if (!attr) {
     MV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
     attr = true;
   }
-  MV_CUDA_CHECK(cudaMemsetAsync(a.dq_acc, 0, rows * H * sizeof(float), s));
+  if (!a.dq_part) MV_CUDA_CHECK(cudaMemsetAsync(a.dq_acc, 0, rows * H * sizeof(float), s));
   attn_delta_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, s>>>(static_cast<const bf16*>(a.dctx),
                                                                              static_cast<const bf16*>(a.ctx), a.delta,
                                                                              static_cast<int>(rows), a.L, a.nh);
   MV_LAUNCH_CHECK();
   dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
-  attn_bwd_tc05_kernel<<<grid, 544, kBwdSmem, s>>>(tmQKV, tmDO, tmDQ, a);
+  attn_bwd_tc05_kernel<<<grid, 544, kBwdSmem, s>>>(tmQKV, tmDO, tmDQ, tmDQP, a);
   MV_LAUNCH_CHECK();
-  attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
+  if (a.dq_part) attn_dq_sum_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_part, static_cast<bf16*>(a.dqkv), a);
+  else attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
   MV_LAUNCH_CHECK();
   return 0;
 }

@@ -251,6 +251,7 @@ int Engine::init(const mv_config& c) {
       alloc(reinterpret_cast<void**>(&stats), sizeof(mv_step_stats)))
     return -2;
   if (rf32 && (alloc(reinterpret_cast<void**>(&xres), M * H * 4) || alloc(reinterpret_cast<void**>(&x1res), M * H * 4))) return -2;
+  if (!f32 && (c.flags & MV_FLAG_DETERMINISTIC) && alloc(reinterpret_cast<void**>(&dq_part), static_cast<size_t>((L + 127) / 128) * M * H * 4)) return -2;
   MV_CUDA_CHECK(cudaMemset(zero_idx, 0, 16));
   MV_CUDA_CHECK(cudaMemset(stats, 0, sizeof(mv_step_stats)));
   MV_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&stats_host), sizeof(mv_step_stats)));
@@ -568,7 +569,7 @@ int Engine::backward(const mv_batch& b, int allreduce, cudaStream_t s) {
     AttnArgs aa;
     memset(&aa, 0, sizeof(aa));
     aa.B = B; aa.L = L; aa.nh = nh; aa.A = A; aa.mode = b.mode; aa.t_len = b.t_len; aa.qkv = w.qkv; aa.ctx = w.ctx; aa.lse = w.lse;
-    aa.dctx = dctx; aa.dqkv = dqkv; aa.dq_acc = dq_acc; aa.delta = delta;
+    aa.dctx = dctx; aa.dqkv = dqkv; aa.dq_acc = dq_acc; aa.delta = delta; aa.dq_part = dq_part;
     aa.drop_on = drop_att; aa.drop_site = site_att(l); aa.drop = dc_att;
     MV_TRY(prof_begin(2, 10.0 * B * nh * static_cast<double>(L) * L * 64, s));
     MV_TRY(f32 ? attention_bwd_simt(aa, s) : attention_bwd_tc05(aa, s));

@@ -43,6 +43,7 @@ struct Engine {
   float* itm_logits = nullptr;
   void *dxa = nullptr, *dxb = nullptr, *dxc = nullptr, *dh1 = nullptr, *dqkv = nullptr, *dctx = nullptr, *dproj = nullptr;
   float *dq_acc = nullptr, *delta = nullptr;
+  float* dq_part = nullptr;        // MV_FLAG_DETERMINISTIC: per-key-tile dQ partials [ceil(L/128)][B][L][H]
   int64_t* zero_idx = nullptr;     // [1] = {0}: gather/scatter of the [CLS] rows
   mv_step_stats* stats = nullptr;    // device
   mv_step_stats* stats_host = nullptr;  // pinned

@@ -180,6 +180,8 @@ struct AttnArgs {
   const void* dctx;                  // [B*L, H]
   void* dqkv;                        // [B*L, 3H]
   float* dq_acc;                     // [B*L, H] fp32 scratch (tcgen05 path; zeroed by the launcher)
+  float* dq_part = nullptr;          // deterministic mode (tcgen05 path): [ceil(L/128)][B][L][H] fp32 per-key-tile dQ partials, summed
+                                     // in key-tile order by the convert pass instead of fp32 reduce-adds in arrival order
   float* delta;                      // [B, nh, L] scratch: rowsum(dO * O)
   int drop_on; uint32_t drop_site; DropoutCfg drop;
 #ifdef MV_ATTN_TIMELINE

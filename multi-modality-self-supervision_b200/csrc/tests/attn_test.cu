@@ -230,7 +230,7 @@ static void perf(int drop) {
 // dK and dV are owned by exactly one CTA each and must be identical; dQ is summed over key tiles by fp32 TMA reduce-adds in
 // arrival order, so only its fp32 accumulator may differ (and the few bf16 values that land on the other side of a rounding
 // boundary).  A difference anywhere else would mean a race in the pipelined backward.
-static int repro(int drop) {
+static int repro(int drop, int det = 0) {
   const int B = 64, nh = 12, L = 436, A = 182, H = nh * 64;
   const size_t rows = (size_t)B * L;
   std::vector<float> qkv(rows * 3 * H), dctx(rows * H);
@@ -250,6 +250,11 @@ static int repro(int drop) {
   memset(&a, 0, sizeof(a));
   a.B = B; a.L = L; a.nh = nh; a.A = A; a.mode = d_mode; a.t_len = d_tlen; a.qkv = d_qkv; a.ctx = d_ctx; a.lse = lse;
   a.dctx = d_dctx; a.dqkv = d_dqkv; a.dq_acc = dq_acc; a.delta = delta; a.drop_on = drop; a.drop_site = 3; a.drop = make_dropout(0.1f, 7);
+  if (det) {      // ordered dQ reduction (MV_FLAG_DETERMINISTIC): per-key-tile partial slots summed in key-tile order
+    float* part = nullptr;
+    cudaMalloc(&part, (size_t)((L + 127) / 128) * rows * H * 4);
+    a.dq_part = part;
+  }
   std::vector<unsigned short> ctx[2], dqkv[2];
   std::vector<float> l[2];
   for (int r = 0; r < 2; ++r) {
@@ -271,7 +276,22 @@ static int repro(int drop) {
     }
   printf("  repro (dropout=%d): differing elements  ctx %zu  lse %zu  dQ %zu (of %zu, fp32 reduce order)  dK %zu  dV %zu\n", drop,
          d_ctx_n, d_lse_n, d_q, rows * H, d_k, d_v);
-  const bool ok = d_ctx_n == 0 && d_lse_n == 0 && d_k == 0 && d_v == 0 && d_q < rows * H / 100;
+  const bool ok = d_ctx_n == 0 && d_lse_n == 0 && d_k == 0 && d_v == 0 && (det ? d_q == 0 : d_q < rows * H / 100);
+  if (det) {      // cost of the ordered reduction, next to the reduce-add path
+    cudaEvent_t e0, e1, e2;
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    AttnArgs a2 = a;
+    a2.dq_part = nullptr;
+    cudaEventRecord(e0);
+    for (int i = 0; i < 10; ++i) attention_bwd_tc05(a, 0);
+    cudaEventRecord(e1);
+    for (int i = 0; i < 10; ++i) attention_bwd_tc05(a2, 0);
+    cudaEventRecord(e2);
+    cudaEventSynchronize(e2);
+    float t1, t2;
+    cudaEventElapsedTime(&t1, e0, e1); cudaEventElapsedTime(&t2, e1, e2);
+    printf("  backward per layer: ordered dQ %.3f ms, reduce-add dQ %.3f ms\n", t1 / 10, t2 / 10);
+  }
   printf("%s\n", ok ? "ATTN REPRO PASSED" : "ATTN REPRO FAILED");
   return ok ? 0 : 1;
 }
@@ -321,7 +341,7 @@ static void timeline(int drop) {
 
 int main(int argc, char** argv) {
   if (argc > 1 && !strcmp(argv[1], "--perf")) { perf(argc > 2 ? atoi(argv[2]) : 1); return 0; }
-  if (argc > 1 && !strcmp(argv[1], "--repro")) return repro(argc > 2 ? atoi(argv[2]) : 0);
+  if (argc > 1 && !strcmp(argv[1], "--repro")) return repro(argc > 2 ? atoi(argv[2]) : 0, argc > 3 ? atoi(argv[3]) : 0);
 #ifdef MV_ATTN_TIMELINE
   if (argc > 1 && !strcmp(argv[1], "--timeline")) { timeline(argc > 2 ? atoi(argv[2]) : 1); return 0; }
 #endif

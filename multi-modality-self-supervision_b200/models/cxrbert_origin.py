@@ -23,6 +23,7 @@ import torch.nn as nn
 from .. import _lib
 from ..config import BertConfig
 from ..engine import EngineDims, PretrainEngine
+from ..utils.utils import deterministic_requested
 from .image import ImageEncoder_cnn
 
 _FUSED_MSG = ("%s.forward is fused into libmedvill_sm100 (mv_forward); call CXRBERT / CXRBertEncoder.forward or "
@@ -364,7 +365,8 @@ class CXRBERT(nn.Module):
                           # embeddings, args.dropout_prob only for the image embeddings (cxrbert_origin.py:19)
                           dropout_p=float(getattr(c, "hidden_dropout_prob", a.dropout_prob)),
                           attn_dropout_p=float(getattr(c, "attention_probs_dropout_prob", a.dropout_prob)),
-                          img_dropout_p=float(a.dropout_prob), flags=int(getattr(a, "engine_flags", 0)))
+                          img_dropout_p=float(a.dropout_prob),
+                          flags=int(getattr(a, "engine_flags", 0)) | (_lib.FLAG_DETERMINISTIC if deterministic_requested() else 0))
 
     def _trainable(self):
         """reference-named trainable parameters (aliases de-duplicated, ResNet excluded)"""

@@ -5,7 +5,18 @@ import numpy as np
 import torch
 
 
+_DETERMINISTIC = False
+
+
+def deterministic_requested():
+    """True once set_seed() ran: the reference's set_seed switches cuDNN to deterministic algorithms (utils/utils.py:14-15);
+    here it additionally selects the engine's ordered (bit-reproducible) attention-dQ reduction (MV_FLAG_DETERMINISTIC)."""
+    return _DETERMINISTIC
+
+
 def set_seed(seed):
+    global _DETERMINISTIC
+    _DETERMINISTIC = True
     random.seed(seed)
     np.random.seed(seed)
     torch.manual_seed(seed)
