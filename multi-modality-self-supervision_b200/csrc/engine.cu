@@ -164,6 +164,15 @@ int engine_comm_init(Engine* e, const uint8_t id[128], int rank, int world) {
     MV_REQUIRE(rc == 0, "ncclCommInitRank failed: %s", n->GetErrorString ? n->GetErrorString(rc) : "?");
   }
   e->nccl = n; e->comm = comm; e->rank = rank; e->world = world;
+  const char* gc = getenv("MEDVILL_GRAD_COMM");
+  e->comm_bf16 = (!e->f32 && gc && !strcmp(gc, "bf16")) ? 1 : 0;
+  if (e->comm_bf16 && !e->comm_stage) {
+    int64_t mx = 0;
+    for (const Bucket& b : e->buckets) mx = b.count > mx ? b.count : mx;
+    void* p = nullptr;
+    if (e->alloc(&p, static_cast<size_t>(mx) * sizeof(bf16))) return -2;
+    e->comm_stage = static_cast<bf16*>(p);
+  }
   MV_CUDA_CHECK(cudaStreamCreateWithFlags(&e->comm_stream, cudaStreamNonBlocking));
   MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_ready, cudaEventDisableTiming));
   MV_CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
@@ -176,6 +185,18 @@ int engine_allreduce(Engine* e, float* buf, int64_t count, cudaStream_t s) {
   const int rc = e->nccl->AllReduce(buf, buf, static_cast<size_t>(count), /*ncclFloat32*/ 7, /*ncclSum*/ 0, e->comm, s);
   MV_REQUIRE(rc == 0, "ncclAllReduce failed: %s", e->nccl->GetErrorString ? e->nccl->GetErrorString(rc) : "?");
   return 0;
+}
+
+// Gradient bucket exchange.  MEDVILL_GRAD_COMM=bf16 (bf16 precision mode only): the bucket travels as bf16 — half the NVLink
+// bytes and half the time the collective's CTAs share the SMs with the persistent GEMMs — and comes back into the fp32
+// arena; the arena itself (accumulation across micro-batches, Adam) stays fp32.  Default: fp32 on the wire.
+static int engine_allreduce_bucket(Engine* e, float* buf, int64_t count, cudaStream_t s) {
+  if (!e->comm_bf16) return engine_allreduce(e, buf, count, s);
+  MV_REQUIRE(e->comm != nullptr && e->comm_stage != nullptr, "communicator not initialised (mv_comm_init)");
+  if (cast_f32_to_bf16(buf, e->comm_stage, count, s)) return -2;
+  const int rc = e->nccl->AllReduce(e->comm_stage, e->comm_stage, static_cast<size_t>(count), /*ncclBfloat16*/ 9, /*ncclSum*/ 0, e->comm, s);
+  MV_REQUIRE(rc == 0, "ncclAllReduce(bf16) failed: %s", e->nccl->GetErrorString ? e->nccl->GetErrorString(rc) : "?");
+  return cast_bf16_to_f32(e->comm_stage, buf, count, s);
 }
 
 int engine_comm_sync(Engine* e, cudaStream_t s) {
@@ -495,7 +516,7 @@ int Engine::bucket_done(size_t idx, int allreduce, cudaStream_t s) {
   const Bucket& bk = buckets[idx];
   MV_CUDA_CHECK(cudaEventRecord(ev_ready, s));
   MV_CUDA_CHECK(cudaStreamWaitEvent(comm_stream, ev_ready, 0));
-  MV_TRY(engine_allreduce(this, grads + bk.offset, bk.count, comm_stream));
+  MV_TRY(engine_allreduce_bucket(this, grads + bk.offset, bk.count, comm_stream));
   comm_pending = true;
   if (idx + 2 == buckets.size()) {          // everything except the last bucket (embeddings) is now queued on comm_stream
     MV_CUDA_CHECK(cudaEventRecord(ev_mid, comm_stream));

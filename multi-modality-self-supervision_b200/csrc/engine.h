@@ -59,6 +59,8 @@ struct Engine {
   cudaStream_t comm_stream = nullptr; cudaEvent_t ev_ready = nullptr, ev_done = nullptr; bool comm_pending = false;
   cudaEvent_t ev_mid = nullptr; bool mid_recorded = false;   // all buckets but the last (embeddings) have been reduced
   std::vector<Bucket> buckets;
+  bf16* comm_stage = nullptr;      // bf16 gradient exchange (MEDVILL_GRAD_COMM=bf16): staging for the largest bucket
+  int comm_bf16 = 0;
 
   // optional per-kernel-family timing (CUDA events on the launch stream): tag 0 = tcgen05/SIMT GEMM, 1 = attention fwd,
   // 2 = attention bwd.  Used by bench.py for the live roofline numbers; off by default.
