@@ -331,11 +331,13 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
             if (32 * ch + 64 * c < n_col && c_lo < hi_max && c_lo + 31 >= lo_min) {
 #pragma unroll
               for (int g = 0; g < 2; ++g) {
-                const uint4 rnd = dropout_rand16(a.drop, a.drop_site, attn_drop_group(it.b, a.nh, it.h, L, qc, (c_lo + 16 * g) >> 4));
-                kf[c][4 * g + 0] = keep_flags4(rnd.x, a.drop.thresh4);
-                kf[c][4 * g + 1] = keep_flags4(rnd.y, a.drop.thresh4);
-                kf[c][4 * g + 2] = keep_flags4(rnd.z, a.drop.thresh4);
-                kf[c][4 * g + 3] = keep_flags4(rnd.w, a.drop.thresh4);
+                const uint64_t grp = attn_drop_group(it.b, a.nh, it.h, L, qc, (c_lo + 16 * g) >> 4);
+                const uint4 rnd = dropout_rand16(a.drop, a.drop_site, grp);
+                const uint32_t t4 = dropout_thresh4(a.drop, grp);
+                kf[c][4 * g + 0] = keep_flags4(rnd.x, t4);
+                kf[c][4 * g + 1] = keep_flags4(rnd.y, t4);
+                kf[c][4 * g + 2] = keep_flags4(rnd.z, t4);
+                kf[c][4 * g + 3] = keep_flags4(rnd.w, t4);
               }
             }
           }
@@ -491,7 +493,7 @@ int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s) {
   static int legacy = -1;                    // MV_ATTN_FWD_LEGACY=1: the r01 kernel (A/B measurements)
   if (legacy < 0) { const char* e = getenv("MV_ATTN_FWD_LEGACY"); legacy = e ? atoi(e) : 0; }
   // byte-sliced threshold compare of the keep bits needs a threshold <= 128 (p <= 0.5)
-  if (legacy || (a.drop_on && (a.drop.thresh4 & 0xFFu) > 128u)) return attention_fwd_legacy_tc05(a, s);
+  if (legacy || (a.drop_on && (a.drop.thresh4 & 0xFFu) > 127u)) return attention_fwd_legacy_tc05(a, s);
   const int H = a.nh * D;
   CUtensorMap tm;
   int rc = tmap_encode_2d(&tm, TMAP_BF16, a.qkv, 3 * H, static_cast<uint64_t>(a.B) * a.L, static_cast<uint64_t>(3 * H) * 2, D, TQ);

@@ -219,11 +219,13 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
         // dropped probabilities are zeroed with one AND per bf16 pair; the 1/(1-p) keep-scale is applied once to O
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
-          const uint4 rnd = dropout_rand16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, min(q, L - 1), (kc0 + c * 32 + 16 * g) >> 4));
+          const uint64_t grp = attn_drop_group(b, a.nh, h, L, min(q, L - 1), (kc0 + c * 32 + 16 * g) >> 4);
+          const uint4 rnd = dropout_rand16(a.drop, a.drop_site, grp);
+          const uint32_t t4 = dropout_thresh4(a.drop, grp);
           const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
-            const uint32_t fl = keep_flags4_any(rw[w], a.drop.thresh4);
+            const uint32_t fl = keep_flags4_any(rw[w], t4);
             pk[8 * g + 2 * w] &= keep_mask_pair(fl, 0);
             pk[8 * g + 2 * w + 1] &= keep_mask_pair(fl, 1);
           }
@@ -621,11 +623,13 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           p[e] = (static_cast<uint32_t>(e - rel_lo) < span) ? ex2(fmaf(__uint_as_float(sv[e]), scale2, -lse2)) : 0.f;
       }
       if (a.drop_on) {
-        const uint4 rnd = dropout_rand16(a.drop, a.drop_site, attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + col) >> 4));
+        const uint64_t grp = attn_drop_group(b, a.nh, h, L, q_ok ? q : 0, (k_lo + col) >> 4);
+        const uint4 rnd = dropout_rand16(a.drop, a.drop_site, grp);
+        const uint32_t t4 = dropout_thresh4(a.drop, grp);
         const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          const uint32_t fl = keep_flags4_any(rw[w], a.drop.thresh4);
+          const uint32_t fl = keep_flags4_any(rw[w], t4);
           // per-lane masks: byte j of `fl` has bit 7 set iff element 4 w + j is kept
           const uint32_t m01 = keep_mask_pair(fl, 0), m23 = keep_mask_pair(fl, 1);
 #pragma unroll

@@ -98,24 +98,37 @@ __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat1
 // ---- dropout RNG: Philox4x32-7, one call -> 16 x 8-bit lanes ----
 // Keyed by (seed, site); counter = 64-bit element-group index (16 consecutive elements of a row).
 // The same (seed, site, group) regenerates the same keep-mask in forward and backward, so no mask tensor is ever
-// stored.  8-bit thresholds: the effective drop probability is round(256 p) / 256 (p = 0.1 -> 0.1016) and the
-// keep-scale uses the effective value, so dropout stays unbiased.
+// stored.  An element is dropped iff its random byte < the group's threshold.  256 p is not an integer in general
+// (p = 0.1 -> 25.6), so the threshold is DITHERED per group: floor(256 p) + 1 with probability frac(256 p), else
+// floor(256 p), decided by an 8-bit hash of the group index and the seed (dropout_thresh4).  Every element is then
+// dropped with probability p to within 2^-16 (p = 0.1 -> 0.100006; plain 8-bit rounding gave 0.1016) and the keep-scale
+// is the reference's 1 / (1 - p).
 struct DropoutCfg {
   float p;             // drop probability as configured
-  uint32_t thresh4;    // the 8-bit threshold replicated in 4 bytes: element dropped iff its random byte < threshold
-  float scale;         // 1 / (1 - threshold/256)
+  uint32_t thresh4;    // floor(256 p) replicated in 4 bytes
+  uint32_t frac8;      // round(256 * frac(256 p)): groups whose hash byte is below it use threshold floor(256 p) + 1
+  float scale;         // 1 / (1 - p)
   uint64_t seed;       // per-step seed
 };
 
 __host__ __device__ inline DropoutCfg make_dropout(float p, uint64_t seed) {
   DropoutCfg d;
   d.p = p;
-  uint32_t t = static_cast<uint32_t>(p * 256.0f + 0.5f);
-  if (t > 255u) t = 255u;
+  const float t256 = p * 256.0f;
+  uint32_t t = static_cast<uint32_t>(t256);
+  if (t > 254u) t = 254u;
+  uint32_t f = static_cast<uint32_t>((t256 - static_cast<float>(t)) * 256.0f + 0.5f);
+  if (f > 255u) { f = 0u; t += 1u; }
   d.thresh4 = t * 0x01010101u;
-  d.scale = 1.0f / (1.0f - static_cast<float>(t) / 256.0f);
+  d.frac8 = f;
+  d.scale = 1.0f / (1.0f - p);
   d.seed = seed;
   return d;
+}
+// the (replicated) byte threshold of element group g
+__device__ __forceinline__ uint32_t dropout_thresh4(const DropoutCfg& d, uint64_t g) {
+  const uint32_t h = (static_cast<uint32_t>(g) * 0x9E3779B1u) ^ (static_cast<uint32_t>(g >> 32) * 0x85EBCA6Bu) ^ static_cast<uint32_t>(d.seed >> 7);
+  return ((h * 0xC2B2AE35u) >> 24) < d.frac8 ? d.thresh4 + 0x01010101u : d.thresh4;
 }
 
 __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
@@ -136,8 +149,9 @@ __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ uint4 dropout_keep16(const DropoutCfg& d, uint32_t site, uint64_t g) {
   uint4 r = philox4x32_7(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), site, 0x4d56u,
                          static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
-  r.x = __vcmpgeu4(r.x, d.thresh4); r.y = __vcmpgeu4(r.y, d.thresh4);
-  r.z = __vcmpgeu4(r.z, d.thresh4); r.w = __vcmpgeu4(r.w, d.thresh4);
+  const uint32_t t4 = dropout_thresh4(d, g);
+  r.x = __vcmpgeu4(r.x, t4); r.y = __vcmpgeu4(r.y, t4);
+  r.z = __vcmpgeu4(r.z, t4); r.w = __vcmpgeu4(r.w, t4);
   return r;
 }
 // The raw 128 random bits of group `g` (16 x 8-bit lanes): dropout_keep16 == byte-wise (lane >= threshold) of this.

@@ -35,7 +35,7 @@ struct GemmDesc {
   const void* resid = nullptr; long ldr = 0;            // [M,N] activation dtype, or fp32 when resid_f32 (then c_f32 too)
   int resid_f32 = 0;                                    // fp32 residual stream: resid AND C are fp32 (EPI_BIAS_RESID only)
   const void* aux = nullptr; long ldaux = 0;            // [M,N] activation dtype
-  int drop_on = 0; uint32_t drop_site = 0; DropoutCfg drop = {0.f, 0u, 1.f, 0ull};
+  int drop_on = 0; uint32_t drop_site = 0; DropoutCfg drop = {0.f, 0u, 0u, 1.f, 0ull};
   int splitk = 0;                                       // 0 = auto (only used when accumulate=1)
   int pair = -1;                                        // CTA-pair (cta_group::2, 256-row tiles): -1 auto, 0 off, 1 on
   int bn = 0;                                           // N tile: 0 auto, else 128 / 192 / 256 (tests, tuning)

@@ -300,3 +300,34 @@ def test_adamw_kernel_matches_hf_formula():
         ref_p.update(orc.adamw_step(ref_p, {"w": grad}, state, lr=1e-3, step=step))
     assert rel_err(p.cpu(), ref_p["w"]) < 1e-6
     assert torch.equal(shadow.cpu(), p.cpu().to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("p", [0.1, 0.25, 0.037])
+def test_dropout_probability_and_scale_are_the_configured_ones(p):
+    """Dropout keep decisions are byte compares against a per-group DITHERED threshold (floor(256 p) or floor(256 p) + 1, by
+    an 8-bit hash of the group): the drop rate is p to ~1e-4 over 12.6 M elements (plain 8-bit rounding would give 26/256 =
+    0.1016 for p = 0.1) and kept values are scaled by exactly 1 / (1 - p), as torch.nn.Dropout does."""
+    L = _L()
+    M, N, K = 16384, 768, 64
+    g = torch.Generator(device=DEV).manual_seed(3)
+    X = torch.randn(M, K, device=DEV, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(torch.bfloat16)
+    b = torch.full((N,), 4.0, device=DEV)                       # keeps every pre-dropout value well away from zero
+    R = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    Y = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    d = L.mv_gemm_desc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda, d.B, d.ldb = X.data_ptr(), K, W.data_ptr(), K
+    d.C, d.ldc = Y.data_ptr(), N
+    d.epi, d.bias, d.resid, d.ldr = L.EPI_BIAS_RESID, b.data_ptr(), R.data_ptr(), N
+    d.dropout_p, d.dropout_seed, d.dropout_site = p, 12345, 9
+    L.check(L.lib().mv_gemm(C.byref(d), L.MV_PREC_BF16, L.stream_ptr()), "mv_gemm")
+    torch.cuda.synchronize()
+    pre = X.float() @ W.float().t() + b
+    dropped = Y == 0
+    rate = float(dropped.float().mean())
+    sigma = (p * (1 - p) / (M * N)) ** 0.5
+    print("dropout p=%.3f: measured drop rate %.6f (binomial sigma %.1e)" % (p, rate, sigma))
+    assert abs(rate - p) <= 6 * sigma + 2e-5
+    ratio = (Y.float()[~dropped] / pre[~dropped]).mean()
+    assert abs(float(ratio) - 1.0 / (1.0 - p)) <= 3e-3 * (1.0 / (1.0 - p))       # bf16 output rounding averages out

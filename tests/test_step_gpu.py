@@ -111,7 +111,9 @@ def test_step_fp32_check_mode_tiny(name):
 def test_step_bf16_tiny(name):
     o = run_step(name, "bf16")
     check_forward(o, 1e-2, 3e-2)
-    w = check_grads_vs_oracle(o, 0.95, 0.12)     # B = 3..4, H = 128: few-term contractions, near-cancelling head gradients
+    # measured (r02, fp32 residual stream): tensors carrying >= 1 % of the largest gradient norm: cosine >= 0.99995, norm within
+    # 0.3 %; the small ITM-head / pooler tensors of the B = 4 mixed batch (near-tied ITM logits): 0.972 / 6 %
+    w = check_grads_vs_oracle(o, 0.9995, 0.01, cos_min_small=0.96, norm_tol_small=0.08)
     print("worst grad cosine %.5f" % w)
 
 
@@ -122,15 +124,18 @@ def test_step_fp32_config1():
     check_grads(o, 3e-3, 1e-2)
 
 
-def check_grads_vs_oracle(o, cos_min, norm_tol):
+def check_grads_vs_oracle(o, cos_min, norm_tol, cos_min_small=None, norm_tol_small=None):
     """bf16 gradients, tensor by tensor, against the CPU oracle's full gradients (the oracle itself is pinned to the
     reference to 1e-5): cosine similarity and norm ratio.  Element probes are meaningless in bf16 for entries far below
-    the tensor's scale (LayerNorm-backward cancellation), so this is the bf16 gradient gate."""
+    the tensor's scale (LayerNorm-backward cancellation), so this is the bf16 gradient gate.  Tensors whose gradient norm is
+    below 1 % of the largest tensor's (biases / LayerNorm gains whose terms nearly cancel) get `cos_min_small`."""
     eng, cfg, params = o["eng"], o["cfg"], o["params"]
     batch = golden_batch(o["g"], cfg)
     ref = orc.loss_and_grads(params, batch, cfg, feats=oracle_feats(params, batch))["grads"]
     scale = max(float(v.norm()) for v in ref.values())
-    worst = 1.0
+    cos_min_small = cos_min if cos_min_small is None else cos_min_small
+    norm_tol_small = norm_tol if norm_tol_small is None else norm_tol_small
+    rows = []
     for n, r in ref.items():
         got = eng.view(n, eng.grads).float().cpu().flatten().double()
         r = r.flatten().double()
@@ -138,10 +143,15 @@ def check_grads_vs_oracle(o, cos_min, norm_tol):
             assert float(got.norm()) <= 1e-3 * scale, n
             continue
         cos = float(got @ r / (got.norm() * r.norm()))
-        worst = min(worst, cos)
-        assert cos >= cos_min, "grad cosine %s: %.5f" % (n, cos)
-        assert abs(float(got.norm()) / float(r.norm()) - 1.0) <= norm_tol, "grad norm %s: %.4e vs %.4e" % (n, got.norm(), r.norm())
-    return worst
+        rows.append((cos, abs(float(got.norm()) / float(r.norm()) - 1.0), float(r.norm()) / scale, n))
+    rows.sort()
+    for cos, dn, rel, n in rows[:3]:
+        print("  low-cosine tensor %-60s cos %.5f  norm dev %.4f  |g| / max|g| %.2e" % (n, cos, dn, rel))
+    print("  worst norm deviation %.4f" % max(r[1] for r in rows))
+    for cos, dn, rel, n in rows:
+        assert cos >= (cos_min if rel >= 1e-2 else cos_min_small), "grad cosine %s: %.5f" % (n, cos)
+        assert dn <= (norm_tol if rel >= 1e-2 else norm_tol_small), "grad norm %s: deviation %.4f" % (n, dn)
+    return rows[0][0]
 
 
 def autocast_logit_error(o):
@@ -176,5 +186,5 @@ def test_step_bf16_config1():
     floor = autocast_logit_error(o)
     print("bf16 logits rel-L2: ours %.3e, torch autocast floor %.3e" % (ours, floor))
     assert ours <= 1.3 * floor        # same rounding points as autocast: bf16 GEMM operands, fp32 residual stream
-    w = check_grads_vs_oracle(o, 0.99, 0.08)
+    w = check_grads_vs_oracle(o, 0.999, 0.02)        # measured: worst cosine 0.9996, worst norm deviation 1.0 %
     print("worst grad cosine %.5f" % w)
