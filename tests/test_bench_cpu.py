@@ -1,4 +1,5 @@
-"""bench.py contract on the CPU: the reference arm (`--impl reference`, the oracle port of the reference's CPU path) prints
+"""bench.py contract on the CPU: the reference arm (`--impl reference`: the reference's own modules when oracle/make_ref.py has
+vendored them into oracle/_ref, else the oracle port of the reference's CPU path) prints
 exactly ONE JSON line on stdout with the keys the driver reads, and `bench.py` without a GPU fails loudly instead of
 falling back."""
 import json
@@ -21,7 +22,10 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "MLM+ITM pretrain samples/sec" and d["unit"] == "samples/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "models", "cxrbert_origin.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "B = 2" in d["config"]["sample"] and "B = 2" in d["cpu_baseline"]["sample"]       # the line says what it timed
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 
