@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -20,6 +21,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+int tmap_encode_2d_uncached(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t inner, uint64_t outer,
+                            uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -39,8 +43,43 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// Descriptor cache: a training step encodes the same ~600 maps (same workspace pointers and shapes) every step, four per
+// GEMM launch; cuTensorMapEncodeTiled costs ~1 us of host time each.  Keyed by every argument of the encode; thread-local
+// (the engine launches from one thread), bounded.
+namespace {
+struct TmapKey {
+  const void* base; uint64_t inner, outer, stride; uint32_t box_inner, box_outer, dt;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && stride == o.stride && box_inner == o.box_inner &&
+           box_outer == o.box_outer && dt == o.dt;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner * 0xC2B2AE3D27D4EB4Full) ^ (k.outer << 17) ^ (k.stride << 33) ^ (static_cast<uint64_t>(k.box_inner) << 7) ^
+         (static_cast<uint64_t>(k.box_outer) << 23) ^ k.dt;
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+}  // namespace
+
 int tmap_encode_2d(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t inner, uint64_t outer,
                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  const TmapKey key{base, inner, outer, row_stride_bytes, box_inner, box_outer, static_cast<uint32_t>(dt)};
+  auto hit = cache.find(key);
+  if (hit != cache.end()) { *out = hit->second; return 0; }
+  const int rc = tmap_encode_2d_uncached(out, dt, base, inner, outer, row_stride_bytes, box_inner, box_outer);
+  if (rc == 0) {
+    if (cache.size() > 16384) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return rc;
+}
+
+int tmap_encode_2d_uncached(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t inner, uint64_t outer,
+                            uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn enc = get_encode();
   MV_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   const uint32_t esz = dt == TMAP_BF16 ? 2 : 4;

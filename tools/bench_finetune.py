@@ -23,12 +23,18 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 a = ap.parse_args()
-dev = torch.device("cuda:0")
+world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:       # one process per GPU (torchrun): gradients averaged over ranks as the reference's DistributedDataParallel does
+    torch.distributed.init_process_group("nccl", device_id=dev)
 B = a.batch
 args = types.SimpleNamespace(img_hidden_sz=2048, hidden_size=768, img_postion=True, img_encoding="fully_use_cnn", allow_random_trunk=True, len_vis_input=256,
                              img_size=512, max_len_b=253, precision="bf16", max_micro_batch=B, tasks="report_generation")
 torch.manual_seed(0)
 model = BertForPreTrainingLossMask(BertConfig.from_pretrained("bert-base-uncased"), args, len_vis_input=256).to(dev).train()
+if world > 1:
+    model.init_distributed()
 words = ["[PAD]"] + ["w%d" % i for i in range(1, 30522)]
 for tok, i in (("[UNK]", 100), ("[CLS]", 101), ("[SEP]", 102), ("[MASK]", 103)):
     words[i] = tok
@@ -36,8 +42,8 @@ stoi = {w: i for i, w in enumerate(words)}
 pipe = Preprocess4Seq2seq(args, 10, 0.15, words, lambda t: [stoi[x] for x in t], 512, False, mode="s2s", len_vis_input=256,
                           truncate_config={"max_len_b": 253, "trunc_seg": "b", "always_truncate_tail": False}, compact_mask=True,
                           image_loader=lambda p: None)
-random.seed(123)
-rng = np.random.RandomState(123)
+random.seed(123 + rank)
+rng = np.random.RandomState(123 + rank)
 rows = [pipe((None, [words[t] for t in rng.randint(999, 30522, size=rng.randint(16, 254))], None, None, None)) for _ in range(B)]
 col = lambda i: torch.tensor([r[i] for r in rows])
 input_ids, segment_ids, masked_ids, masked_pos, masked_w = col(0).to(dev), col(1).to(dev), col(3), col(4), col(5)
@@ -66,7 +72,17 @@ out = run(a.steps)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
-print(json.dumps({"metric": "report-generation fine-tune samples/sec", "value": B / (ms / 1e3), "unit": "samples/s", "n_gpus": 1,
-                  "ms_per_step": ms, "batch": B, "joint_len": 512, "max_pred": 10, "mask": "s2s (fine-tune variant)",
-                  "optimizer": "BertAdam (mv_bert_adam_step)", "encoder_tflops_dense": B * 2.8991e11 / (ms / 1e3) / 1e12,
+if world > 1:
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t)
+if rank == 0:
+  print(json.dumps({"metric": "report-generation fine-tune samples/sec", "value": B * world / (ms / 1e3), "unit": "samples/s", "n_gpus": world,
+                  "ms_per_step": ms, "batch_per_gpu": B, "joint_len": 512, "max_pred": 10, "mask": "s2s (fine-tune variant)",
+                  "optimizer": "BertAdam (mv_bert_adam_step)", "encoder_tflops_dense_per_gpu": B * 2.8991e11 / (ms / 1e3) / 1e12,
                   "last_loss": out["loss"], "dtype": "bf16", "data": "synthetic"}))
+if world > 1:
+    torch.cuda.synchronize()
+    torch.distributed.barrier()
+    model._cxrbert._release_engine()
+    torch.distributed.destroy_process_group()
