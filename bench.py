@@ -94,6 +94,17 @@ def _reference_modules_step_rate(steps, warmup, batch):
     from oracle import ref_shim
 
     ref_shim.REF_ROOT = os.environ["MEDVILL_REFERENCE"]
+    # the reference hard-codes .cuda() on a few index tensors (cxrbert_origin.py:92-95,115,117; image.py:60); this arm is
+    # the CPU path, so on a box WITH a GPU those calls are made no-ops for the duration of the timing and restored after
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        return _reference_modules_timed(steps, warmup, batch, ref_shim, orc, types, np, torch, nn)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+
+def _reference_modules_timed(steps, warmup, batch, ref_shim, orc, types, np, torch, nn):
     cxr, _ = ref_shim.load_reference_models()
     from transformers import BertConfig
 
