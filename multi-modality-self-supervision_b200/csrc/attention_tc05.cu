@@ -535,7 +535,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           tma_reduce_add_2d(&tmDQ, stg + TILE_BYTES, h * D + 32, row0 + prev * TQ);
         }
         tma_commit_group();
-        tma_wait_group<0>();
+        // only the staging buffer has to outlive the copy: wait until the bulk operation has READ shared memory, not until its
+        // global reduction has completed (~1-2 us; the grid's completion orders it before the next kernel as for every
+        // TMA-store epilogue)
+        tma_wait_group_read<0>();
       }
       __syncwarp();
     }
