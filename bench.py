@@ -359,10 +359,11 @@ def run_ours(args):
     # profiled step, dram__bytes_read.sum + dram__bytes_write.sum per launch; tools/summarize_launches.py --json)
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_step_traffic.json")) as f:
+        tr_name = next(n for n in ("r02_step_traffic.json", "r01_step_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", n)))
+        with open(os.path.join(ROOT, "profiles", tr_name)) as f:
             tr = json.load(f)["gemm_tc05"]
         traffic = tr["dram_bytes"] / tr["launches"]
-        traffic_src = "profiles/r01_step_traffic.json: %.1f GB over %d launches of one step (ncu)" % (tr["dram_bytes"] / 1e9, tr["launches"])
+        traffic_src = "profiles/%s: %.1f GB over %d launches of one step (ncu)" % (tr_name, tr["dram_bytes"] / 1e9, tr["launches"])
     except Exception:
         pass
     n_gemm = max(1, pcn[0] // 2)
