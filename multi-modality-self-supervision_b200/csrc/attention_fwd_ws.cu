@@ -113,6 +113,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
+  pdl_sync();
 
   auto decode = [&](int item) {
     Item it;
@@ -506,7 +507,7 @@ int attention_fwd_tc05(const AttnArgs& a, cudaStream_t s) {
   const int n_q = (a.L + TQ - 1) / TQ, n_qp = (n_q + 1) / 2;
   const int n_items = a.B * a.nh * n_qp;
   const int grid = n_items < device_sm_count() ? n_items : device_sm_count();
-  attn_fwd_ws_kernel<<<grid, kThreads, kWsSmem, s>>>(tm, a, n_items);
+  MV_CUDA_CHECK(launch_pdl(attn_fwd_ws_kernel, dim3(grid), dim3(kThreads), kWsSmem, s, tm, a, n_items));
   MV_LAUNCH_CHECK();
   return 0;
 }

@@ -298,6 +298,7 @@ attn_fwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnArgs a
 // delta[b,h,q] = sum_d dO[q,d] * O[q,d]   (one warp per row of the [B*L, H] activations)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O,
                                                          float* __restrict__ delta, int rows, int L, int nh) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int H = nh * D, b = warp / L, q = warp % L;
@@ -316,6 +317,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ dq_acc, bf16* __restrict__ dqkv,
                                                               long rows, int H) {
+  pdl_sync();
   const long n8 = rows * (H >> 3);
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const long r = i / (H >> 3);
@@ -330,6 +332,7 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 // Deterministic mode: dQ[b, q, :] = sum over the key tiles that can see query tile (q / 128), in ASCENDING key-tile order, of
 // the per-key-tile partials the backward CTAs stored — the same terms the fp32 reduce-adds would have summed in arrival order.
 __global__ void __launch_bounds__(256) attn_dq_sum_convert_kernel(const float* __restrict__ part, bf16* __restrict__ dqkv, AttnArgs a) {
+  pdl_sync();
   const int H = a.nh * D, L = a.L, n_kv = (L + TK - 1) / TK;
   const long rows = static_cast<long>(a.B) * L;
   const long n8 = rows * (H >> 3);
@@ -397,7 +400,6 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int L = a.L, H = a.nh * D, A = a.A;
-  const int mode = a.mode[b], tl = a.t_len[b];
   const int k_lo = kt * TK, k_hi = min(k_lo + TK - 1, L - 1);
   const int n_q = (L + TQ - 1) / TQ;
   const int row0 = b * L;
@@ -418,6 +420,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
+  pdl_sync();
+  const int mode = a.mode[b], tl = a.t_len[b];
 
   auto active = [&](int i) { return tile_any_allowed(mode, i * TQ, min(i * TQ + TQ - 1, L - 1), k_lo, k_hi, A, tl); };
   auto next_active = [&](int i) { ++i; while (i < n_q && !active(i)) ++i; return i; };
@@ -777,10 +781,11 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
                                                                              static_cast<int>(rows), a.L, a.nh);
   MV_LAUNCH_CHECK();
   dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
-  attn_bwd_tc05_kernel<<<grid, 544, kBwdSmem, s>>>(tmQKV, tmDO, tmDQ, tmDQP, a);
+  // (the delta kernel above follows a memset: launched with full stream ordering; it only triggers its dependents early)
+  MV_CUDA_CHECK(launch_pdl(attn_bwd_tc05_kernel, grid, dim3(544), kBwdSmem, s, tmQKV, tmDO, tmDQ, tmDQP, a));
   MV_LAUNCH_CHECK();
-  if (a.dq_part) attn_dq_sum_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_part, static_cast<bf16*>(a.dqkv), a);
-  else attn_dq_convert_kernel<<<148 * 4, 256, 0, s>>>(a.dq_acc, static_cast<bf16*>(a.dqkv), rows, H);
+  if (a.dq_part) MV_CUDA_CHECK(launch_pdl(attn_dq_sum_convert_kernel, dim3(148 * 4), dim3(256), 0, s, static_cast<const float*>(a.dq_part), static_cast<bf16*>(a.dqkv), a));
+  else MV_CUDA_CHECK(launch_pdl(attn_dq_convert_kernel, dim3(148 * 4), dim3(256), 0, s, static_cast<const float*>(a.dq_acc), static_cast<bf16*>(a.dqkv), rows, H));
   MV_LAUNCH_CHECK();
   return 0;
 }

@@ -56,6 +56,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long rows, int C, long rows_per_cta,
                                                        float* __restrict__ partial) {
   __shared__ float red[32][kBnCh][3];      // 24 KB
+  pdl_sync();
   const int ct = threadIdx.x & 7, rl = threadIdx.x >> 3;
   const int c0 = blockIdx.y * kBnCh + ct * 8;
   const long r0 = static_cast<long>(blockIdx.x) * rows_per_cta;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                            int update_running, float* __restrict__ scale_shift /* [2][C] */) {
   __shared__ float red[16][kBnCh][2];
   __shared__ float s_mean[kBnCh], s_n[kBnCh];
+  pdl_sync();
   const int ch = threadIdx.x & (kBnCh - 1), pl = threadIdx.x >> 6;
   const int c = blockIdx.x * kBnCh + ch;
   const float* base = partial + static_cast<long>(blockIdx.x) * nparts * kBnCh * 3;
@@ -175,6 +177,7 @@ __global__ void bn_eval_scale_kernel(int C, const float* gamma, const float* bet
 template <typename T>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ resid, T* __restrict__ y,
                                                        long n8, int C, const float* __restrict__ scale_shift, int relu) {
+  pdl_sync();
   const int c8 = C >> 3;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>(i % c8) * 8;
@@ -222,11 +225,11 @@ static int bn_launch_stats(const void* x, long rows, int C, const float* gamma, 
   const int cblocks = (C + kBnCh - 1) / kBnCh;
   const long rows_per_cta = (rows + nparts - 1) / nparts;
   dim3 grid(nparts, cblocks);
-  if (f32) bn_stats_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(x), rows, C, rows_per_cta, workspace);
-  else bn_stats_kernel<bf16><<<grid, 256, 0, s>>>(static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace);
+  if (f32) MV_CUDA_CHECK(launch_pdl(bn_stats_kernel<float>, grid, dim3(256), 0, s, static_cast<const float*>(x), rows, C, rows_per_cta, workspace));
+  else MV_CUDA_CHECK(launch_pdl(bn_stats_kernel<bf16>, grid, dim3(256), 0, s, static_cast<const bf16*>(x), rows, C, rows_per_cta, workspace));
   MV_LAUNCH_CHECK();
-  bn_finalize_kernel<<<cblocks, 1024, 0, s>>>(workspace, nparts, C, gamma, beta, running_mean, running_var, momentum, eps, 1,
-                                              scale_shift);
+  MV_CUDA_CHECK(launch_pdl(bn_finalize_kernel, dim3(cblocks), dim3(1024), 0, s, static_cast<const float*>(workspace), nparts, C, gamma, beta,
+                           running_mean, running_var, momentum, eps, 1, scale_shift));
   MV_LAUNCH_CHECK();
   return 0;
 }
@@ -248,10 +251,11 @@ int bn_forward(const void* x, const void* resid, void* y, long rows, int C, cons
   long blocks = (n8 + 255) / 256;
   const long cap = static_cast<long>(device_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  if (f32) bn_apply_kernel<float><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const float*>(x), static_cast<const float*>(resid),
-                                                                          static_cast<float*>(y), n8, C, scale_shift, relu);
-  else bn_apply_kernel<bf16><<<static_cast<int>(blocks), 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<const bf16*>(resid),
-                                                                      static_cast<bf16*>(y), n8, C, scale_shift, relu);
+  const dim3 agrid(static_cast<unsigned>(blocks));
+  if (f32) MV_CUDA_CHECK(launch_pdl(bn_apply_kernel<float>, agrid, dim3(256), 0, s, static_cast<const float*>(x), static_cast<const float*>(resid),
+                                    static_cast<float*>(y), n8, C, static_cast<const float*>(scale_shift), relu));
+  else MV_CUDA_CHECK(launch_pdl(bn_apply_kernel<bf16>, agrid, dim3(256), 0, s, static_cast<const bf16*>(x), static_cast<const bf16*>(resid),
+                                static_cast<bf16*>(y), n8, C, static_cast<const float*>(scale_shift), relu));
   MV_LAUNCH_CHECK();
   return 0;
 }

@@ -36,6 +36,32 @@ long launch_count();
     MV_CUDA_CHECK(cudaGetLastError());           \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ----
+// Kernels that begin with pdl_wait() may be launched with launch_pdl(): the grid is allowed to start (CTA launch, barrier /
+// TMEM / descriptor set-up) while the previous kernel of the stream is still draining, and blocks in pdl_wait() until that
+// kernel has completed and its writes are visible.  pdl_trigger() lets the NEXT kernel do the same with respect to this one.
+// Rule: a kernel launched through launch_pdl() executes pdl_wait() in every CTA before its first global-memory access (reads
+// AND writes: workspaces are reused).  Without the launch attribute both instructions are no-ops.  MV_PDL=0 disables it.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define MV_REQUIRE(cond, ...)          \
   do {                                 \
     if (!(cond)) {                     \

@@ -274,6 +274,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (TWO) cluster_sync_all();            // both CTAs' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_sync();                                       // everything above overlapped the previous kernel's tail
 
   const int tiles = p.m_tiles * p.n_tiles;          // pair mode: m_tiles counts 256-row tiles
   const int total_units = tiles * p.splits;   // see decode_unit for the order
@@ -688,14 +689,16 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
     cfg.blockDim = dim3(kThreadsEw, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MV_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmX, p));
   } else {
-    kern<<<grid, kThreadsEw, smem, stream>>>(tmA, tmB, tmC, tmX, p);
+    MV_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreadsEw), smem, stream, tmA, tmB, tmC, tmX, p));
   }
   MV_LAUNCH_CHECK();
   return 0;

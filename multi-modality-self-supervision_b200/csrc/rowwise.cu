@@ -140,6 +140,7 @@ template <typename TX, typename T>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const TX* __restrict__ x, T* __restrict__ y, float* __restrict__ y32,
                                                      const float* gamma, const float* beta, int rows, int H, float eps,
                                                      int drop_on, uint32_t site, DropoutCfg drop) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const int nch = H >> 3;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void raw_unpack(const Raw8<float>& r, float (&v)[8]) 
 }
 
 template <typename TX, typename T, int NC>
-__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy, const TX* __restrict__ x,
+__global__ void __launch_bounds__(256, 1) ln_bwd_kernel(const T* __restrict__ dy, const TX* __restrict__ x,
                                                         const float* __restrict__ gamma, T* __restrict__ dx,
                                                         T* __restrict__ dx_drop, float* dgamma, float* dbeta, float* dbias,
                                                         int rows, int H, float eps, int in_drop, int out_drop, uint32_t site,
@@ -222,8 +223,14 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy
   const int nch = H >> 3;
   const float inv_h = 1.f / static_cast<float>(H);
   float* my = red + static_cast<size_t>(warp) * 3 * H;
-  for (int i = lane; i < 3 * H; i += 32) my[i] = 0.f;
-  __syncwarp();
+  // column sums of this warp's rows live in registers (a lane owns the same 8-column chunks in every row); the r01 version
+  // kept them in shared memory and paid 36 LDS/STS per row per lane, the kernel's top stall (short scoreboard, 34 %)
+  float acc_g[NC][8], acc_b[NC][8], acc_bias[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_g[c][j] = acc_b[c][j] = acc_bias[c][j] = 0.f;
+  pdl_sync();
   const long stride = static_cast<long>(gridDim.x) * 8;
   long row = static_cast<long>(blockIdx.x) * 8 + warp;
   RawRow<TX, T, NC> cur;
@@ -279,32 +286,34 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const T* __restrict__ dy
     for (int c = 0; c < NC; ++c) {
       const int ch = lane + 32 * c;
       if (ch < nch) {
-        float g[8], ag[8], ab[8], o[8];
+        float g[8], o[8];
         load8<float>(gamma + ch * 8, g);
-        load8<float>(my + ch * 8, ag);
-        load8<float>(my + H + ch * 8, ab);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (xv[c][j] - mean) * rstd;
-          ag[j] = fmaf(dv[c][j], xh, ag[j]);
-          ab[j] += dv[c][j];
+          acc_g[c][j] = fmaf(dv[c][j], xh, acc_g[c][j]);
+          acc_b[c][j] += dv[c][j];
           o[j] = rstd * (dv[c][j] * g[j] - s1 - xh * s2);
         }
-        store8<float>(my + ch * 8, ag);
-        store8<float>(my + H + ch * 8, ab);
         store8<T>(dx + row * H + ch * 8, o);
         if (out_drop) {
           apply_dropout8(o, drop, site, row, H, ch * 8);
           store8<T>(dx_drop + row * H + ch * 8, o);
         }
         if (dbias) {
-          float acc[8];
-          load8<float>(my + 2 * H + ch * 8, acc);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += o[j];
-          store8<float>(my + 2 * H + ch * 8, acc);
+          for (int j = 0; j < 8; ++j) acc_bias[c][j] += o[j];
         }
       }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nch) {
+      store8<float>(my + ch * 8, acc_g[c]);
+      store8<float>(my + H + ch * 8, acc_b[c]);
+      store8<float>(my + 2 * H + ch * 8, acc_bias[c]);
     }
   }
   __syncthreads();
@@ -396,6 +405,7 @@ __global__ void __launch_bounds__(256) embed_bwd_scatter_kernel(const EmbedBwdAr
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ld, int rows, int cols, float* out) {
   __shared__ float red[8][256 + 8];
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -613,15 +623,16 @@ int ln_fwd(const void* x, void* y, const float* gamma, const float* beta, int ro
            uint32_t drop_site, const DropoutCfg& drop, int f32, cudaStream_t s, int x_f32, float* y32) {
   if (check_h(H)) return -1;
   if (rows <= 0) return 0;
+  const dim3 grid(rows_grid(rows)), block(256);
   if (f32) {
-    ln_fwd_kernel<float, float><<<rows_grid(rows), 256, 0, s>>>(static_cast<const float*>(x), static_cast<float*>(y), y32, gamma, beta,
-                                                                 rows, H, eps, drop_on, drop_site, drop);
+    MV_CUDA_CHECK(launch_pdl(ln_fwd_kernel<float, float>, grid, block, 0, s, static_cast<const float*>(x), static_cast<float*>(y), y32, gamma,
+                             beta, rows, H, eps, drop_on, drop_site, drop));
   } else if (x_f32) {
-    ln_fwd_kernel<float, bf16><<<rows_grid(rows), 256, 0, s>>>(static_cast<const float*>(x), static_cast<bf16*>(y), y32, gamma, beta,
-                                                                rows, H, eps, drop_on, drop_site, drop);
+    MV_CUDA_CHECK(launch_pdl(ln_fwd_kernel<float, bf16>, grid, block, 0, s, static_cast<const float*>(x), static_cast<bf16*>(y), y32, gamma,
+                             beta, rows, H, eps, drop_on, drop_site, drop));
   } else {
-    ln_fwd_kernel<bf16, bf16><<<rows_grid(rows), 256, 0, s>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), y32, gamma, beta, rows,
-                                                               H, eps, drop_on, drop_site, drop);
+    MV_CUDA_CHECK(launch_pdl(ln_fwd_kernel<bf16, bf16>, grid, block, 0, s, static_cast<const bf16*>(x), static_cast<bf16*>(y), y32, gamma,
+                             beta, rows, H, eps, drop_on, drop_site, drop));
   }
   MV_LAUNCH_CHECK();
   return 0;
@@ -636,9 +647,9 @@ static int ln_bwd_launch(const void* dy, const void* x, const float* gamma, void
     MV_CUDA_CHECK(cudaFuncSetAttribute(ln_bwd_kernel<TX, T, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
     attr = true;
   }
-  ln_bwd_kernel<TX, T, NC><<<grid, 256, smem, s>>>(static_cast<const T*>(dy), static_cast<const TX*>(x), gamma, static_cast<T*>(dx),
-                                                   static_cast<T*>(dx_drop), dgamma, dbeta, dbias, rows, H, eps, in_drop, out_drop,
-                                                   drop_site, drop, alt);
+  MV_CUDA_CHECK(launch_pdl(ln_bwd_kernel<TX, T, NC>, dim3(grid), dim3(256), smem, s, static_cast<const T*>(dy), static_cast<const TX*>(x),
+                           gamma, static_cast<T*>(dx), static_cast<T*>(dx_drop), dgamma, dbeta, dbias, rows, H, eps, in_drop, out_drop,
+                           drop_site, drop, alt));
   MV_LAUNCH_CHECK();
   return 0;
 }
@@ -652,7 +663,7 @@ int ln_bwd(const void* dy, const void* x, const float* gamma, void* dx, void* dx
   LnAltDrop alt;
   if (alt_in) alt = *alt_in; else { alt.period = 0; alt.lo = 0; alt.hi = 0; alt.drop = drop; }
   int grid = (rows + 7) / 8;
-  const int cap = device_sm_count() * 2;
+  const int cap = device_sm_count();          // one 8-warp CTA per SM: the row + the prefetched row + 72 column sums in registers
   if (grid > cap) grid = cap;
   const size_t smem = static_cast<size_t>(8) * 3 * H * sizeof(float);
   // H <= 768 (BERT-base): three 8-element chunks per lane, which keeps the whole row + the prefetched next row in registers
@@ -675,7 +686,8 @@ int colsum_add(const void* x, long ld, int rows, int cols, float* out, int f32, 
   int ysplit = (rows + 63) / 64;
   if (ysplit > 64) ysplit = 64;
   dim3 grid((cols + 255) / 256, ysplit);
-  MV_DISPATCH_T(f32, (colsum_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, rows, cols, out)));
+  if (f32) MV_CUDA_CHECK(launch_pdl(colsum_kernel<float>, grid, dim3(256), 0, s, static_cast<const float*>(x), ld, rows, cols, out));
+  else MV_CUDA_CHECK(launch_pdl(colsum_kernel<bf16>, grid, dim3(256), 0, s, static_cast<const bf16*>(x), ld, rows, cols, out));
   MV_LAUNCH_CHECK();
   return 0;
 }

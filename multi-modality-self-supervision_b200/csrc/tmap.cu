@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -119,6 +120,13 @@ int tmap_encode_3d(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t d0
 }
 
 static std::atomic<long> g_launches{0};
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MV_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
