@@ -33,7 +33,7 @@ extern "C" {
 #define MV_ABI_VERSION 4   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries
                               3: mv_batch.drop_worst_keep
                               4: mv_config.{attn_dropout_p, img_dropout_p, flags}; mv_gemm_desc.resid_f32;
-                                 mv_step_stats.error_flags; mv_backward_external, mv_itm_head_*, mv_colsum, mv_dgelu */
+                                 mv_step_stats.error_flags; mv_backward_external, mv_itm_head, mv_profile_read */
 
 enum { MV_PREC_BF16 = 0, MV_PREC_FP32 = 1 };          /* activation / GEMM-operand precision policy */
 enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3,      /* attention-mask modes */
