@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) attn_dq_sum_convert_kernel(const float* _
 }
 
 struct BwdSmem {
-  uint64_t bar_kv, bar_q[2], bar_s, bar_o, bar_pd, bar_stage;
+  uint64_t bar_kv, bar_q[2], bar_s[2], bar_h0, bar_o, bar_dvk, bar_pd, bar_stage, bar_qf;
   uint32_t tmem_base;
 };
 
@@ -374,19 +374,26 @@ __device__ __forceinline__ void store_pk16(uint8_t* sP, int r, int col, const ui
 // softmax-backward math, the dV / dK / dQ products, dQ staging (~7 000 cycles per query tile, of which ~2 600 are math:
 // profiles/r01_attn_timeline.txt) — are software pipelined across query tiles:
 //   * P / dS staging is double buffered, so the products of tile i (which read it) run under the math of tile i+1;
-//   * S / dP of tile i+1 are issued BEFORE the products of tile i, so they are ready when the math warps come around;
+//   * S / dP of tile i+1 are issued BEFORE the products of tile i, in two 64-key-column halves: every math warp works
+//     through its share of half 0 first and signals (bar_h0) once it holds those scores in registers, so half 0 of the NEXT
+//     tile is issued in the middle of this tile's math and is complete when the warps come around (r01 issued the whole
+//     next S / dP only after the math phase: 300 - 1 700 cycles of S wait per tile);
 //   * dQ of tile i is drained from TMEM at the end of tile i+1's math and staged in the (by then dead) P buffer of
 //     tile i; the issuer sends it off as one fp32 TMA reduce-add per 32-column half.
 // TMEM columns: S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448)
 // mbarriers (completion k belongs to the k-th ACTIVE query tile of this CTA, parity k & 1):
-//   bar_s      S / dP of tile k complete (tcgen05.commit)            math warps wait
+//   bar_s[h]   half h (key columns [64 h, 64 h + 64)) of S / dP of tile k complete (tcgen05.commit)   math warps wait
+//   bar_h0     every math thread has loaded its half-0 scores of tile k from TMEM    512 arrivals, issuer waits
 //   bar_pd     P / dS of tile k stored and dQ of tile k-1 staged     512 arrivals, issuer waits (one extra for the tail)
+//   bar_dvk    LAST tile only: its dV / dK products (issued after dQ, which then owns bar_o) complete    math warps wait
+//   bar_qf     dV / dK products of tile k (not the last) complete: its Q / dO buffer may be refilled    issuer waits
 //   bar_o      dV / dK / dQ products of tile k complete              math warps wait before draining dQ(k); issuer before
 //                                                                    re-using the Q / dO buffer
 //   bar_stage  the reduce-add of dQ(k) has read its staging          issuer arrives, math warps wait before tile k+2's stores
 __global__ void __launch_bounds__(544, 1)
 attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                     const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDQP, const AttnArgs a) {
+                     const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDQP,
+                     const __grid_constant__ CUtensorMap tmDKV, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   uint8_t* smem = smem_raw + pad;
@@ -411,8 +418,12 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQ);
     tma_prefetch_desc(&tmDQP);
+    tma_prefetch_desc(&tmDKV);
+    mbar_init(&sh->bar_dvk, 1);
+    mbar_init(&sh->bar_qf, 1);
     mbar_init(&sh->bar_kv, 1); mbar_init(&sh->bar_q[0], 1); mbar_init(&sh->bar_q[1], 1);
-    mbar_init(&sh->bar_s, 1); mbar_init(&sh->bar_o, 1); mbar_init(&sh->bar_pd, 512); mbar_init(&sh->bar_stage, 1);
+    mbar_init(&sh->bar_s[0], 1); mbar_init(&sh->bar_s[1], 1); mbar_init(&sh->bar_h0, 512);
+    mbar_init(&sh->bar_o, 1); mbar_init(&sh->bar_pd, 512); mbar_init(&sh->bar_stage, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&sh->tmem_base, 512); tmem_relinquish(); }
@@ -428,7 +439,7 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   int i = next_active(-1);
   const bool any = i < n_q;
 
-  constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);     // S, dP : K-major x K-major
+  constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK / 2, 0, 0); // S, dP : K-major x K-major, one 64-key half per issue
   constexpr uint32_t idesc_t = make_idesc_bf16(TK, D, 1, 1);      // dV, dK: P^T / dS^T (MN-major) x dO / Q (MN-major)
   constexpr uint32_t idesc_q = make_idesc_bf16(TQ, D, 0, 1);      // dQ    : dS (K-major) x K (MN-major)
 
@@ -439,16 +450,18 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       tma_load_2d(&tmQKV, &sh->bar_q[buf], sQ + buf * TILE_BYTES, h * D, row0 + qi * TQ);
       tma_load_2d(&tmDO, &sh->bar_q[buf], sdO + buf * TILE_BYTES, h * D, row0 + qi * TQ);
     };
-    auto issue_s_dp = [&](uint32_t buf) {
-      const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK), va = smem_u32(sV), da = smem_u32(sdO + buf * TILE_BYTES);
+    // half hf of S = Q K^T and dP = dO V^T for the query tile in buffer `buf`: key rows [64 hf, 64 hf + 64) of K / V
+    auto issue_s_dp = [&](uint32_t buf, uint32_t hf) {
+      const uint32_t qa = smem_u32(sQ + buf * TILE_BYTES), ka = smem_u32(sK) + hf * (TILE_BYTES / 2),
+                     va = smem_u32(sV) + hf * (TILE_BYTES / 2), da = smem_u32(sdO + buf * TILE_BYTES);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_bf16(tmem, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
+          umma_bf16(tmem + 64 * hf, make_smem_desc_sw128(qa + k * 32, 16, 1024), make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < D / 16; ++k)
-          umma_bf16(tmem + 128, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
-        umma_commit(&sh->bar_s);
+          umma_bf16(tmem + 128 + 64 * hf, make_smem_desc_sw128(da + k * 32, 16, 1024), make_smem_desc_sw128(va + k * 32, 16, 1024), idesc_s, k > 0);
+        umma_commit(&sh->bar_s[hf]);
       }
       __syncwarp();
     };
@@ -465,7 +478,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_wait(&sh->bar_kv, 0);
       mbar_wait(&sh->bar_q[0], 0);
       tc_fence_after();
-      issue_s_dp(0);
+      issue_s_dp(0, 0);
+      issue_s_dp(0, 1);
     }
     int prev = -1;
     uint32_t it = 0;
@@ -473,6 +487,12 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t buf = it & 1u;
       const int inn = in < n_q ? next_active(in) : n_q;
       TL_MARK();
+      if (in < n_q) {                             // mid-math of this tile: its half-0 scores are in registers -> next tile's half 0
+        mbar_wait(&sh->bar_q[buf ^ 1u], ((it + 1) >> 1) & 1u);
+        mbar_wait(&sh->bar_h0, it & 1u);
+        tc_fence_after();
+        issue_s_dp(buf ^ 1u, 0);
+      }
       mbar_wait(&sh->bar_pd, it & 1u);            // P / dS of this tile stored; dQ of the previous tile staged
       tc_fence_after();
       TL_MARK();
@@ -488,15 +508,25 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tma_commit_group();
       }
       __syncwarp();
-      if (in < n_q) {                             // next tile's S / dP first: ready when the math warps come around
-        mbar_wait(&sh->bar_q[buf ^ 1u], ((it + 1) >> 1) & 1u);
-        tc_fence_after();
-        issue_s_dp(buf ^ 1u);
+      if (in < n_q) issue_s_dp(buf ^ 1u, 1);      // next tile's second half before this tile's products
+      if (it > 0) {                               // the reduce-add has read its staging: tile it+1 may overwrite that buffer.
+        // Before the products: their 24 tcgen05.mma take ~2 000 cycles to issue (queue back-pressure), and the math warps of
+        // tile it+1 need this buffer ~1 500 cycles into their phase (ncu: 9 % of the kernel's samples sat in that wait)
+        if (lane == 0) { tma_wait_group_read<0>(); mbar_arrive(&sh->bar_stage); }
+        __syncwarp();
       }
       {
         const uint32_t pa = smem_u32(sPD + buf * 2 * P_BYTES), sa = pa + P_BYTES, qa = smem_u32(sQ + buf * TILE_BYTES),
                        ka = smem_u32(sK), da = smem_u32(sdO + buf * TILE_BYTES);
+        const bool last = in >= n_q;              // last tile: dQ first (its drain + reduce-add run under the dV / dK products)
         if (elect_one()) {
+          if (last) {
+#pragma unroll
+            for (int kk = 0; kk < TK / 16; ++kk)  // dQ[q,d] = sum_k dS[q,k] K[k,d]
+              umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                        make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+            umma_commit(&sh->bar_o);
+          }
 #pragma unroll
           for (int kk = 0; kk < TQ / 16; ++kk)  // dV[k,d] += sum_q P[q,k] dO[q,d]
             umma_bf16(tmem + 256, make_smem_desc_sw128(pa + kk * 2048, TILE_BYTES, 1024),
@@ -505,21 +535,22 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           for (int kk = 0; kk < TQ / 16; ++kk)  // dK[k,d] += sum_q dS[q,k] Q[q,d]
             umma_bf16(tmem + 320, make_smem_desc_sw128(sa + kk * 2048, TILE_BYTES, 1024),
                       make_smem_desc_sw128(qa + kk * 2048, 8192, 1024), idesc_t, (it > 0 || kk > 0));
+          if (last) {
+            umma_commit(&sh->bar_dvk);
+          } else {
+            umma_commit(&sh->bar_qf);             // Q / dO of this tile are free once dV / dK are done: dQ does not read them
 #pragma unroll
-          for (int kk = 0; kk < TK / 16; ++kk)  // dQ[q,d] = sum_k dS[q,k] K[k,d]
-            umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
-          umma_commit(&sh->bar_o);
+            for (int kk = 0; kk < TK / 16; ++kk)
+              umma_bf16(tmem + 384, make_smem_desc_sw128(sa + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                        make_smem_desc_sw128(ka + kk * 2048, 8192, 1024), idesc_q, kk > 0);
+            umma_commit(&sh->bar_o);
+          }
         }
         __syncwarp();
       }
-      if (it > 0) {                               // the reduce-add has read its staging: tile it+1 may overwrite that buffer
-        if (lane == 0) { tma_wait_group_read<0>(); mbar_arrive(&sh->bar_stage); }
-        __syncwarp();
-      }
       TL_MARK();
-      if (inn < n_q) {                            // Q / dO two tiles ahead: this buffer is free once the products are complete
-        mbar_wait(&sh->bar_o, it & 1u);
+      if (inn < n_q) {                            // Q / dO two tiles ahead: this buffer is free once dV / dK are complete
+        mbar_wait(&sh->bar_qf, it & 1u);
         if (lane == 0) load_q(inn, static_cast<int>(buf));
         __syncwarp();
       }
@@ -527,10 +558,10 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       i = in;
       in = inn;
     }
-    if (any) {                                    // tail: the last tile's dQ
-      mbar_wait(&sh->bar_pd, it & 1u);
+    if (any) {                                    // tail: the last tile's dQ (staged in the OTHER buffer: the last tile's own
+      mbar_wait(&sh->bar_pd, it & 1u);            // P / dS are still being read by its dV / dK products)
       if (lane == 0) {
-        uint8_t* stg = sPD + ((it - 1) & 1u) * 2 * P_BYTES;
+        uint8_t* stg = sPD + (it & 1u) * 2 * P_BYTES;
         if (a.dq_part) {
           tma_store_3d(&tmDQP, stg, h * D, prev * TQ, kt * a.B + b);
           tma_store_3d(&tmDQP, stg + TILE_BYTES, h * D + 32, prev * TQ, kt * a.B + b);
@@ -559,8 +590,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   auto row_stats = [&](int qi, float& lse2_o, float& delta_o) {
     const int qq = qi * TQ + r;
     const long st = (static_cast<long>(b) * a.nh + h) * L + (qq < L ? qq : 0);
-    lse2_o = qq < L ? a.lse[st] * kLog2e : 0.f;
-    delta_o = qq < L ? a.delta[st] : 0.f;
+    lse2_o = qq < L ? a.lse[st] : 0.f;               // natural-log LSE; the caller scales by log2(e) where it is consumed, so
+    delta_o = qq < L ? a.delta[st] : 0.f;            // that nothing depends on these loads until the next tile
   };
   auto drain_dq = [&](uint32_t buf) {
     // dQ tile (x 1/8) -> swizzled fp32 staging in the dead P buffer `buf`.  Rows past the sequence end hold exact zeros.
@@ -574,8 +605,8 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           make_float4(0.125f * __uint_as_float(v[e]), 0.125f * __uint_as_float(v[e + 1]), 0.125f * __uint_as_float(v[e + 2]),
                       0.125f * __uint_as_float(v[e + 3]));
   };
-  float lse2 = 0.f, delta = 0.f;
-  if (any) row_stats(i, lse2, delta);
+  float lse_raw = 0.f, delta = 0.f;
+  if (any) row_stats(i, lse_raw, delta);
   uint32_t it = 0;
 
   for (; i < n_q; ++it) {
@@ -586,8 +617,9 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int q_lo = i * TQ;
     const int q = q_lo + r;
     const bool q_ok = q < L;
-    float lse2_n = 0.f, delta_n = 0.f;
-    if (in < n_q) row_stats(in, lse2_n, delta_n);        // next tile's row statistics: latency hidden behind this tile
+    float lse_n = 0.f, delta_n = 0.f;
+    if (in < n_q) row_stats(in, lse_n, delta_n);         // next tile's row statistics: latency hidden behind this tile
+    const float lse2 = lse_raw * kLog2e;
     int m_lo, m_hi;
     mask_row_interval(mode, q_ok ? q : 0, A, tl, L, m_lo, m_hi);
     const bool full = tile_all_allowed(mode, q_lo, min(q_lo + TQ - 1, L - 1), k_lo, k_lo + TK - 1, A, tl) && (k_lo + TK <= L) &&
@@ -601,18 +633,25 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       w_hi = max(w_hi, __shfl_xor_sync(0xffffffffu, w_hi, o));
     }
     TL_MARK();
-    mbar_wait(&sh->bar_s, it & 1u);
-    tc_fence_after();
-    TL_MARK();
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
-      const int col = cq * 32 + c * 16;                  // column inside the 128-wide tile
+      const int col = c * 64 + cq * 16;                  // column inside the 128-wide tile: every warp takes half 0 first
       uint32_t pk[8], dk[8];
-      if (k_lo + col < w_hi && k_lo + col + 15 >= w_lo) {
+      mbar_wait(&sh->bar_s[c], it & 1u);
+      tc_fence_after();
+      if (c == 0) TL_MARK();
+      const bool seen = k_lo + col < w_hi && k_lo + col + 15 >= w_lo;
       uint32_t sv[16], dv[16];
-      tmem_ld16(t_lane + col, sv);
-      tmem_ld16(t_lane + 128 + col, dv);
-      tmem_ld_wait();
+      if (seen) {
+        tmem_ld16(t_lane + col, sv);
+        tmem_ld16(t_lane + 128 + col, dv);
+        tmem_ld_wait();
+      }
+      if (c == 0) {                                      // half 0 of S / dP may be overwritten by the next tile's
+        tc_fence_before();
+        mbar_arrive(&sh->bar_h0);
+      }
+      if (seen) {
       // Work saved per element: the softmax scale 1/8 of dS is folded into the dQ / dK epilogues, the dropout
       // keep-scale of P into the dV epilogue, and dropped entries are zeroed with integer ANDs on the keep bytes.
       float p[16];
@@ -679,26 +718,33 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mbar_arrive(&sh->bar_pd);
     TL_MARK();
     i = in;
-    lse2 = lse2_n;
+    lse_raw = lse_n;
     delta = delta_n;
   }
-  if (any) {           // tail: the last tile's dQ, then dV / dK
+  if (any) {           // tail: the last tile's dQ (its products were issued first), then dV / dK
     mbar_wait(&sh->bar_o, (it - 1) & 1u);
     tc_fence_after();
-    drain_dq((it - 1) & 1u);
+    TL_MARK();
+    // staged in the buffer the last tile does NOT use (its own P / dS are still being read by the dV / dK products); that
+    // buffer's previous occupant, dQ of tile it-2, must have been read by its reduce-add
+    if (it >= 2) mbar_wait(&sh->bar_stage, (it - 2) & 1u);
+    drain_dq(it & 1u);
     tc_fence_before();
     fence_proxy_async_smem();
     mbar_arrive(&sh->bar_pd);
+    TL_MARK();
+    mbar_wait(&sh->bar_dvk, 0);
+    tc_fence_after();
+    TL_MARK();
   }
 
-  // epilogue: dV, dK rows of this key tile.  tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only
-  // the stores are predicated on k < L.  `any` is uniform across the CTA (an unseen key tile gets exact zeros).
-  const int k = k_lo + r;
-  bf16* dk_dst = static_cast<bf16*>(a.dqkv) + (static_cast<long>(row0) + (k < L ? k : 0)) * 3 * H + H + h * D + cq * 16;
-  bf16* dv_dst = dk_dst + H;
+  // epilogue: dV, dK rows of this key tile -> bf16 -> swizzled staging (the dead dS half of the buffer the last tile does not
+  // use) -> one TMA store each.  The 3-D map [B][L][3H] clips key rows past the sequence end.  (r01 / early r02 stored
+  // straight from registers: 32 B per thread at a 4.6 KB row stride = one L1 transaction per lane, 4 500 cycles per CTA.)
+  // `any` is uniform across the CTA (an unseen key tile gets exact zeros).
+  uint8_t* stg_kv = sPD + (it & 1u) * 2 * P_BYTES + P_BYTES;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
-    bf16* dst = which == 0 ? dv_dst : dk_dst;
     uint32_t v[16];
     if (any) {
       tmem_ld16(t_lane + 256 + which * 64 + cq * 16, v);
@@ -707,19 +753,26 @@ attn_bwd_tc05_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] = 0u;
     }
-    if (k < L) {
-      // deferred factors: dropout keep-scale for dV (which == 0), softmax scale 1/8 for dK
-      const float fs = which == 0 ? (a.drop_on ? a.drop.scale : 1.f) : 0.125f;
+    // deferred factors: dropout keep-scale for dV (which == 0), softmax scale 1/8 for dK
+    const float fs = which == 0 ? (a.drop_on ? a.drop.scale : 1.f) : 0.125f;
+    uint8_t* tile = stg_kv + which * TILE_BYTES;
 #pragma unroll
-      for (int e = 0; e < 16; e += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(fs * __uint_as_float(v[e]), fs * __uint_as_float(v[e + 1]));
-        u.y = pack_bf16x2(fs * __uint_as_float(v[e + 2]), fs * __uint_as_float(v[e + 3]));
-        u.z = pack_bf16x2(fs * __uint_as_float(v[e + 4]), fs * __uint_as_float(v[e + 5]));
-        u.w = pack_bf16x2(fs * __uint_as_float(v[e + 6]), fs * __uint_as_float(v[e + 7]));
-        *reinterpret_cast<uint4*>(dst + e) = u;
-      }
+    for (int e = 0; e < 16; e += 8) {
+      uint4 u;
+      u.x = pack_bf16x2(fs * __uint_as_float(v[e]), fs * __uint_as_float(v[e + 1]));
+      u.y = pack_bf16x2(fs * __uint_as_float(v[e + 2]), fs * __uint_as_float(v[e + 3]));
+      u.z = pack_bf16x2(fs * __uint_as_float(v[e + 4]), fs * __uint_as_float(v[e + 5]));
+      u.w = pack_bf16x2(fs * __uint_as_float(v[e + 6]), fs * __uint_as_float(v[e + 7]));
+      *reinterpret_cast<uint4*>(tile + sw128_off(r, 2 * cq + (e >> 3))) = u;
     }
+  }
+  fence_proxy_async_smem();
+  asm volatile("bar.sync 1, 512;" ::: "memory");             // the 16 math warps (the issuer warp is not part of it)
+  if (tid == 0) {
+    tma_store_3d(&tmDKV, stg_kv, 2 * H + h * D, k_lo, b);                   // dV
+    tma_store_3d(&tmDKV, stg_kv + TILE_BYTES, H + h * D, k_lo, b);          // dK
+    tma_commit_group();
+    tma_wait_group_read<0>();
   }
   TL_MARK();
   tc_fence_before();
@@ -770,6 +823,10 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
                         static_cast<uint64_t>(a.L) * H * 4, 32, TQ, 1);
     if (rc) return rc;
   }
+  CUtensorMap tmDKV;   // dqkv as [B][L][3H] bf16, box 64 x 128 x 1: dV / dK tiles, key rows past a sample's end clipped
+  rc = tmap_encode_3d(&tmDKV, TMAP_BF16, a.dqkv, 3 * H, a.L, a.B, static_cast<uint64_t>(3 * H) * 2,
+                      static_cast<uint64_t>(a.L) * 3 * H * 2, D, TK, 1);
+  if (rc) return rc;
   static bool attr = false;
   if (!attr) {
     MV_CUDA_CHECK(cudaFuncSetAttribute(attn_bwd_tc05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
@@ -782,7 +839,7 @@ int attention_bwd_tc05(const AttnArgs& a, cudaStream_t s) {
   MV_LAUNCH_CHECK();
   dim3 grid((a.L + TK - 1) / TK, a.nh, a.B);
   // (the delta kernel above follows a memset: launched with full stream ordering; it only triggers its dependents early)
-  MV_CUDA_CHECK(launch_pdl(attn_bwd_tc05_kernel, grid, dim3(544), kBwdSmem, s, tmQKV, tmDO, tmDQ, tmDQP, a));
+  MV_CUDA_CHECK(launch_pdl(attn_bwd_tc05_kernel, grid, dim3(544), kBwdSmem, s, tmQKV, tmDO, tmDQ, tmDQP, tmDKV, a));
   MV_LAUNCH_CHECK();
   if (a.dq_part) MV_CUDA_CHECK(launch_pdl(attn_dq_sum_convert_kernel, dim3(148 * 4), dim3(256), 0, s, static_cast<const float*>(a.dq_part), static_cast<bf16*>(a.dqkv), a));
   else MV_CUDA_CHECK(launch_pdl(attn_dq_convert_kernel, dim3(148 * 4), dim3(256), 0, s, static_cast<const float*>(a.dq_acc), static_cast<bf16*>(a.dqkv), rows, H));
