@@ -116,19 +116,17 @@ int nccl_unique_id(uint8_t out[128]) {
 // assigned tiles on those SMs wait for the whole collective (GEMM time per step 13.6 -> 15.6 ms at 8 GPUs; 14.8 ms with
 // the reservation, profiles/r01_bench_n8.json).  447 MB of fp32 gradients per step need ~2 ms of NVLink time spread over
 // a 25 ms backward, so a few CTAs are plenty.  MEDVILL_COMM_CTAS=n sets the reservation AND caps this communicator at n
-// CTAs through ncclConfig_t.maxCTAs; unset, the reservation is 8 and NCCL keeps its own channel count (the measured
-// configuration -- an NCCL_MAX_CTAS exported by the launcher is honoured by NCCL itself either way).
-static int comm_ctas(bool* explicit_cap = nullptr) {
-  static int n = -1;
-  static bool from_env = false;
-  if (n < 0) {
-    const char* e = getenv("MEDVILL_COMM_CTAS");
-    from_env = e != nullptr && *e != 0;
-    n = from_env ? atoi(e) : 8;
-    if (n < 1) n = 1;
-    if (n > 32) n = 32;
-  }
-  if (explicit_cap) *explicit_cap = from_env;
+// CTAs through ncclConfig_t.maxCTAs.  Unset: up to 4 ranks the reservation is 8 and NCCL keeps its own channel count (the
+// configuration measured at 2 / 4 GPUs); from 8 ranks on both are 16 — the 8-GPU sweep profiles/r02_ctas_sweep_n8.jsonl:
+// cap = reservation 8 / 12 / 16 -> 0.934 / 0.947 / 0.954 of 8 x 1 GPU, uncapped with 8 reserved 0.936 (uncapped, NCCL's
+// CTAs spill onto the GEMMs' SMs: GEMM time 14.2 ms per step instead of 13.5; capped lower, the last bucket's tail grows).
+static int comm_ctas(int world, bool* explicit_cap = nullptr) {
+  const char* e = getenv("MEDVILL_COMM_CTAS");
+  const bool from_env = e != nullptr && *e != 0;
+  int n = from_env ? atoi(e) : (world >= 8 ? 16 : 8);
+  if (n < 1) n = 1;
+  if (n > 32) n = 32;
+  if (explicit_cap) *explicit_cap = from_env || world >= 8;
   return n;
 }
 
@@ -152,7 +150,7 @@ int engine_comm_init(Engine* e, const uint8_t id[128], int rank, int world) {
   memcpy(uid.b, id, 128);
   void* comm = nullptr;
   bool cap = false;
-  const int ctas = comm_ctas(&cap);
+  const int ctas = comm_ctas(world, &cap);
   int rc;
   if (cap && n->CommInitRankConfig) {
     constexpr int kUndef = INT_MIN;                                  // NCCL_CONFIG_UNDEF_INT
@@ -522,7 +520,7 @@ int Engine::bucket_done(size_t idx, int allreduce, cudaStream_t s) {
     MV_CUDA_CHECK(cudaEventRecord(ev_mid, comm_stream));
     mid_recorded = true;
   }
-  set_reserved_sms(comm_ctas());            // GEMMs launched from now on leave room for the collective's CTAs
+  set_reserved_sms(comm_ctas(world));       // GEMMs launched from now on leave room for the collective's CTAs
   return 0;
 }
 
