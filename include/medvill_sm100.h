@@ -30,10 +30,11 @@
 extern "C" {
 #endif
 
-#define MV_ABI_VERSION 4   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries
+#define MV_ABI_VERSION 5   /* 2: mv_batch grew the embedding-layout switches, global_counts and lab_weights; new entries
                               3: mv_batch.drop_worst_keep
                               4: mv_config.{attn_dropout_p, img_dropout_p, flags}; mv_gemm_desc.resid_f32;
-                                 mv_step_stats.error_flags; mv_backward_external, mv_itm_head, mv_profile_read */
+                                 mv_step_stats.error_flags; mv_backward_external, mv_itm_head, mv_profile_read
+                              5: mv_stem_conv_s2d */
 
 enum { MV_PREC_BF16 = 0, MV_PREC_FP32 = 1 };          /* activation / GEMM-operand precision policy */
 enum { MV_MODE_BIDIR = 0, MV_MODE_S2S = 1, MV_MODE_BAR = 2, MV_MODE_NONCROSS = 3,      /* attention-mask modes */
@@ -257,6 +258,12 @@ int mv_bn_relu_maxpool(const void* x, void* y, int32_t B, int32_t H, int32_t W, 
  * dw[2,H] += , db[2] += (fp32). */
 int mv_itm_head(const void* pooled, const float* w, const float* b, float* logits, int32_t B, int32_t H, const float* dlogits,
                 void* d_pooled, float* dw, float* db, int32_t precision, void* stream);
+/* Stem convolution of ImageEncoder_cnn (torchvision resnet50 conv1, 7x7 / stride 2 / pad 3, models/image.py:50-56) in its
+ * space-to-depth form: x [B, Hs, Ws, 16] bf16 channels-last as written by mv_normalize_u8_s2d (2x2 pixel blocks, zero border),
+ * w [O, 4, 4, 16] bf16 (the re-indexed 7x7 weights, one K-major row of 256 per output channel), y [B, Hs-3, Ws-3, O] bf16
+ * channels-last.  Runs as a tcgen05 GEMM whose A rows are overlapping 64-element windows of x read in place through a 4-D
+ * tensor map (no im2col copy).  (Ws - 3) % 128 == 0, O % 8 == 0. */
+int mv_stem_conv_s2d(const void* x, const void* w, void* y, int32_t B, int32_t Hs, int32_t Ws, int32_t O, void* stream);
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream);
 

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmedvill_sm100.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-ABI_VERSION = 4          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
+ABI_VERSION = 5          # must equal MV_ABI_VERSION of include/medvill_sm100.h (struct layouts below mirror that header)
 MV_PREC_BF16, MV_PREC_FP32 = 0, 1
 MODE_BIDIR, MODE_S2S, MODE_BAR, MODE_NONCROSS, MODE_S2S_FT, MODE_BAR_FT = 0, 1, 2, 3, 4, 5
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_BIAS_TANH, EPI_RESID, EPI_DGELU, EPI_BIAS_GELU_GRAD, EPI_MUL = range(9)
@@ -116,6 +116,7 @@ SYMBOLS = {
     "mv_normalize_u8_s2d": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _P]),
     "mv_bn_relu_maxpool": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _F, _F, _I, _P, _L, _I, _P]),
     "mv_itm_head": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "mv_stem_conv_s2d": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "mv_adamw": (_I, [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _I, _P]),
 }
 

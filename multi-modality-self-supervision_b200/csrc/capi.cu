@@ -364,6 +364,19 @@ int mv_itm_head(const void* pooled, const float* w, const float* b, float* logit
   return itm_head_fwd_bwd(a, precision == MV_PREC_FP32, S(stream));
 }
 
+int mv_stem_conv_s2d(const void* x, const void* w, void* y, int32_t B, int32_t Hs, int32_t Ws, int32_t O, void* stream) {
+  MV_REQUIRE(x && w && y && B > 0 && Hs > 3 && Ws > 3 && O > 0 && O % 8 == 0, "mv_stem_conv_s2d: bad arguments");
+  MV_REQUIRE((Ws - 3) % 128 == 0, "mv_stem_conv_s2d: output width %d must be a multiple of 128", Ws - 3);
+  GemmDesc d;
+  d.M = B * (Hs - 3) * (Ws - 3); d.N = O; d.K = 256;
+  d.A = x; d.lda = 64; d.a_mn = 0;
+  d.B = w; d.ldb = 256; d.b_mn = 0;
+  d.C = y; d.ldc = O; d.c_f32 = 0;
+  d.epi = EPI_NONE;
+  d.a_win = 1; d.win_b = B; d.win_ho = Hs - 3; d.win_wo = Ws - 3; d.win_hs = Hs; d.win_ws = Ws; d.win_c = 16;
+  return gemm_bf16_tc05(d, S(stream));
+}
+
 int mv_adamw(float* p, float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1, float beta2,
              float eps, float weight_decay, int32_t step, float grad_scale, int32_t zero_grad, void* stream) {
   AdamArgs a;

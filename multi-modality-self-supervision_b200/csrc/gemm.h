@@ -39,6 +39,12 @@ struct GemmDesc {
   int splitk = 0;                                       // 0 = auto (only used when accumulate=1)
   int pair = -1;                                        // CTA-pair (cta_group::2, 256-row tiles): -1 auto, 0 off, 1 on
   int bn = 0;                                           // N tile: 0 auto, else 128 / 192 / 256 (tests, tuning)
+  // Sliding-window A operand (tcgen05 path, a_mn = 0): row m = (b, y, x) of an output image [win_b, win_ho, win_wo]; k-block kb
+  // (64 elements) is the contiguous run of 64 input elements starting at pixel (y + kb, x) of the channels-last input
+  // A[win_b, win_hs, win_ws, win_c] (win_c channels per pixel: 64 / win_c pixels per run).  That is a convolution with a
+  // (K / 64) x (64 / win_c) window, stride 1, no padding, read in place through a 4-D tensor map whose pixel stride
+  // (win_c elements) is smaller than the 64-element box: no im2col copy.  M = win_b * win_ho * win_wo, win_wo % 128 == 0.
+  int a_win = 0, win_b = 0, win_ho = 0, win_wo = 0, win_hs = 0, win_ws = 0, win_c = 0;
 };
 
 // bf16 operands / fp32 accumulate in TMEM / bf16 or fp32 output. sm_100a only.

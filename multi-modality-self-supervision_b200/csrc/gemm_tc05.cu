@@ -35,6 +35,7 @@ struct GemmParams {
   const float* bias;
   int has_c2, has_in, accumulate;
   int drop_on; uint32_t drop_site; DropoutCfg drop;
+  int a_win, win_wo, win_ho;          // sliding-window A operand (gemm.h): output image width / height
 };
 
 struct Barriers {
@@ -301,7 +302,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (crank == 0) mbar_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
             const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
             if constexpr (!A_MN) {
-              tma_load_2d_pair(&tmA, fb, sA, kb * BK, m0);
+              if (p.a_win) {                        // row m0 = (b, y, x0): window row y + kb of sample b, pixels x0 .. x0 + 127
+                const int x0 = m0 % p.win_wo, yb = m0 / p.win_wo;
+                tma_load_4d_pair(&tmA, fb, sA, 0, x0, yb % p.win_ho + kb, yb / p.win_ho);
+              } else {
+                tma_load_2d_pair(&tmA, fb, sA, kb * BK, m0);
+              }
             } else {
 #pragma unroll
               for (int g = 0; g < BM / 64; ++g) tma_load_2d_pair(&tmA, fb, sA + g * 8192, m0 + g * 64, kb * BK);
@@ -315,7 +321,12 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
             if constexpr (!A_MN) {
-              tma_load_2d(&tmA, &bars->full[stage], sA, kb * BK, m0);
+              if (p.a_win) {
+                const int x0 = m0 % p.win_wo, yb = m0 / p.win_wo;
+                tma_load_4d(&tmA, &bars->full[stage], sA, 0, x0, yb % p.win_ho + kb, yb / p.win_ho);
+              } else {
+                tma_load_2d(&tmA, &bars->full[stage], sA, kb * BK, m0);
+              }
             } else {
 #pragma unroll
               for (int g = 0; g < BM / 64; ++g) tma_load_2d(&tmA, &bars->full[stage], sA + g * 8192, m0 + g * 64, kb * BK);
@@ -627,7 +638,12 @@ int launch(const GemmDesc& d, GemmParams p, cudaStream_t stream) {
   constexpr int BMT = TWO ? 2 * BM : BM;     // rows of one work unit
   CUtensorMap tmA, tmB, tmC, tmX;
   int rc;
-  if (!d.a_mn) rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.K, d.M, d.lda * 2, BK, BM);
+  if (d.a_win) {
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(d.win_wo), static_cast<uint64_t>(d.win_hs), static_cast<uint64_t>(d.win_b)};
+    const uint64_t str[3] = {static_cast<uint64_t>(d.win_c) * 2, static_cast<uint64_t>(d.win_ws) * d.win_c * 2,
+                             static_cast<uint64_t>(d.win_hs) * d.win_ws * d.win_c * 2};
+    rc = tmap_encode_4d(&tmA, TMAP_BF16, d.A, dims, str, BK, BM);
+  } else if (!d.a_mn) rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.K, d.M, d.lda * 2, BK, BM);
   else rc = tmap_encode_2d(&tmA, TMAP_BF16, d.A, d.M, d.K, d.lda * 2, 64, BK);
   if (rc) return rc;
   if (!d.b_mn) rc = tmap_encode_2d(&tmB, TMAP_BF16, d.B, d.K, d.N, d.ldb * 2, BK, BNL);
@@ -785,6 +801,13 @@ int gemm_bf16_tc05(const GemmDesc& d, cudaStream_t stream) {
   p.has_c2 = d.C2 != nullptr; p.accumulate = d.accumulate;
   p.has_in = (d.epi == EPI_BIAS_RESID || d.epi == EPI_RESID || d.epi == EPI_DGELU || d.epi == EPI_MUL) ? 1 : 0;
   p.drop_on = d.drop_on; p.drop_site = d.drop_site; p.drop = d.drop;
+  p.a_win = d.a_win; p.win_wo = d.win_wo; p.win_ho = d.win_ho;
+  if (d.a_win) {
+    MV_REQUIRE(!d.a_mn && !d.b_mn && !d.accumulate && d.win_c > 0 && 64 % d.win_c == 0 && (d.win_c * 2) % 16 == 0 && d.K % 64 == 0 &&
+                   d.win_wo % BM == 0 && d.win_ho + d.K / 64 - 1 <= d.win_hs && d.win_wo + 64 / d.win_c - 1 <= d.win_ws &&
+                   static_cast<long>(d.win_b) * d.win_ho * d.win_wo == d.M,
+               "gemm: sliding-window A needs a_mn = b_mn = 0, K %% 64 == 0, win_wo %% 128 == 0 and a window inside the input");
+  }
   bool pair = d.M > BM;                       // a single 128-row tile gains nothing from a partner SM
   if (pair_env() >= 0) pair = pair_env() != 0;
   if (d.pair >= 0) pair = d.pair != 0;

@@ -119,6 +119,26 @@ int tmap_encode_3d(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t d0
   return 0;
 }
 
+int tmap_encode_4d(CUtensorMap* out, TmapDtype dt, const void* base, const uint64_t dims_in[4], const uint64_t strides_bytes[3],
+                   uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  MV_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  const uint32_t esz = dt == TMAP_BF16 ? 2 : 4;
+  MV_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base %p not 16-byte aligned", base);
+  MV_REQUIRE(strides_bytes[0] % 16 == 0 && strides_bytes[1] % 16 == 0 && strides_bytes[2] % 16 == 0, "TMA strides not multiples of 16 B");
+  MV_REQUIRE(box0 * esz <= 128 && box1 <= 256, "TMA box too large");
+  cuuint64_t dims[4] = {dims_in[0], dims_in[1], dims_in[2], dims_in[3]};
+  cuuint64_t strides[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t box[4] = {box0, box1, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, dt == TMAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed: CUresult %d (strides %llu %llu %llu)", (int)r,
+             (unsigned long long)strides[0], (unsigned long long)strides[1], (unsigned long long)strides[2]);
+  return 0;
+}
+
 static std::atomic<long> g_launches{0};
 bool pdl_enabled() {
   static const bool on = [] {

@@ -17,5 +17,9 @@ int tmap_encode_2d(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t in
 // 3-D variant (attention: [batch*rows, heads.., cols] style views); strides in bytes for dims 1 and 2.
 int tmap_encode_3d(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
                    uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+// 4-D tiled map with caller-chosen strides (they may OVERLAP: the stem convolution reads 64-element windows that advance by
+// 16 elements per output pixel); box = box0 x box1 x 1 x 1
+int tmap_encode_4d(CUtensorMap* out, TmapDtype dt, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                   uint32_t box0, uint32_t box1);
 
 }  // namespace mv

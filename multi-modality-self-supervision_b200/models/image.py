@@ -32,6 +32,10 @@ class TrunkExecutor:
     # (12 channels, padded to 16) with re-indexed weights.  Same arithmetic (zero taps added), but a shape cuDNN's
     # tensor-core implicit GEMM handles well; the 3-channel strided form took 1.93 ms at B=64 (0.39 TB/s).
     STEM_S2D = os.environ.get("MEDVILL_STEM_S2D", "1") != "0"
+    # ... and that 4x4 / stride-1 convolution over 16 channels on the library's tcgen05 GEMM (mv_stem_conv_s2d: the A operand is
+    # the s2d image itself, read as overlapping 64-element windows through a 4-D tensor map) instead of cuDNN's implicit GEMM
+    # (0.72 ms at B = 64, 190 TFLOP/s): bf16 only, output width a multiple of 128.  MEDVILL_STEM_GEMM=0 goes back to cuDNN.
+    STEM_GEMM = os.environ.get("MEDVILL_STEM_GEMM", "1") != "0"
 
     def __init__(self, seq, act_dtype):
         self.seq, self.act_dtype = seq, act_dtype
@@ -155,8 +159,16 @@ class TrunkExecutor:
     def _run_layers(self, x, training):
         s = self.seq
         if self.STEM_S2D and "0.s2d" in self.w and x.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
-            y = F.conv2d(self._stem_s2d_input(x), self.w["0.s2d"], None, 1, 0)
-            x = y if y.is_contiguous(memory_format=torch.channels_last) else y.contiguous(memory_format=torch.channels_last)
+            xin = self._stem_s2d_input(x)
+            Bn, _, Hs, Ws = xin.shape
+            w2 = self.w["0.s2d"]
+            if self.STEM_GEMM and self.act_dtype == torch.bfloat16 and (Ws - 3) % 128 == 0 and w2.shape[0] % 8 == 0:
+                x = torch.empty((Bn, w2.shape[0], Hs - 3, Ws - 3), dtype=self.act_dtype, device=xin.device, memory_format=torch.channels_last)
+                _lib.check(_lib.lib().mv_stem_conv_s2d(_lib.ptr(xin), _lib.ptr(w2), _lib.ptr(x), Bn, Hs, Ws, w2.shape[0],
+                                                       _lib.stream_ptr(xin.device)), "mv_stem_conv_s2d")
+            else:
+                y = F.conv2d(xin, w2, None, 1, 0)
+                x = y if y.is_contiguous(memory_format=torch.channels_last) else y.contiguous(memory_format=torch.channels_last)
         else:
             if x.dtype == torch.uint8:
                 x = self._normalize_u8(x)

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libmedvill_sm100.so lacks %s" % s
     assert set(syms) == set(_lib.SYMBOLS), set(syms) ^ set(_lib.SYMBOLS)      # ctypes table mirrors the header
-    assert _lib.lib().mv_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.lib().mv_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_layout_matches_reference_parameter_count():

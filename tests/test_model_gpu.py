@@ -112,6 +112,31 @@ def test_stem_space_to_depth_equals_the_strided_convolution():
             assert (out.float().cpu() - ref).abs().max() <= tol * ref.abs().max()
 
 
+def test_stem_convolution_on_the_library_gemm_equals_cudnn():
+    """mv_stem_conv_s2d (sliding-window A operand of the tcgen05 GEMM, overlapping 4-D tensor-map strides) against
+    F.conv2d on the same space-to-depth input and re-indexed weights; includes an image pair so that the (b, y, x) decode
+    of the row index and the last rows / columns of every image are exercised."""
+    import torch.nn.functional as F
+
+    from medvill_b200 import _lib
+
+    torch.manual_seed(3)
+    for B, H in ((2, 256), (1, 512)):
+        Hs = H // 2 + 3
+        x = torch.randn(B, 16, Hs, Hs, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w = (torch.randn(64, 16, 4, 4, device="cuda") * 0.1).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = torch.empty(B, 64, Hs - 3, Hs - 3, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        _lib.check(_lib.lib().mv_stem_conv_s2d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), B, Hs, Hs, 64, _lib.stream_ptr(x.device)),
+                   "mv_stem_conv_s2d")
+        ref = F.conv2d(x.float(), w.float())
+        torch.cuda.synchronize()
+        err = float((y.float() - ref).abs().max() / ref.abs().max())
+        assert err <= 1e-2, (B, H, err)                       # bf16 output rounding of a 256-term fp32 sum
+        # every image / row / column position carries its own value: a wrong window decode cannot hide
+        for b, yy, xx in ((0, 0, 0), (B - 1, Hs - 4, Hs - 4), (B - 1, 0, Hs - 4), (0, Hs - 4, 0), (B - 1, 77, 130 % (Hs - 3))):
+            assert float((y[b, :, yy, xx].float() - ref[b, :, yy, xx]).abs().max()) <= 2e-2 * float(ref.abs().max())
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
 def test_stem_tail_bn_relu_maxpool_vs_torch(dtype, tol):
     from medvill_b200 import _lib
