@@ -437,12 +437,13 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+      const int nch = min(BN / 64, (p.N - n0 + 63) / 64);     // chunks that hold real columns (N may end inside the tile)
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c, ++cnt) {
+      for (int c = 0; c < nch; ++c, ++cnt) {
         const uint32_t buf = has_c2 ? 0u : (cnt & 1u);
         if (leader && lane == 0) {
           if (has_in) {
-            if (c + 1 < BN / 64) {
+            if (c + 1 < nch) {
               tma_wait_group_read<0>();
               issue_in(cnt + 1, m0, n0, c + 1);
             }
@@ -471,7 +472,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           stage_bf16_16(s1, lane, hf * 2 + sub, f);
           if (has_c2) stage_bf16_16(s2, lane, hf * 2 + sub, pre);
         }
-        if (c == BN / 64 - 1) {
+        if (c == nch - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -534,12 +535,14 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+      // chunks that hold real columns: N may end inside the tile (N = 64 of the stem convolution under BN = 128 drains half)
+      const int nch = min(NCHUNK, (p.N - n0 + CHUNK_COLS - 1) / CHUNK_COLS);
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c, ++cnt) {
+      for (int c = 0; c < nch; ++c, ++cnt) {
         const uint32_t buf = has_c2 ? 0u : (cnt & 1u);
         if (lane == 0) {
           if (has_in) {
-            if (c + 1 < NCHUNK) {
+            if (c + 1 < nch) {
               tma_wait_group_read<0>();              // the other buffer's last store has been read out
               issue_in(cnt + 1, m0, n0, c + 1);      // input tile of the next chunk
             }
@@ -582,7 +585,7 @@ gemm_tc05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           epilogue_apply(p, f, pre, in, row, n0 + c * 32, bias_cur);
           stage_f32(s1, lane, f);
         }
-        if (c == NCHUNK - 1) {
+        if (c == nch - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
